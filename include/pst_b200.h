@@ -1,0 +1,136 @@
+/* pst_b200.h -- C ABI of libpst_b200.so, the B200 (sm_100a) genotype hot path.
+ *
+ * The reference (PySnpTools) reaches its native code through nine symbols of the third-party
+ * `bed_reader` extension.  Each entry point below names the reference call site it
+ * replaces.  Conventions, identical for every function:
+ *   - plain pointers and sizes only; no ownership transfer; the caller frees what it allocated;
+ *   - return value 0 = success, non-zero = failure with the message in pstb_last_error()
+ *     (thread-local, valid until the next call on that thread);
+ *   - `d_` pointers are device (HBM) pointers of the current CUDA device, `h_` pointers are host
+ *     pointers; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions taking only `d_` pointers are asynchronous on `stream`; `_host` functions return
+ *     after the result is in the caller's host buffer;
+ *   - dtype codes: PSTB_F32 / PSTB_F64 / PSTB_I8; order codes: PSTB_ORDER_F (iid fastest) /
+ *     PSTB_ORDER_C (sid fastest).
+ *
+ * Packed genotype store in HBM: `d_packed` holds sid_count records of `ld` bytes each; record j is
+ * the PLINK SNP-major record of SNP j (ceil(iid_count/4) bytes, 4 genotypes per byte, least
+ * significant pair first; 3-byte file header stripped).  `ld >= ceil(iid_count/4)`; a 16-byte
+ * multiple enables the 128-bit load path (pstb_packed_ld gives the preferred value).
+ *
+ * Index selection on either axis: `idx` (uint32 device vector of `n` entries) or, when idx == NULL,
+ * the arithmetic progression start + k*step, k < n.  The host layer resolves negative / boolean /
+ * nested indexers (pysnptools/pstreader/_subset.py:55-142) before calling.
+ */
+#ifndef PST_B200_H
+#define PST_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PSTB_F32 = 0, PSTB_F64 = 1, PSTB_I8 = 2 };
+enum { PSTB_ORDER_F = 0, PSTB_ORDER_C = 1 };
+/* standardize modes */
+enum { PSTB_STD_NONE = 0, PSTB_STD_UNIT = 1, PSTB_STD_BETA = 2 };
+
+typedef struct pstb_axis {
+    const uint32_t* idx; /* device pointer or NULL */
+    int64_t start;       /* used when idx == NULL */
+    int64_t step;        /* used when idx == NULL */
+    int64_t n;           /* number of selected entries */
+} pstb_axis;
+
+/* ---- housekeeping ------------------------------------------------------------------------- */
+int pstb_version(void);
+const char* pstb_last_error(void);
+/* replaces bed_reader.get_num_threads (standardizer.py:110, util/__init__.py:335): the GPU path has
+ * no host thread pool; returns the SM count of the current device (0 if no device). */
+int pstb_sm_count(void);
+int64_t pstb_packed_ld(int64_t iid_count);
+/* number of this library's kernels launched by the calling process so far (bench.py "gpu_launches") */
+int64_t pstb_launch_count(void);
+
+/* ---- K1: decode  (replaces open_bed(...).read -> Rust read_f32/f64/i8; bed.py:337-343) ------ */
+int pstb_decode(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                pstb_axis iid, pstb_axis sid, int count_a1,
+                void* d_out, int dtype, int order, void* stream);
+
+/* ---- K2: fused decode + per-SNP statistics + standardize ------------------------------------
+ * replaces read (bed.py:337-343) followed by standardize_f32/f64 (standardizer.py:114,120) without
+ * materialising the raw matrix.  mode = PSTB_STD_UNIT | PSTB_STD_BETA (a, b = Beta parameters).
+ * use_stats == 0: d_stats[n_sid][2] (float64, C order: mean, std) is WRITTEN; use_stats != 0: it is
+ * READ (UnitTrained / BetaTrained; unittrained.py:47-70, betatrained.py:47-63).  d_out may be NULL to
+ * compute statistics only.  dtype is PSTB_F32 or PSTB_F64. */
+int pstb_decode_standardize(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                            pstb_axis iid, pstb_axis sid, int count_a1,
+                            int mode, double a, double b, int use_stats, double* d_stats,
+                            void* d_out, int dtype, int order, void* stream);
+
+/* ---- K2f: standardize an existing float matrix in place -------------------------------------
+ * replaces standardize_f32 / standardize_f64(snps, is_beta, a, b, apply_in_place, use_stats, stats,
+ * num_threads) (standardizer.py:109-121).  d_val is [n_iid, n_sid] in `order`; d_stats as above.
+ * d_work: device scratch of pstb_standardize_work_bytes(n_sid) bytes. */
+int64_t pstb_standardize_work_bytes(int64_t n_sid);
+int pstb_standardize(void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid,
+                     int mode, double a, double b, int apply_in_place, int use_stats, double* d_stats,
+                     void* d_work, void* stream);
+
+/* ---- gather: replaces subset_f64_f64 / subset_f32_f64 / subset_f32_f32 (util/__init__.py:341-375)
+ * out[i, j, k] = in[rows[i], cols[j], k] for 3-D [n, m, v] arrays, C or F contiguous each. */
+int pstb_subset(const void* d_in, int dtype_in, int order_in, int64_t n_in, int64_t m_in, int64_t v,
+                pstb_axis rows, pstb_axis cols, void* d_out, int dtype_out, int order_out, void* stream);
+
+/* ---- K0: pack  (replaces to_bed -> Rust write_f32/f64/i8; bed.py:300-314) --------------------
+ * d_val [n_iid, n_sid] (any dtype / order) -> d_packed (ld bytes per SNP).  *d_bad (int32 on device)
+ * is set non-zero when a value is not one of 0, 1, 2, NaN (-127 for int8). */
+int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int count_a1,
+              uint8_t* d_packed, int64_t ld, int32_t* d_bad, void* stream);
+
+/* ---- K3: kinship  K = X X^T on tcgen05 -------------------------------------------------------
+ * replaces the block loop of SnpReader._read_kernel (snpreader.py:651-655: read + standardize +
+ * val.dot(val.T) + `K +=`; snpdata.py:203-206).
+ *
+ * pstb_kernel_workspace_bytes: scratch needed for n_iid selected individuals and SNP chunks of
+ *   `chunk` SNPs (fp16 hi/lo operand planes + per-SNP tables).
+ * pstb_snp_kernel: K (float32, [n_iid, n_iid], ld = n_iid, both triangles filled) =
+ *   sum over the selected SNPs of x_j x_j^T, where x_j is the standardized column of SNP j.
+ *   accumulate != 0 adds to the existing lower triangle of d_K before mirroring (multi-call
+ *   streaming).  d_stats [n_sid][2] float64 is written (or read when use_stats).  The operands are
+ *   split fp16 hi/lo (3 MMA terms, fp32 accumulation in tensor memory): relative Frobenius error
+ *   vs float64 ~3e-7. */
+int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk);
+int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                    pstb_axis iid, pstb_axis sid, int count_a1,
+                    int mode, double a, double b, int use_stats, double* d_stats,
+                    float* d_K, int accumulate, int mirror,
+                    void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* Test/bench hook for the tensor-core stage alone: K_lower (+)= (hi+lo)(hi+lo)^T minus lo*lo^T, on
+ * fp16 planes [n_pad, k_pad] (row-major, k_pad % 64 == 0, n_pad % 128 == 0). */
+int pstb_syrk_planes(const void* d_hi, const void* d_lo, int64_t n, int64_t n_pad, int64_t k_pad,
+                     float* d_K, int64_t ldk, int accumulate, float out_scale, void* stream);
+/* mirror the lower triangle into the upper one (in place) */
+int pstb_mirror_lower(float* d_K, int64_t n, int64_t ldk, void* stream);
+/* float32 K -> float64 / float32 copy with optional scale (KernelData dtype contract, kernelreader.py:245-302) */
+int pstb_convert_kernel(const float* d_K, int64_t n, void* d_out, int dtype, double scale, void* stream);
+
+/* ---- host-buffer entry points (what a bed_reader-style binding calls with NumPy arrays) ------ */
+/* read_f32/f64/i8 equivalent: h_packed = file bytes after the 3-byte header (tight: ceil(iid_count/4)
+ * bytes per SNP); h_iid_idx / h_sid_idx: int64 host vectors or NULL (= all); h_out: caller-allocated
+ * [n_iid, n_sid] host array.  mode != PSTB_STD_NONE fuses the standardize (h_stats [n_sid][2] float64). */
+int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count,
+                   const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
+                   int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
+                   void* h_out, int dtype, int order);
+/* standardize_f32/f64 equivalent on a host array (H2D, K2f, D2H). */
+int pstb_standardize_host(void* h_val, int dtype, int order, int64_t n_iid, int64_t n_sid,
+                          int mode, double a, double b, int apply_in_place, int use_stats, double* h_stats);
+/* subset_* equivalent on host arrays. */
+int pstb_subset_host(const void* h_in, int dtype_in, int order_in, int64_t n_in, int64_t m_in, int64_t v,
+                     const int64_t* h_rows, int64_t n_rows, const int64_t* h_cols, int64_t n_cols,
+                     void* h_out, int dtype_out, int order_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PST_B200_H */

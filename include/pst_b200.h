@@ -50,6 +50,11 @@ int pstb_sm_count(void);
 int64_t pstb_packed_ld(int64_t iid_count);
 /* number of this library's kernels launched by the calling process so far (bench.py "gpu_launches") */
 int64_t pstb_launch_count(void);
+/* page-locked host memory for the `_host` entry points: buffers from here are copied to / from the GPU
+ * directly (asynchronously, overlapped with the kernels); ordinary pageable buffers work too but go
+ * through an internal pinned staging ring.  NULL on failure. */
+void* pstb_host_alloc(int64_t bytes);
+int pstb_host_free(void* p);
 
 /* ---- K1: decode  (replaces open_bed(...).read -> Rust read_f32/f64/i8; bed.py:337-343) ------ */
 int pstb_decode(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,

@@ -1,0 +1,304 @@
+// host_api.cu -- host-buffer entry points: what a bed_reader-style binding calls with NumPy arrays.
+//
+// pstb_read_host streams the selected SNP records through the GPU in chunks on two CUDA streams:
+// H2D of packed records (2 bits / genotype), the fused decode(+standardize) kernel, and D2H of the float
+// output overlap, so the call runs at the speed of the device->host link.  Pinned caller buffers
+// (pstb_host_alloc) are copied directly; pageable ones go through internal pinned staging.
+#include <cstring>
+#include <vector>
+#include "pstb_common.cuh"
+
+namespace pstb {
+int read_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+              int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
+              void* stream);
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool host = false;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        release();
+        if (n < 256) n = 256;
+        cudaError_t e = host ? cudaHostAlloc(&p, n, cudaHostAllocDefault) : cudaMalloc(&p, n);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            return fail("%s(%zu bytes) -> %s", host ? "cudaHostAlloc" : "cudaMalloc", n, cudaGetErrorString(e));
+        }
+        cap = n;
+        return 0;
+    }
+    void release() {
+        if (p) {
+            if (host) cudaFreeHost(p); else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostCtx {
+    int device = -1;
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    Buf d_packed[2], d_out[2], d_stats, d_idx, d_work, h_in[2], h_out[2];
+    HostCtx() {
+        for (int k = 0; k < 2; ++k) { h_in[k].host = true; h_out[k].host = true; }
+    }
+    int init() {
+        int dev = 0;
+        PSTB_CUDA(cudaGetDevice(&dev));
+        if (dev == device) return 0;
+        for (int k = 0; k < 2; ++k) {
+            d_packed[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release();
+            if (s[k]) cudaStreamDestroy(s[k]);
+            if (done[k]) cudaEventDestroy(done[k]);
+            PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
+            PSTB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        }
+        d_stats.release(); d_idx.release(); d_work.release();
+        device = dev;
+        return 0;
+    }
+};
+
+HostCtx& ctx() {
+    static thread_local HostCtx c;
+    return c;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+size_t esize_of(int dtype) { return dtype == PSTB_F64 ? 8 : (dtype == PSTB_F32 ? 4 : 1); }
+
+// host index vector -> device axis (arithmetic progressions stay implicit)
+int make_axis(const int64_t* h_idx, int64_t n, int64_t count, const char* name, Buf& d_idx, cudaStream_t st, pstb_axis* out,
+              std::vector<uint32_t>& scratch) {
+    out->idx = nullptr;
+    out->start = 0;
+    out->step = 1;
+    out->n = n;
+    if (!h_idx) {
+        out->n = count;
+        return 0;
+    }
+    for (int64_t k = 0; k < n; ++k)
+        if (h_idx[k] < 0 || h_idx[k] >= count) return fail("%s index %lld out of range [0, %lld)", name, (long long)h_idx[k], (long long)count);
+    if (n <= 1) {
+        out->start = n ? h_idx[0] : 0;
+        return 0;
+    }
+    const int64_t step = h_idx[1] - h_idx[0];
+    bool arith = step != 0;
+    for (int64_t k = 2; k < n && arith; ++k) arith = (h_idx[k] - h_idx[k - 1]) == step;
+    if (arith) {
+        out->start = h_idx[0];
+        out->step = step;
+        return 0;
+    }
+    scratch.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) scratch[(size_t)k] = (uint32_t)h_idx[k];
+    if (d_idx.ensure((size_t)n * sizeof(uint32_t))) return 1;
+    PSTB_CUDA(cudaMemcpyAsync(d_idx.p, scratch.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PSTB_CUDA(cudaStreamSynchronize(st));
+    out->idx = (const uint32_t*)d_idx.p;
+    return 0;
+}
+
+}  // namespace
+}  // namespace pstb
+
+using namespace pstb;
+
+extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
+                              int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
+                              int use_stats, double* h_stats, void* h_out, int dtype, int order) {
+    if (iid_count < 0 || sid_count < 0) return fail("negative iid_count / sid_count");
+    if (!h_iid_idx) n_iid = iid_count;
+    if (!h_sid_idx) n_sid = sid_count;
+    if (n_iid < 0 || n_sid < 0) return fail("negative selection length");
+    if (iid_count > 0xfffffff0LL) return fail("iid_count too large");
+    if (mode != PSTB_STD_NONE && !h_stats) return fail("h_stats is NULL");
+    if (n_sid > 0)
+        for (int64_t k = 0; h_sid_idx && k < n_sid; ++k)
+            if (h_sid_idx[k] < 0 || h_sid_idx[k] >= sid_count)
+                return fail("sid index %lld out of range [0, %lld)", (long long)h_sid_idx[k], (long long)sid_count);
+    HostCtx& c = ctx();
+    if (c.init()) return 1;
+    std::vector<uint32_t> scratch;
+    pstb_axis iid_ax;
+    if (make_axis(h_iid_idx, n_iid, iid_count, "iid", c.d_idx, c.s[0], &iid_ax, scratch)) return 1;
+    if (n_iid == 0 || n_sid == 0) return 0;
+    if (!h_packed || !h_out) return fail("NULL host buffer");
+
+    const size_t es = esize_of(dtype);
+    const int64_t rec = (iid_count + 3) / 4;
+    const int64_t ld = pstb_packed_ld(iid_count);
+    const size_t col_bytes = (size_t)n_iid * es;
+    const size_t target = (size_t)64 << 20;
+    int64_t chunk = (int64_t)(target / (col_bytes > (size_t)ld ? col_bytes : (size_t)ld));
+    if (chunk < 1) chunk = 1;
+    if (order == PSTB_ORDER_C && chunk < 64) chunk = 64;   // keep the strided D2H rows at >= 256 bytes
+    if (chunk > n_sid) chunk = n_sid;
+    const bool packed_pinned = is_pinned(h_packed), out_pinned = is_pinned(h_out);
+
+    const bool any_stats = mode != PSTB_STD_NONE;
+    if (any_stats) {
+        if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
+        if (use_stats) PSTB_CUDA(cudaMemcpy(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (c.d_packed[k].ensure((size_t)chunk * ld) || c.d_out[k].ensure((size_t)chunk * col_bytes)) return 1;
+        if (!out_pinned && c.h_out[k].ensure((size_t)chunk * col_bytes)) return 1;
+    }
+
+    struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[2];
+    auto finish = [&](int slot) -> int {
+        if (!pend[slot].active) return 0;
+        PSTB_CUDA(cudaEventSynchronize(c.done[slot]));
+        pend[slot].active = false;
+        if (out_pinned) return 0;
+        const int64_t b0 = pend[slot].b0, ns = pend[slot].ns;
+        const char* src = (const char*)c.h_out[slot].p;
+        if (order == PSTB_ORDER_F) {
+            memcpy((char*)h_out + (size_t)b0 * col_bytes, src, (size_t)ns * col_bytes);
+        } else {
+            for (int64_t i = 0; i < n_iid; ++i)
+                memcpy((char*)h_out + ((size_t)i * n_sid + b0) * es, src + (size_t)i * ns * es, (size_t)ns * es);
+        }
+        return 0;
+    };
+
+    int rc = 0;
+    int64_t nchunks = (n_sid + chunk - 1) / chunk;
+    for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
+        const int slot = (int)(ch & 1);
+        const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
+        if ((rc = finish(slot))) break;
+        cudaStream_t st = c.s[slot];
+        // ---- input records ----
+        bool contiguous = true;
+        const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
+        for (int64_t k = 1; h_sid_idx && k < ns && contiguous; ++k) contiguous = h_sid_idx[b0 + k] == j0 + k;
+        if (contiguous && packed_pinned) {
+            PSTB_CUDA(cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, h_packed + (size_t)j0 * rec, (size_t)rec, (size_t)rec,
+                                        (size_t)ns, cudaMemcpyHostToDevice, st));
+        } else {
+            if (c.h_in[slot].ensure((size_t)chunk * ld)) return 1;
+            char* stage = (char*)c.h_in[slot].p;
+            for (int64_t k = 0; k < ns; ++k) {
+                const int64_t j = h_sid_idx ? h_sid_idx[b0 + k] : b0 + k;
+                memcpy(stage + (size_t)k * ld, h_packed + (size_t)j * rec, (size_t)rec);
+            }
+            PSTB_CUDA(cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
+        }
+        // ---- kernel ----
+        pstb_axis sid_ax{nullptr, 0, 1, ns};
+        double* d_st = any_stats ? (double*)c.d_stats.p + 2 * b0 : nullptr;
+        rc = read_impl((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats, d_st,
+                       c.d_out[slot].p, dtype, order, st);
+        if (rc) break;
+        // ---- output ----
+        if (order == PSTB_ORDER_F) {
+            void* dst = out_pinned ? (void*)((char*)h_out + (size_t)b0 * col_bytes) : c.h_out[slot].p;
+            PSTB_CUDA(cudaMemcpyAsync(dst, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
+        } else if (out_pinned) {
+            PSTB_CUDA(cudaMemcpy2DAsync((char*)h_out + (size_t)b0 * es, (size_t)n_sid * es, c.d_out[slot].p, (size_t)ns * es,
+                                        (size_t)ns * es, (size_t)n_iid, cudaMemcpyDeviceToHost, st));
+        } else {
+            PSTB_CUDA(cudaMemcpyAsync(c.h_out[slot].p, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        PSTB_CUDA(cudaEventRecord(c.done[slot], st));
+        pend[slot].b0 = b0;
+        pend[slot].ns = ns;
+        pend[slot].active = true;
+    }
+    for (int k = 0; k < 2; ++k) {
+        int r2 = finish(k);
+        if (!rc) rc = r2;
+    }
+    if (rc) {
+        cudaDeviceSynchronize();
+        return rc;
+    }
+    if (any_stats && !use_stats)
+        PSTB_CUDA(cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pstb_standardize_host(void* h_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int mode, double a, double b,
+                                     int apply_in_place, int use_stats, double* h_stats) {
+    if (n_iid < 0 || n_sid < 0) return fail("negative shape");
+    if (dtype != PSTB_F32 && dtype != PSTB_F64) return fail("standardize needs float32 or float64");
+    if (n_sid == 0) return 0;
+    if (!h_stats) return fail("h_stats is NULL");
+    HostCtx& c = ctx();
+    if (c.init()) return 1;
+    const size_t es = esize_of(dtype);
+    cudaStream_t st = c.s[0];
+    if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
+    if (c.d_work.ensure((size_t)pstb_standardize_work_bytes(n_sid))) return 1;
+    if (use_stats) PSTB_CUDA(cudaMemcpyAsync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    // F order streams column blocks; C order needs the whole matrix resident
+    const size_t col_bytes = (size_t)n_iid * es;
+    int64_t chunk = n_sid;
+    if (order == PSTB_ORDER_F && col_bytes > 0) {
+        chunk = (int64_t)(((size_t)256 << 20) / col_bytes);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_sid) chunk = n_sid;
+    }
+    if (c.d_out[0].ensure((size_t)chunk * col_bytes + 16)) return 1;
+    for (int64_t b0 = 0; b0 < n_sid; b0 += chunk) {
+        const int64_t ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
+        char* hp = (char*)h_val + (order == PSTB_ORDER_F ? (size_t)b0 * col_bytes : 0);
+        const size_t bytes = (size_t)ns * col_bytes;
+        if (bytes) PSTB_CUDA(cudaMemcpyAsync(c.d_out[0].p, hp, bytes, cudaMemcpyHostToDevice, st));
+        if (pstb_standardize(c.d_out[0].p, dtype, order, n_iid, ns, mode, a, b, apply_in_place, use_stats,
+                             (double*)c.d_stats.p + 2 * b0, c.d_work.p, st))
+            return 1;
+        if (apply_in_place && bytes) PSTB_CUDA(cudaMemcpyAsync(hp, c.d_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+        PSTB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (!use_stats) PSTB_CUDA(cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pstb_subset_host(const void* h_in, int dtype_in, int order_in, int64_t n_in, int64_t m_in, int64_t v,
+                                const int64_t* h_rows, int64_t n_rows, const int64_t* h_cols, int64_t n_cols, void* h_out,
+                                int dtype_out, int order_out) {
+    if (n_in < 0 || m_in < 0 || v < 0) return fail("negative shape");
+    HostCtx& c = ctx();
+    if (c.init()) return 1;
+    cudaStream_t st = c.s[0];
+    std::vector<uint32_t> scratch;
+    pstb_axis rows, cols;
+    Buf d_cols;
+    if (make_axis(h_rows, n_rows, n_in, "row", c.d_idx, st, &rows, scratch)) return 1;
+    int rc = make_axis(h_cols, n_cols, m_in, "col", d_cols, st, &cols, scratch);
+    if (!rc) {
+        const size_t in_bytes = (size_t)n_in * m_in * v * esize_of(dtype_in);
+        const size_t out_bytes = (size_t)rows.n * cols.n * v * esize_of(dtype_out);
+        if (out_bytes > 0) {
+            rc = c.d_out[0].ensure(in_bytes) || c.d_out[1].ensure(out_bytes);
+            if (!rc && cudaMemcpyAsync(c.d_out[0].p, h_in, in_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                rc = fail("H2D copy failed");
+            if (!rc) rc = pstb_subset(c.d_out[0].p, dtype_in, order_in, n_in, m_in, v, rows, cols, c.d_out[1].p, dtype_out, order_out, st);
+            if (!rc && cudaMemcpyAsync(h_out, c.d_out[1].p, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                rc = fail("D2H copy failed");
+            if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail("stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    d_cols.release();
+    return rc;
+}

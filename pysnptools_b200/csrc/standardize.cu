@@ -1,0 +1,310 @@
+// standardize.cu -- K2f (standardize an existing float matrix in place), gather (sub_matrix) and K0 (pack).
+//
+// K2f replaces bed_reader.standardize_f32 / standardize_f64 as called from
+// pysnptools/standardizer/standardizer.py:109-121; semantics follow the reference's python twins
+// (standardizer.py:135-163 Unit, :175-211 Beta): per SNP over non-NaN entries mean and population sd
+// (two-pass), sd == 0 -> inf, (x-mean)/sd or (x-mean)*BetaPDF(maf), NaN -> 0.
+// The gather replaces subset_f64_f64 / f32_f64 / f32_f32 (util/__init__.py:341-375), the packer replaces
+// to_bed's write_f32/f64/i8 (bed.py:300-314).
+#include "pstb_common.cuh"
+
+namespace pstb {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the whole CTA; every thread receives the result.  `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < nw; ++k) t += scratch[k];
+    return t;
+}
+
+// ---- F order: one CTA per SNP column --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_std_f(T* val, long long n_iid, long long n_sid, int mode, double a, double b,
+                                               double lnB, int apply, int use_stats, double* stats) {
+    __shared__ double scratch[32];
+    for (long long j = blockIdx.x; j < n_sid; j += gridDim.x) {
+        T* col = val + j * n_iid;
+        double mean, sd;
+        if (use_stats) {
+            mean = stats[2 * j];
+            sd = stats[2 * j + 1];
+        } else {
+            double s = 0.0, c = 0.0;
+            for (long long i = threadIdx.x; i < n_iid; i += blockDim.x) {
+                double x = (double)col[i];
+                if (x == x) { s += x; c += 1.0; }
+            }
+            s = block_sum(s, scratch);
+            c = block_sum(c, scratch);
+            mean = s / c;
+            double ss = 0.0;
+            for (long long i = threadIdx.x; i < n_iid; i += blockDim.x) {
+                double x = (double)col[i];
+                if (x == x) ss += (x - mean) * (x - mean);
+            }
+            ss = block_sum(ss, scratch);
+            sd = sqrt(ss / c);
+            if (sd == 0.0) sd = INFINITY;
+            if (threadIdx.x == 0) { stats[2 * j] = mean; stats[2 * j + 1] = sd; }
+        }
+        if (apply) {
+            const double f = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
+            for (long long i = threadIdx.x; i < n_iid; i += blockDim.x) {
+                double x = (double)col[i];
+                col[i] = (x != x) ? (T)0 : from_double<T>(std_value(mode, x, mean, sd, f));
+            }
+        }
+    }
+}
+
+// ---- C order: column sums with lanes along SNPs ---------------------------------------------------------
+// work layout (doubles): [0,m) sum  [m,2m) count  [2m,3m) sum of squared deviations  [3m,4m) mean  [4m,5m) sd  [5m,6m) factor
+template <typename T, int kPass>
+__global__ void __launch_bounds__(256) k_colacc_c(const T* val, long long n_iid, long long n_sid, long long rows_per_block,
+                                                  double* work) {
+    __shared__ double sh[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long j = (long long)blockIdx.x * 32 + tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(n_iid, r0 + rows_per_block);
+    double acc0 = 0.0, acc1 = 0.0;
+    if (j < n_sid) {
+        double mean = 0.0;
+        if (kPass == 1) mean = work[j] / work[n_sid + j];
+        for (long long i = r0 + ty; i < r1; i += 8) {
+            double x = (double)val[i * n_sid + j];
+            if (x == x) {
+                if (kPass == 0) { acc0 += x; acc1 += 1.0; }
+                else acc0 += (x - mean) * (x - mean);
+            }
+        }
+    }
+    sh[0][ty][tx] = acc0;
+    sh[1][ty][tx] = acc1;
+    __syncthreads();
+    if (ty == 0 && j < n_sid) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = 0; k < 8; ++k) { t0 += sh[0][k][tx]; t1 += sh[1][k][tx]; }
+        if (kPass == 0) { atomicAdd(work + j, t0); atomicAdd(work + n_sid + j, t1); }
+        else atomicAdd(work + 2 * n_sid + j, t0);
+    }
+}
+
+__global__ void k_finalize_c(long long n_sid, int mode, double a, double b, double lnB, int use_stats, double* stats, double* work) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sid) return;
+    double mean, sd;
+    if (use_stats) {
+        mean = stats[2 * j];
+        sd = stats[2 * j + 1];
+    } else {
+        const double c = work[n_sid + j];
+        mean = work[j] / c;
+        sd = sqrt(work[2 * n_sid + j] / c);
+        if (sd == 0.0) sd = INFINITY;
+        stats[2 * j] = mean;
+        stats[2 * j + 1] = sd;
+    }
+    work[3 * n_sid + j] = mean;
+    work[4 * n_sid + j] = sd;
+    work[5 * n_sid + j] = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_c(T* val, long long n_iid, long long n_sid, int mode, const double* work) {
+    const long long total = n_iid * n_sid;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e % n_sid;
+        double x = (double)val[e];
+        val[e] = (x != x) ? (T)0 : from_double<T>(std_value(mode, x, work[3 * n_sid + j], work[4 * n_sid + j], work[5 * n_sid + j]));
+    }
+}
+
+template <typename T>
+static int standardize_impl(T* d_val, int order, int64_t n_iid, int64_t n_sid, int mode, double a, double b, double lnB,
+                            int apply, int use_stats, double* d_stats, double* d_work, cudaStream_t st) {
+    const int sms = sm_count_cached();
+    if (order == PSTB_ORDER_F) {
+        long long grid = n_sid < (long long)sms * 8 ? n_sid : (long long)sms * 8;
+        k_std_f<T><<<(unsigned)grid, 256, 0, st>>>(d_val, n_iid, n_sid, mode, a, b, lnB, apply, use_stats, d_stats);
+        PSTB_AFTER_LAUNCH("k_std_f");
+        return 0;
+    }
+    if (!d_work) return fail("C-order standardize needs d_work (pstb_standardize_work_bytes)");
+    const unsigned gx = (unsigned)((n_sid + 31) / 32);
+    if (!use_stats) {
+        PSTB_CUDA(cudaMemsetAsync(d_work, 0, 3 * n_sid * sizeof(double), st));
+        long long splits = ((long long)sms * 8 + gx - 1) / gx;
+        if (splits < 1) splits = 1;
+        if (splits > 65535) splits = 65535;
+        long long rows_per_block = (n_iid + splits - 1) / splits;
+        if (rows_per_block < 8) rows_per_block = 8;
+        const unsigned gy = (unsigned)((n_iid + rows_per_block - 1) / rows_per_block);
+        k_colacc_c<T, 0><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
+        PSTB_AFTER_LAUNCH("k_colacc_c<0>");
+        k_colacc_c<T, 1><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
+        PSTB_AFTER_LAUNCH("k_colacc_c<1>");
+    }
+    k_finalize_c<<<(unsigned)((n_sid + 255) / 256), 256, 0, st>>>(n_sid, mode, a, b, lnB, use_stats, d_stats, d_work);
+    PSTB_AFTER_LAUNCH("k_finalize_c");
+    if (apply) {
+        long long total = n_iid * n_sid;
+        long long grid = (total + 255) / 256;
+        if (grid > (long long)sms * 16) grid = (long long)sms * 16;
+        k_apply_c<T><<<(unsigned)grid, 256, 0, st>>>(d_val, n_iid, n_sid, mode, d_work);
+        PSTB_AFTER_LAUNCH("k_apply_c");
+    }
+    return 0;
+}
+
+// ---- gather -------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_subset(const TI* in, long long si, long long sj, long long sk, Axis rows, Axis cols,
+                                                long long v, TO* out, int order_out, long long n_in, long long m_in) {
+    const long long n = rows.n, m = cols.n, total = n * m * v;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long i, j, k;
+        if (order_out == PSTB_ORDER_C) { k = e % v; j = (e / v) % m; i = e / (v * m); }
+        else { i = e % n; j = (e / n) % m; k = e / (n * m); }
+        long long r = rows.at(i), c = cols.at(j);
+        r = r < 0 ? 0 : (r >= n_in ? n_in - 1 : r);
+        c = c < 0 ? 0 : (c >= m_in ? m_in - 1 : c);
+        out[e] = (TO)in[r * si + c * sj + k * sk];
+    }
+}
+
+// ---- pack -----------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int code_of(T x, int count_a1, int* bad);
+template <>
+__device__ __forceinline__ int code_of<int8_t>(int8_t x, int count_a1, int* bad) {
+    if (x == 0) return count_a1 ? 3 : 0;
+    if (x == 1) return 2;
+    if (x == 2) return count_a1 ? 0 : 3;
+    if (x != -127) *bad = 1;
+    return 1;
+}
+template <typename T>
+__device__ __forceinline__ int code_of(T x, int count_a1, int* bad) {
+    if (x == (T)0) return count_a1 ? 3 : 0;
+    if (x == (T)1) return 2;
+    if (x == (T)2) return count_a1 ? 0 : 3;
+    if (x == x) *bad = 1;
+    return 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(const T* val, long long si, long long sj, long long n_iid, long long n_sid,
+                                              int count_a1, uint8_t* packed, long long ld, int32_t* d_bad) {
+    const long long rec = (n_iid + 3) / 4, total = rec * n_sid;
+    int bad = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e / rec, q = e % rec;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            long long i = 4 * q + t;
+            if (i < n_iid) byte |= (uint32_t)code_of<T>(val[i * si + j * sj], count_a1, &bad) << (2 * t);
+        }
+        packed[j * ld + q] = (uint8_t)byte;
+    }
+    if (bad && d_bad) *d_bad = 1;
+}
+
+}  // namespace pstb
+
+using namespace pstb;
+
+extern "C" int64_t pstb_standardize_work_bytes(int64_t n_sid) { return (int64_t)(6 * (n_sid > 0 ? n_sid : 1) * sizeof(double)); }
+
+extern "C" int pstb_standardize(void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int mode, double a, double b,
+                                int apply_in_place, int use_stats, double* d_stats, void* d_work, void* stream) {
+    if (n_iid < 0 || n_sid < 0) return fail("negative shape");
+    if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("mode must be PSTB_STD_UNIT or PSTB_STD_BETA");
+    if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
+    if (order != PSTB_ORDER_F && order != PSTB_ORDER_C) return fail("bad order");
+    if (n_sid == 0) return 0;
+    if (!d_stats) return fail("d_stats is NULL");
+    if (n_iid > 0 && !d_val) return fail("d_val is NULL");
+    const double lnB = (mode == PSTB_STD_BETA) ? lgamma(a) + lgamma(b) - lgamma(a + b) : 0.0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == PSTB_F32)
+        return standardize_impl<float>((float*)d_val, order, n_iid, n_sid, mode, a, b, lnB, apply_in_place, use_stats, d_stats,
+                                       (double*)d_work, st);
+    if (dtype == PSTB_F64)
+        return standardize_impl<double>((double*)d_val, order, n_iid, n_sid, mode, a, b, lnB, apply_in_place, use_stats, d_stats,
+                                        (double*)d_work, st);
+    return fail("standardize needs float32 or float64");
+}
+
+extern "C" int pstb_subset(const void* d_in, int dtype_in, int order_in, int64_t n_in, int64_t m_in, int64_t v, pstb_axis rows,
+                           pstb_axis cols, void* d_out, int dtype_out, int order_out, void* stream) {
+    if (n_in < 0 || m_in < 0 || v < 0 || rows.n < 0 || cols.n < 0) return fail("negative shape");
+    const long long total = (long long)rows.n * cols.n * v;
+    if (total == 0) return 0;
+    if (!d_in || !d_out) return fail("NULL array");
+    for (int ax = 0; ax < 2; ++ax) {
+        const pstb_axis& s = ax ? cols : rows;
+        const int64_t cnt = ax ? m_in : n_in;
+        if (!s.idx) {
+            int64_t last = s.start + (s.n - 1) * s.step;
+            if (s.start < 0 || s.start >= cnt || last < 0 || last >= cnt) return fail("subset selection out of range");
+        }
+    }
+    long long si, sj, sk;
+    if (order_in == PSTB_ORDER_C) { si = m_in * v; sj = v; sk = 1; }
+    else if (order_in == PSTB_ORDER_F) { si = 1; sj = n_in; sk = n_in * m_in; }
+    else return fail("bad order_in");
+    if (order_out != PSTB_ORDER_C && order_out != PSTB_ORDER_F) return fail("bad order_out");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)sm_count_cached() * 16;
+    if (grid > cap) grid = cap;
+    Axis r = to_axis(rows), c = to_axis(cols);
+    if (dtype_in == PSTB_F64 && dtype_out == PSTB_F64)
+        k_subset<double, double><<<(unsigned)grid, 256, 0, st>>>((const double*)d_in, si, sj, sk, r, c, v, (double*)d_out, order_out, n_in, m_in);
+    else if (dtype_in == PSTB_F32 && dtype_out == PSTB_F64)
+        k_subset<float, double><<<(unsigned)grid, 256, 0, st>>>((const float*)d_in, si, sj, sk, r, c, v, (double*)d_out, order_out, n_in, m_in);
+    else if (dtype_in == PSTB_F32 && dtype_out == PSTB_F32)
+        k_subset<float, float><<<(unsigned)grid, 256, 0, st>>>((const float*)d_in, si, sj, sk, r, c, v, (float*)d_out, order_out, n_in, m_in);
+    else if (dtype_in == PSTB_F64 && dtype_out == PSTB_F32)
+        k_subset<double, float><<<(unsigned)grid, 256, 0, st>>>((const double*)d_in, si, sj, sk, r, c, v, (float*)d_out, order_out, n_in, m_in);
+    else
+        return fail("subset supports float32 / float64");
+    PSTB_AFTER_LAUNCH("k_subset");
+    return 0;
+}
+
+extern "C" int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int count_a1, uint8_t* d_packed,
+                         int64_t ld, int32_t* d_bad, void* stream) {
+    if (n_iid < 0 || n_sid < 0) return fail("negative shape");
+    const long long rec = (n_iid + 3) / 4;
+    if (ld < rec) return fail("ld smaller than ceil(iid_count/4)");
+    if (rec * n_sid == 0) return 0;
+    if (!d_val || !d_packed) return fail("NULL array");
+    long long si, sj;
+    if (order == PSTB_ORDER_C) { si = n_sid; sj = 1; }
+    else if (order == PSTB_ORDER_F) { si = 1; sj = n_iid; }
+    else return fail("bad order");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long grid = (rec * n_sid + 255) / 256;
+    const long long cap = (long long)sm_count_cached() * 16;
+    if (grid > cap) grid = cap;
+    if (dtype == PSTB_F32) k_pack<float><<<(unsigned)grid, 256, 0, st>>>((const float*)d_val, si, sj, n_iid, n_sid, count_a1, d_packed, ld, d_bad);
+    else if (dtype == PSTB_F64) k_pack<double><<<(unsigned)grid, 256, 0, st>>>((const double*)d_val, si, sj, n_iid, n_sid, count_a1, d_packed, ld, d_bad);
+    else if (dtype == PSTB_I8) k_pack<int8_t><<<(unsigned)grid, 256, 0, st>>>((const int8_t*)d_val, si, sj, n_iid, n_sid, count_a1, d_packed, ld, d_bad);
+    else return fail("bad dtype");
+    PSTB_AFTER_LAUNCH("k_pack");
+    return 0;
+}

@@ -1,0 +1,256 @@
+"""Device-resident API: packed genotype store in HBM + the kernels of ``libpst_b200.so``.
+
+PyTorch is used only for device buffers and streams; every computation is a call through the C ABI.
+The NumPy-facing classes (:mod:`pysnptools_b200.snpreader` ...) are thin wrappers over this module.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Axis, lib, check
+
+BED_MAGIC = bytes([0x6C, 0x1B, 0x01])
+_DT = {np.dtype(np.float32): (_lib.F32, torch.float32), np.dtype(np.float64): (_lib.F64, torch.float64),
+       np.dtype(np.int8): (_lib.I8, torch.int8)}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _order_code(order):
+    if order in ("F", "A"):
+        return _lib.ORDER_F
+    if order == "C":
+        return _lib.ORDER_C
+    raise ValueError("order must be 'F', 'C' or 'A', not {0!r}".format(order))
+
+
+def _mode_args(standardizer_spec):
+    """(mode, a, b) from None | ('unit',) | ('beta', a, b)."""
+    if standardizer_spec is None:
+        return _lib.STD_NONE, 0.0, 0.0
+    if standardizer_spec[0] == "unit":
+        return _lib.STD_UNIT, float("nan"), float("nan")
+    if standardizer_spec[0] == "beta":
+        return _lib.STD_BETA, float(standardizer_spec[1]), float(standardizer_spec[2])
+    raise ValueError("unknown standardizer spec {0!r}".format(standardizer_spec))
+
+
+class Selection(object):
+    """One axis of a read: ``None`` (all), a slice, or an integer vector -> ``pstb_axis`` (+ keep-alive)."""
+
+    def __init__(self, sel, count, device):
+        self.count = int(count)
+        self.keep = None
+        if sel is None:
+            self.start, self.step, self.n = 0, 1, self.count
+            return
+        if isinstance(sel, slice):
+            r = range(self.count)[sel]
+            self.start, self.step, self.n = (r.start, r.step, len(r)) if len(r) else (0, 1, 0)
+            return
+        idx = np.asarray(sel)
+        if idx.dtype == bool:
+            idx = np.nonzero(idx)[0]
+        idx = idx.astype(np.int64).reshape(-1)
+        idx = np.where(idx < 0, idx + self.count, idx)
+        if idx.size and (idx.min() < 0 or idx.max() >= self.count):
+            raise IndexError("index out of range for axis of size {0}".format(self.count))
+        self.n = int(idx.size)
+        if self.n <= 1:
+            self.start, self.step = (int(idx[0]) if self.n else 0), 1
+            return
+        d = np.diff(idx)
+        if d[0] != 0 and np.all(d == d[0]):           # identity / range / constant stride stay implicit
+            self.start, self.step = int(idx[0]), int(d[0])
+            return
+        self.start, self.step = 0, 1
+        # int32 carries the same bits as the uint32 the C ABI reads (indices < 2**31)
+        self.keep = torch.from_numpy(idx.astype(np.int32)).to(device)
+
+    def axis(self):
+        return Axis(self.keep.data_ptr() if self.keep is not None else None, self.start, self.step, self.n)
+
+    def indices(self):
+        if self.keep is not None:
+            return self.keep.cpu().numpy().astype(np.int64)
+        return self.start + self.step * np.arange(self.n, dtype=np.int64)
+
+
+class PackedStore(object):
+    """SNP-major 2-bit records in HBM: uint8 tensor ``[sid_count, ld]`` with ``ld`` a 16-byte multiple."""
+
+    def __init__(self, tensor, iid_count, sid_count):
+        self.tensor, self.iid_count, self.sid_count = tensor, int(iid_count), int(sid_count)
+        self.ld = int(tensor.shape[1]) if tensor.dim() == 2 else int(lib.pstb_packed_ld(iid_count))
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+    @staticmethod
+    def from_host(packed, iid_count, device="cuda"):
+        """``packed``: uint8 ndarray ``[sid_count, ceil(iid_count/4)]`` (file bytes after the 3-byte header)."""
+        _lib.require_gpu()
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        sid_count, rec = packed.shape if packed.ndim == 2 else (0, 0)
+        assert rec == (iid_count + 3) // 4 or sid_count == 0
+        ld = int(lib.pstb_packed_ld(iid_count))
+        t = torch.zeros((sid_count, max(ld, 16)), dtype=torch.uint8, device=device)
+        if sid_count and rec:
+            t[:, :rec].copy_(torch.from_numpy(packed), non_blocking=False)
+        return PackedStore(t, iid_count, sid_count)
+
+    @staticmethod
+    def from_file(path, iid_count, sid_count, skip_format_check=False, device="cuda"):
+        rec = (int(iid_count) + 3) // 4
+        with open(path, "rb") as f:
+            head = f.read(3)
+            if not skip_format_check and head != BED_MAGIC:
+                raise ValueError("'{0}' is not a SNP-major PLINK .bed file (bad magic bytes)".format(path))
+            raw = np.fromfile(f, dtype=np.uint8)
+        if raw.size != sid_count * rec:
+            raise ValueError("'{0}': expected {1} genotype bytes for {2} x {3}, found {4}".format(
+                path, sid_count * rec, iid_count, sid_count, raw.size))
+        return PackedStore.from_host(raw.reshape(sid_count, rec), iid_count, device=device)
+
+
+def _alloc_out(n_iid, n_sid, dtype, order, device):
+    code, tdt = _DT[np.dtype(dtype)]
+    if _order_code(order) == _lib.ORDER_F:
+        base = torch.empty((n_sid, n_iid), dtype=tdt, device=device)
+        return code, base, base.t()
+    base = torch.empty((n_iid, n_sid), dtype=tdt, device=device)
+    return code, base, base
+
+
+def read(store, iid_sel=None, sid_sel=None, count_A1=False, dtype=np.float32, order="F", standardizer=None,
+         stats=None, want_out=True):
+    """Decode (and optionally standardize) a selection of the store on the GPU.
+
+    Returns ``(val, stats)``: ``val`` a CUDA tensor ``[n_iid, n_sid]`` with the requested memory order
+    (``None`` when ``want_out`` is False), ``stats`` a float64 CUDA tensor ``[n_sid, 2]`` (``None`` for a
+    plain decode).  ``stats`` given => applied as trained statistics (UnitTrained / BetaTrained).
+    """
+    _lib.require_gpu()
+    dev = store.device
+    isel = iid_sel if isinstance(iid_sel, Selection) else Selection(iid_sel, store.iid_count, dev)
+    ssel = sid_sel if isinstance(sid_sel, Selection) else Selection(sid_sel, store.sid_count, dev)
+    mode, a, b = _mode_args(standardizer)
+    with torch.cuda.device(dev):
+        code, base, view = _alloc_out(isel.n, ssel.n, dtype, order, dev) if want_out else (_DT[np.dtype(dtype)][0], None, None)
+        use_stats = 0
+        d_stats = None
+        if mode != _lib.STD_NONE:
+            if stats is not None:
+                d_stats = torch.as_tensor(np.asarray(stats, dtype=np.float64) if not torch.is_tensor(stats) else stats,
+                                          dtype=torch.float64, device=dev).contiguous()
+                assert tuple(d_stats.shape) == (ssel.n, 2), "stats must be [n_sid, 2]"
+                use_stats = 1
+            else:
+                d_stats = torch.empty((ssel.n, 2), dtype=torch.float64, device=dev)
+        check(lib.pstb_decode_standardize(
+            store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(), int(bool(count_A1)),
+            mode, a, b, use_stats, d_stats.data_ptr() if d_stats is not None else None,
+            base.data_ptr() if base is not None else None, code, _order_code(order), _stream()))
+    return view, d_stats
+
+
+def standardize(val, standardizer, stats=None, apply_in_place=True):
+    """In-place Unit / Beta standardize of a CUDA tensor ``[n_iid, n_sid]`` (C- or F-contiguous). Returns stats."""
+    _lib.require_gpu()
+    mode, a, b = _mode_args(standardizer)
+    n_iid, n_sid = val.shape
+    if val.is_contiguous():
+        order = _lib.ORDER_C
+    elif val.t().is_contiguous():
+        order = _lib.ORDER_F
+    else:
+        raise ValueError("val must be C- or F-contiguous")
+    code = {torch.float32: _lib.F32, torch.float64: _lib.F64}[val.dtype]
+    dev = val.device
+    with torch.cuda.device(dev):
+        use_stats = 0
+        if stats is not None:
+            d_stats = torch.as_tensor(stats, dtype=torch.float64, device=dev).contiguous().clone()
+            use_stats = 1
+        else:
+            d_stats = torch.empty((n_sid, 2), dtype=torch.float64, device=dev)
+        work = torch.empty(int(lib.pstb_standardize_work_bytes(n_sid)), dtype=torch.uint8, device=dev)
+        check(lib.pstb_standardize(val.data_ptr(), code, order, n_iid, n_sid, mode, a, b, int(bool(apply_in_place)), use_stats,
+                                   d_stats.data_ptr(), work.data_ptr(), _stream()))
+    return d_stats
+
+
+def pack(val, count_A1=False):
+    """CUDA tensor ``[n_iid, n_sid]`` of {0,1,2,NaN / -127} -> PackedStore. Raises ValueError on other values."""
+    _lib.require_gpu()
+    n_iid, n_sid = val.shape
+    if val.is_contiguous():
+        order = _lib.ORDER_C
+    elif val.t().is_contiguous():
+        order = _lib.ORDER_F
+    else:
+        val, order = val.contiguous(), _lib.ORDER_C
+    code = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.int8: _lib.I8}[val.dtype]
+    dev = val.device
+    with torch.cuda.device(dev):
+        ld = int(lib.pstb_packed_ld(n_iid))
+        out = torch.zeros((n_sid, max(ld, 16)), dtype=torch.uint8, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib.pstb_pack(val.data_ptr(), code, order, n_iid, n_sid, int(bool(count_A1)), out.data_ptr(), out.shape[1],
+                            bad.data_ptr(), _stream()))
+        if int(bad.item()) != 0:
+            raise ValueError("Attempt to write illegal value to .bed: values must be 0, 1, 2 or missing (NaN / -127)")
+    return PackedStore(out, n_iid, n_sid)
+
+
+def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
+               K=None, accumulate=False, mirror=True):
+    """``K = sum_j x_j x_j^T`` over the selected SNPs on tcgen05 tensor cores (float32 CUDA tensor [n, n]).
+
+    Returns ``(K, stats)``.  ``K`` given + ``accumulate`` => the partial sum is added (streaming / sharding).
+    """
+    _lib.require_gpu()
+    dev = store.device
+    isel = iid_sel if isinstance(iid_sel, Selection) else Selection(iid_sel, store.iid_count, dev)
+    ssel = sid_sel if isinstance(sid_sel, Selection) else Selection(sid_sel, store.sid_count, dev)
+    mode, a, b = _mode_args(standardizer)
+    n = isel.n
+    with torch.cuda.device(dev):
+        if K is None:
+            K = torch.zeros((n, n), dtype=torch.float32, device=dev)
+            accumulate = False
+        assert K.dtype == torch.float32 and K.is_contiguous() and tuple(K.shape) == (n, n)
+        use_stats = 0
+        if stats is not None:
+            d_stats = torch.as_tensor(stats, dtype=torch.float64, device=dev).contiguous()
+            use_stats = 1
+        else:
+            d_stats = torch.empty((ssel.n, 2), dtype=torch.float64, device=dev)
+        if chunk is None:
+            chunk = default_kernel_chunk(n, ssel.n)
+        wbytes = int(lib.pstb_kernel_workspace_bytes(n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(lib.pstb_snp_kernel(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
+                                  int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), K.data_ptr(),
+                                  int(bool(accumulate)), int(bool(mirror)), work.data_ptr(), wbytes, chunk, _stream()))
+    return K, d_stats
+
+
+def default_kernel_chunk(n_iid, n_sid):
+    """SNPs per operand-plane chunk: as large as ~6 GB of fp16 planes allows, a multiple of 64."""
+    per_snp = max(1, ((n_iid + 127) // 128) * 128) * 4          # hi + lo planes, 2 bytes each
+    chunk = max(64, min(16384, (6 << 30) // per_snp) // 64 * 64)
+    return int(min(chunk, max(64, (n_sid + 63) // 64 * 64)))
+
+
+def convert_kernel(K32, dtype=np.float64, scale=1.0):
+    """float32 K -> float32 / float64 CUDA tensor with an optional scalar factor (DiagKtoN)."""
+    n = K32.shape[0]
+    code, tdt = _DT[np.dtype(dtype)]
+    out = torch.empty((n, n), dtype=tdt, device=K32.device)
+    with torch.cuda.device(K32.device):
+        check(lib.pstb_convert_kernel(K32.data_ptr(), n, out.data_ptr(), code, float(scale), _stream()))
+    return out

@@ -33,6 +33,8 @@ struct ReadParams {
     unsigned raw_stride;    // shared-memory bytes per raw buffer
     unsigned group_smem;    // shared-memory bytes per group
     int nbuf;               // raw buffers per group (1 or 2)
+    int direct;             // record too large for shared memory: gather straight from global, in segments
+    long long seg_len;      // outputs per segment (multiple of 16) when direct
     int vec_ok;             // output columns are 16-byte aligned
 };
 
@@ -187,44 +189,64 @@ __global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p)
         mbar_expect_tx(&bars[buf], p.copy_bytes);
         bulk_g2s(raw0 + (size_t)buf * p.raw_stride, p.packed + j * p.ld, p.copy_bytes, &bars[buf]);
     };
-    if (p.bulk_ok && gid == 0 && b < p.sid.n) issue(b, 0);
+    if (p.bulk_ok && !p.direct && gid == 0 && b < p.sid.n) issue(b, 0);
 
     for (uint32_t it = 0; b < p.sid.n; b += ngroups, ++it) {
         const int cur = (p.nbuf == 2) ? (int)(it & 1u) : 0;
         const uint32_t parity = (p.nbuf == 2) ? ((it >> 1) & 1u) : (it & 1u);
         unsigned char* raw = raw0 + (size_t)cur * p.raw_stride;
         const long long nb = b + ngroups;
-        if (p.bulk_ok) {
+        const long long j = clampll(p.sid.at(b), p.sid_count);
+        const uint8_t* src = p.packed + j * p.ld;
+        if (p.direct) {
+            // nothing staged
+        } else if (p.bulk_ok) {
             if (p.nbuf == 2 && gid == 0 && nb < p.sid.n) issue(nb, cur ^ 1);
             mbar_wait(&bars[cur], parity);
         } else {
-            const long long j = clampll(p.sid.at(b), p.sid_count);
-            const uint8_t* src = p.packed + j * p.ld;
             for (unsigned i = gid; i < p.rec_bytes; i += gsize) raw[i] = __ldg(src + i);
             gsync();
         }
 
-        const unsigned char* rec;
-        if (!p.dense) {
-            // re-pack the selected individuals into a dense 2-bit record (output order)
-            const long long nbytes = (n_out + 3) >> 2;
+        // dense 2-bit record of outputs [seg0, seg0 + seg_n) in shared memory
+        auto prepare = [&](long long seg0, long long seg_n) -> const unsigned char* {
+            if (!p.direct && p.dense) return raw + p.byte_off;
+            const long long nbytes = (seg_n + 3) >> 2;
             for (long long q = gid; q < nbytes; q += gsize) {
                 uint32_t byte = 0;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     long long a = (q << 2) + t;
-                    if (a < n_out) {
-                        long long i = clampll(p.iid.at(a), p.iid_count);
-                        byte |= ((uint32_t)(raw[i >> 2] >> (2 * (i & 3))) & 3u) << (2 * t);
+                    if (a < seg_n) {
+                        long long i = p.dense ? p.iid.start + seg0 + a : clampll(p.iid.at(seg0 + a), p.iid_count);
+                        uint32_t rb = p.direct ? (uint32_t)__ldg(src + (i >> 2)) : (uint32_t)raw[i >> 2];
+                        byte |= ((rb >> (2 * (i & 3))) & 3u) << (2 * t);
                     }
                 }
                 dense[q] = (unsigned char)byte;
             }
             gsync();
-            rec = dense;
-        } else {
-            rec = raw + p.byte_off;
-        }
+            return dense;
+        };
+        auto count = [&](const unsigned char* rec, long long seg_n, unsigned int& c1, unsigned int& c2, unsigned int& c3) {
+            // exact dosage counts with popc over 16 genotypes per word
+            const uint32_t* rec32 = reinterpret_cast<const uint32_t*>(rec);
+            const long long nwords = (seg_n + 15) >> 4;
+            for (long long w = gid; w < nwords; w += gsize) {
+                uint32_t word = rec32[w];
+                if (w == nwords - 1) {
+                    unsigned rem = (unsigned)(seg_n & 15);
+                    if (rem) word &= (1u << (2 * rem)) - 1u;
+                }
+                uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
+                c1 += __popc(lo & ~hi);
+                c2 += __popc(hi & ~lo);
+                c3 += __popc(hi & lo);
+            }
+        };
+        const long long nseg = p.direct ? (n_out + p.seg_len - 1) / p.seg_len : 1;
+        const unsigned char* rec = nullptr;
+        if (nseg == 1) rec = prepare(0, n_out);
 
         double mean = 0.0, sd = 1.0;
         if (p.mode != PSTB_STD_NONE) {
@@ -232,20 +254,15 @@ __global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p)
                 mean = p.stats[2 * b];
                 sd = p.stats[2 * b + 1];
             } else {
-                // exact dosage counts with popc over 16 genotypes per word
-                const uint32_t* rec32 = reinterpret_cast<const uint32_t*>(rec);
-                const long long nwords = (n_out + 15) >> 4;
                 unsigned int c1 = 0, c2 = 0, c3 = 0;
-                for (long long w = gid; w < nwords; w += gsize) {
-                    uint32_t word = rec32[w];
-                    if (w == nwords - 1) {
-                        unsigned rem = (unsigned)(n_out & 15);
-                        if (rem) word &= (1u << (2 * rem)) - 1u;
+                if (nseg == 1) {
+                    count(rec, n_out, c1, c2, c3);
+                } else {
+                    for (long long sgi = 0; sgi < nseg; ++sgi) {
+                        const long long seg0 = sgi * p.seg_len, seg_n = min(p.seg_len, n_out - seg0);
+                        count(prepare(seg0, seg_n), seg_n, c1, c2, c3);
+                        gsync();
                     }
-                    uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
-                    c1 += __popc(lo & ~hi);
-                    c2 += __popc(hi & ~lo);
-                    c3 += __popc(hi & lo);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -255,6 +272,7 @@ __global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p)
                 }
                 if (kCta) {
                     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                    __syncthreads();
                     if ((threadIdx.x & 31) == 0) { red[0][w] = c1; red[1][w] = c2; red[2][w] = c3; }
                     __syncthreads();
                     c1 = c2 = c3 = 0;
@@ -270,10 +288,19 @@ __global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p)
         }
         if (p.out) {
             const Lut4<T> lut = make_code_lut<T>(p.mode, p.count_a1, p.a, p.b, p.lnB, mean, sd);
-            emit_column<T>(rec, reinterpret_cast<T*>(p.out) + b * p.out_ld, n_out, lut, p.vec_ok, gid, gsize);
+            T* o = reinterpret_cast<T*>(p.out) + b * p.out_ld;
+            if (nseg == 1) {
+                emit_column<T>(rec, o, n_out, lut, p.vec_ok, gid, gsize);
+            } else {
+                for (long long sgi = 0; sgi < nseg; ++sgi) {
+                    const long long seg0 = sgi * p.seg_len, seg_n = min(p.seg_len, n_out - seg0);
+                    emit_column<T>(prepare(seg0, seg_n), o + seg0, seg_n, lut, p.vec_ok, gid, gsize);
+                    gsync();
+                }
+            }
         }
         gsync();
-        if (p.bulk_ok && p.nbuf == 1 && gid == 0 && nb < p.sid.n) issue(nb, 0);
+        if (p.bulk_ok && !p.direct && p.nbuf == 1 && gid == 0 && nb < p.sid.n) issue(nb, 0);
     }
 }
 
@@ -402,8 +429,15 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     } else {
         p.nbuf = (16u + 2u * rec16 + dense_bytes <= max_smem / 2) ? 2 : 1;
         p.group_smem = 16u + (unsigned)p.nbuf * rec16 + dense_bytes;
-        if (p.group_smem > max_smem)
-            return fail("SNP record of %u bytes (+%u gather bytes) does not fit in shared memory", p.rec_bytes, dense_bytes);
+        if (p.group_smem > max_smem) {
+            // record (+ gather buffer) larger than shared memory: gather straight from global in segments
+            p.direct = 1;
+            p.nbuf = 0;
+            p.raw_stride = 0;
+            p.seg_len = 256 * 1024;                               // 64 KiB of 2-bit codes per segment
+            if (p.seg_len > ((n_out + 15) & ~15LL)) p.seg_len = (n_out + 15) & ~15LL;
+            p.group_smem = 16u + (unsigned)(p.seg_len / 4);
+        }
         int ctas_per_sm = (int)(max_smem / (p.group_smem + 1024u));
         if (ctas_per_sm > 4) ctas_per_sm = 4;
         if (ctas_per_sm < 1) ctas_per_sm = 1;

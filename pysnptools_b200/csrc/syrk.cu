@@ -1,8 +1,599 @@
-// placeholder until the tcgen05 kernel lands
+// syrk.cu -- K3: kinship K = X X^T on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the block loop of SnpReader._read_kernel (pysnptools/snpreader/snpreader.py:651-655: read +
+// standardize + val.dot(val.T) + `K +=`; GEMM call site snpdata.py:203-206).
+//
+// Per chunk of SNPs:
+//   1. per-SNP statistics from exact 2-bit counts (decode.cu, no output matrix);
+//   2. k_absmax: largest |standardized value| of the chunk -> one power-of-two scale so fp16 never overflows
+//      or loses small SNPs to subnormals;
+//   3. k_planes: decode + standardize + split every value x*scale into fp16 hi + fp16 lo and store the two
+//      operand planes [n_pad, k_pad] K-major (SNP index fastest) -- the only time X exists, as 4 bytes/genotype
+//      of scratch that is consumed from L2/HBM by TMA;
+//   4. k_syrk: persistent warp-specialised tcgen05 kernel over the lower-triangular 128x256 tiles:
+//      TMA (128B swizzle) -> 2-stage smem ring -> three MMAs per k-step (hi*hi + hi*lo + lo*hi; the dropped
+//      lo*lo term is 2^-22 relative) accumulating fp32 in tensor memory (two 256-column accumulators so the
+//      epilogue of tile t overlaps the MMAs of tile t+1) -> tcgen05.ld -> K (+)= acc / scale^2.
+//   5. k_mirror copies the lower triangle into the upper one.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <vector>
 #include "pstb_common.cuh"
+
+namespace pstb {
+int read_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+              int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
+              void* stream);
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;                      // 16 KiB  (one fp16 plane tile)
+constexpr int B_BYTES = BN * BK * 2;                      // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // hi + lo of both operands: 96 KiB
+constexpr int SYRK_SMEM = STAGES * STAGE_BYTES + 1024;    // + slack for the 1024-byte alignment of swizzled tiles
+constexpr int SYRK_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TMEM_COLS = 512;                            // two 128x256 fp32 accumulators
+constexpr int ROW_PAD = 256;                              // plane rows padded so every TMA box is in bounds
+constexpr int GROUP_I = 16, GROUP_J = 8;                  // tile rasterisation: 2048 x 2048 super-blocks stay L2 resident
+
+// scalars block in the workspace
+struct Scalars {
+    unsigned int absmax_bits;   // float bits of max |v| over the chunk (atomicMax on positive floats)
+    unsigned int pad[63];
+};
+
+__device__ __forceinline__ int scale_exponent(unsigned int absmax_bits) {
+    // scale = 2^(14 - e) with absmax < 2^e, clamped so 1/scale^2 stays a normal float
+    float m = __uint_as_float(absmax_bits);
+    int e = 14;
+    if (m > 0.0f && m < INFINITY) (void)frexpf(m, &e);
+    e = e < -45 ? -45 : (e > 60 ? 60 : e);
+    return 14 - e;
+}
+
+__global__ void k_absmax(const double* stats, long long ns, int mode, double a, double b, double lnB, Scalars* sc) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (s < ns) {
+        const double mean = stats[2 * s], sd = stats[2 * s + 1];
+        const double f = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
+        for (int g = 0; g < 3; ++g) {
+            double v = fabs(std_value(mode, (double)g, mean, sd, f));
+            if (v == v && v < 1e300) m = fmaxf(m, __double2float_ru(v));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&sc->absmax_bits, __float_as_uint(m));
+}
+
+// ---- operand planes --------------------------------------------------------------------------------------
+constexpr int PT_S = 64, PT_I = 256, PT_PITCH = PT_I / 4 + 2;   // 66-byte pitch: conflict-free for 2 SNPs per lane
+
+struct PlaneParams {
+    const uint8_t* packed;
+    long long ld, iid_count, sid_count;
+    Axis iid, sid;          // sid already offset to the chunk
+    int count_a1, mode;
+    double a, b, lnB;
+    const double* stats;    // [ns][2] of the chunk
+    const Scalars* sc;
+    __half* hi;
+    __half* lo;
+    long long n_pad, k_pad;
+    int dense;
+    long long byte_off;
+};
+
+__global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
+    __shared__ unsigned char codes[PT_S][PT_PITCH];
+    __shared__ __half lut_hi[PT_S][4], lut_lo[PT_S][4];
+    const long long tiles_i = p.n_pad / PT_I;
+    const long long ts = blockIdx.x / tiles_i, ti = blockIdx.x % tiles_i;
+    const long long b0 = ts * PT_S, i0 = ti * PT_I;
+    const long long n_out = p.iid.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int e = threadIdx.x; e < PT_S * (PT_I / 4); e += blockDim.x) {
+        const int s = e / (PT_I / 4), q = e % (PT_I / 4);
+        uint32_t byte = 0x55u;                                 // padding decodes as "missing" -> 0
+        if (b0 + s < p.sid.n && i0 + 4 * q < n_out) {
+            long long j = p.sid.at(b0 + s);
+            j = j < 0 ? 0 : (j >= p.sid_count ? p.sid_count - 1 : j);
+            const uint8_t* src = p.packed + j * p.ld;
+            if (p.dense && i0 + 4 * q + 3 < n_out) {
+                byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+            } else {
+                byte = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    long long a = i0 + 4 * q + t;
+                    uint32_t code = 1u;
+                    if (a < n_out) {
+                        long long i = p.iid.at(a);
+                        i = i < 0 ? 0 : (i >= p.iid_count ? p.iid_count - 1 : i);
+                        code = ((uint32_t)__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u;
+                    }
+                    byte |= code << (2 * t);
+                }
+            }
+        }
+        codes[s][q] = (unsigned char)byte;
+    }
+    if (threadIdx.x < PT_S) {
+        const int s = threadIdx.x;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};                     // by 2-bit code
+        if (b0 + s < p.sid.n) {
+            const double mean = p.stats[2 * (b0 + s)], sd = p.stats[2 * (b0 + s) + 1];
+            const double f = (p.mode == PSTB_STD_BETA) ? beta_factor(mean, p.a, p.b, p.lnB) : 0.0;
+            const double scale = ldexp(1.0, scale_exponent(p.sc->absmax_bits));
+            const double v0 = std_value(p.mode, 0.0, mean, sd, f) * scale, v1 = std_value(p.mode, 1.0, mean, sd, f) * scale,
+                         v2 = std_value(p.mode, 2.0, mean, sd, f) * scale;
+            v[0] = p.count_a1 ? v2 : v0;
+            v[2] = v1;
+            v[3] = p.count_a1 ? v0 : v2;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double x = v[c];
+            if (!(x == x) || fabs(x) > 60000.0) x = 0.0;        // NaN statistics (all-missing SNP) contribute nothing
+            const __half h = __float2half_rn((float)x);
+            lut_hi[s][c] = h;
+            lut_lo[s][c] = __float2half_rn((float)(x - (double)__half2float(h)));
+        }
+    }
+    __syncthreads();
+    // each lane owns SNPs 2*lane, 2*lane+1 of the tile; a warp writes 128 contiguous bytes per row and plane
+    __half2 h01[4], l01[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { h01[c] = __halves2half2(lut_hi[2 * lane][c], lut_hi[2 * lane + 1][c]); l01[c] = __halves2half2(lut_lo[2 * lane][c], lut_lo[2 * lane + 1][c]); }
+    const unsigned char* c0 = codes[2 * lane];
+    const unsigned char* c1 = codes[2 * lane + 1];
+    for (int r = warp; r < PT_I; r += 8) {
+        const uint32_t ca = ((uint32_t)c0[r >> 2] >> (2 * (r & 3))) & 3u, cb = ((uint32_t)c1[r >> 2] >> (2 * (r & 3))) & 3u;
+        // pick(low half from ca, high half from cb)
+        const __half2 ha = (ca & 2u) ? ((ca & 1u) ? h01[3] : h01[2]) : ((ca & 1u) ? h01[1] : h01[0]);
+        const __half2 hb = (cb & 2u) ? ((cb & 1u) ? h01[3] : h01[2]) : ((cb & 1u) ? h01[1] : h01[0]);
+        const __half2 la = (ca & 2u) ? ((ca & 1u) ? l01[3] : l01[2]) : ((ca & 1u) ? l01[1] : l01[0]);
+        const __half2 lb = (cb & 2u) ? ((cb & 1u) ? l01[3] : l01[2]) : ((cb & 1u) ? l01[1] : l01[0]);
+        const long long off = (i0 + r) * p.k_pad + b0 + 2 * lane;
+        *reinterpret_cast<__half2*>(p.hi + off) = __halves2half2(__low2half(ha), __high2half(hb));
+        *reinterpret_cast<__half2*>(p.lo + off) = __halves2half2(__low2half(la), __high2half(lb));
+    }
+}
+
+// ---- tcgen05 / TMA primitives ------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16, fp16 A/B (format 0), fp32 accumulate, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define PSTB_TMEM_LD32(taddr, v)                                                                                             \
+    asm volatile(                                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                            \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),        \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), \
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),             \
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                        \
+        : "r"(taddr)                                                                                                         \
+        : "memory")
+
+struct SyrkParams {
+    const int2* tiles;      // (I, J): rows [128 I, +128), columns [256 J, +256)
+    int ntiles, num_kb;
+    float* K;
+    long long n, ldk;
+    int accumulate;
+    const Scalars* sc;      // NULL -> out_scale is used as is
+    float out_scale;
+};
+
+__global__ void __launch_bounds__(SYRK_THREADS, 1)
+k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const SyrkParams p) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_hi);
+        prefetch_tmap(&map_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                const int2 tile = p.tiles[t];
+                const int row_a = tile.x * BM, row_b = tile.y * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1u);
+                    const uint32_t sb = tiles_base + stage * STAGE_BYTES;
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
+                    const int kc = kb * BK;
+                    tma_load_2d(sb, &map_hi, kc, row_a, full);
+                    tma_load_2d(sb + A_BYTES, &map_lo, kc, row_a, full);
+                    tma_load_2d(sb + 2 * A_BYTES, &map_hi, kc, row_b, full);
+                    tma_load_2d(sb + 2 * A_BYTES + A_BYTES, &map_hi, kc, row_b + 128, full);
+                    tma_load_2d(sb + 2 * A_BYTES + B_BYTES, &map_lo, kc, row_b, full);
+                    tma_load_2d(sb + 2 * A_BYTES + B_BYTES + A_BYTES, &map_lo, kc, row_b + 128, full);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tcount = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1u;
+                mbar_wait(&bar_tempty[acc], ((tcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = tiles_base + stage * STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + A_BYTES);
+                    const uint64_t b_hi = make_smem_desc(sb + 2 * A_BYTES), b_lo = make_smem_desc(sb + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 fp16 = 32 bytes along K inside the swizzle atom
+                        umma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                        umma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                    }
+                    tc_commit(smem_u32(&bar_empty[stage]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(smem_u32(&bar_tfull[acc]));
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> K =====
+        const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
+        float scale = p.out_scale;
+        if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
+        const bool vec = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tcount) {
+            const int2 tile = p.tiles[t];
+            const uint32_t acc = tcount & 1u;
+            mbar_wait(&bar_tfull[acc], (tcount >> 1) & 1u);
+            tc_fence_after();
+            const long long row = (long long)tile.x * BM + quad * 32 + lane;
+            const long long col0 = (long long)tile.y * BN;
+            const long long row_hi = (long long)tile.x * BM + quad * 32 + 31;   // last row of this warp
+            for (int c = 0; c < BN; c += 32) {
+                if (col0 + c > row_hi || col0 + c >= p.n) break;     // warp-uniform: nothing at or below the diagonal
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + acc * BN + c + ((uint32_t)(quad * 32) << 16);
+                PSTB_TMEM_LD32(taddr, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.n) {
+                    float* dst = p.K + row * p.ldk + col0 + c;
+                    if (vec && col0 + c + 32 <= p.n) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                                   __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+                            float4* d4 = reinterpret_cast<float4*>(dst) + q;
+                            if (p.accumulate) { float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                            *d4 = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            if (col0 + c + q < p.n) {
+                                float o = __uint_as_float(v[q]) * scale;
+                                if (p.accumulate) o += dst[q];
+                                dst[q] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long ldk) {
+    __shared__ float tile[32][33];
+    const long long bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = bi * 32 + r, j = bj * 32 + tx;
+        tile[r][tx] = (i < n && j < n) ? K[i * ldk + j] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long j = bj * 32 + r, i = bi * 32 + tx;     // writes K[j][i] = K[i][j] for j < i
+        if (i < n && j < n && j < i) K[j * ldk + i] = tile[tx][r];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_convert(const float* K, long long total, T* out, double scale) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        out[e] = (T)((double)K[e] * scale);
+}
+
+// ---- host helpers --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int make_plane_map(CUtensorMap* map, const void* plane, long long n_pad, long long k_pad) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {BK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(plane), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+// lower-triangular tile list, rasterised in GROUP_I x GROUP_J super-blocks so concurrently running CTAs share operand rows
+void build_tiles(long long n, std::vector<int2>& out) {
+    out.clear();
+    const int ti = (int)((n + BM - 1) / BM), tj = (int)((n + BN - 1) / BN);
+    for (int gi = 0; gi < ti; gi += GROUP_I)
+        for (int gj = 0; gj < tj; gj += GROUP_J)
+            for (int I = gi; I < gi + GROUP_I && I < ti; ++I)
+                for (int J = gj; J < gj + GROUP_J && J < tj; ++J)
+                    if ((long long)J * BN <= (long long)I * BM + BM - 1) out.push_back(make_int2(I, J));
+}
+
+struct TileCache {
+    long long n = -1;
+    int device = -1;
+    int2* d_tiles = nullptr;
+    int ntiles = 0;
+};
+
+int get_tiles(long long n, cudaStream_t st, const int2** d_tiles, int* ntiles) {
+    static thread_local TileCache c;
+    int dev = 0;
+    PSTB_CUDA(cudaGetDevice(&dev));
+    if (c.n != n || c.device != dev) {
+        std::vector<int2> tiles;
+        build_tiles(n, tiles);
+        PSTB_CUDA(cudaStreamSynchronize(st));
+        if (c.d_tiles) cudaFree(c.d_tiles);
+        c.d_tiles = nullptr;
+        c.n = -1;
+        PSTB_CUDA(cudaMalloc(&c.d_tiles, (tiles.size() + 1) * sizeof(int2)));
+        PSTB_CUDA(cudaMemcpy(c.d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        c.ntiles = (int)tiles.size();
+        c.n = n;
+        c.device = dev;
+    }
+    *d_tiles = c.d_tiles;
+    *ntiles = c.ntiles;
+    return 0;
+}
+
+long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad, long long k_pad, float* K, long long ldk,
+                int accumulate, const Scalars* sc, float out_scale, cudaStream_t st) {
+    if (n_pad % ROW_PAD || k_pad % BK || n_pad < n) return fail("planes must be padded to %d rows / %d columns", ROW_PAD, BK);
+    if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
+    CUtensorMap map_hi, map_lo;
+    if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
+    const int2* d_tiles = nullptr;
+    int ntiles = 0;
+    if (get_tiles(n, st, &d_tiles, &ntiles)) return 1;
+    SyrkParams p{};
+    p.tiles = d_tiles;
+    p.ntiles = ntiles;
+    p.num_kb = (int)(k_pad / BK);
+    p.K = K;
+    p.n = n;
+    p.ldk = ldk;
+    p.accumulate = accumulate;
+    p.sc = sc;
+    p.out_scale = out_scale;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
+        attr_set = true;
+    }
+    int grid = sm_count_cached();
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    k_syrk<<<grid, SYRK_THREADS, SYRK_SMEM, st>>>(map_hi, map_lo, p);
+    PSTB_AFTER_LAUNCH("k_syrk");
+    return 0;
+}
+
+}  // namespace
+}  // namespace pstb
+
 using namespace pstb;
-extern "C" int64_t pstb_kernel_workspace_bytes(int64_t, int64_t) { return 16; }
-extern "C" int pstb_snp_kernel(const uint8_t*, int64_t, int64_t, int64_t, pstb_axis, pstb_axis, int, int, double, double, int, double*, float*, int, int, void*, int64_t, int64_t, void*) { return fail("pstb_snp_kernel: not built"); }
-extern "C" int pstb_syrk_planes(const void*, const void*, int64_t, int64_t, int64_t, float*, int64_t, int, float, void*) { return fail("not built"); }
-extern "C" int pstb_mirror_lower(float*, int64_t, int64_t, void*) { return fail("not built"); }
-extern "C" int pstb_convert_kernel(const float*, int64_t, void*, int, double, void*) { return fail("not built"); }
+
+extern "C" int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk) {
+    if (n_iid < 0) n_iid = 0;
+    if (chunk < BK) chunk = BK;
+    const long long n_pad = round_up(n_iid > 0 ? n_iid : 1, ROW_PAD), k_pad = round_up(chunk, BK);
+    return (int64_t)(2 * n_pad * k_pad * 2 + 1024 + sizeof(Scalars));
+}
+
+extern "C" int pstb_syrk_planes(const void* d_hi, const void* d_lo, int64_t n, int64_t n_pad, int64_t k_pad, float* d_K,
+                                int64_t ldk, int accumulate, float out_scale, void* stream) {
+    if (n <= 0) return 0;
+    if (!d_hi || !d_lo || !d_K) return fail("NULL pointer");
+    if (ldk < n) return fail("ldk < n");
+    return launch_syrk((const __half*)d_hi, (const __half*)d_lo, n, n_pad, k_pad, d_K, ldk, accumulate, nullptr, out_scale,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pstb_mirror_lower(float* d_K, int64_t n, int64_t ldk, void* stream) {
+    if (n <= 0) return 0;
+    if (!d_K) return fail("NULL pointer");
+    const unsigned g = (unsigned)((n + 31) / 32);
+    k_mirror<<<dim3(g, g), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_K, n, ldk);
+    PSTB_AFTER_LAUNCH("k_mirror");
+    return 0;
+}
+
+extern "C" int pstb_convert_kernel(const float* d_K, int64_t n, void* d_out, int dtype, double scale, void* stream) {
+    if (n <= 0) return 0;
+    if (!d_K || !d_out) return fail("NULL pointer");
+    const long long total = (long long)n * n;
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)sm_count_cached() * 16;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == PSTB_F64) k_convert<double><<<(unsigned)grid, 256, 0, st>>>(d_K, total, (double*)d_out, scale);
+    else if (dtype == PSTB_F32) k_convert<float><<<(unsigned)grid, 256, 0, st>>>(d_K, total, (float*)d_out, scale);
+    else return fail("kernel dtype must be float32 or float64");
+    PSTB_AFTER_LAUNCH("k_convert");
+    return 0;
+}
+
+extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
+                               pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
+                               float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
+                               void* stream) {
+    if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
+    if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
+    if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
+    if (iid.n == 0) return 0;
+    if (!d_K) return fail("d_K is NULL");
+    if (sid.n > 0 && !d_stats) return fail("d_stats is NULL");
+    if (chunk < BK || chunk % BK) return fail("chunk must be a positive multiple of %d", BK);
+    if (work_bytes < pstb_kernel_workspace_bytes(iid.n, chunk) || !d_work) return fail("workspace too small (pstb_kernel_workspace_bytes)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long n = iid.n, n_pad = round_up(n, ROW_PAD);
+    if (sid.n == 0) {
+        if (!accumulate) PSTB_CUDA(cudaMemsetAsync(d_K, 0, (size_t)n * n * sizeof(float), st));
+        return 0;
+    }
+    const double lnB = (mode == PSTB_STD_BETA) ? lgamma(a) + lgamma(b) - lgamma(a + b) : 0.0;
+    const long long k_cap = round_up(chunk, BK);
+    char* w = reinterpret_cast<char*>(d_work);
+    w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(w) + 1023) & ~(uintptr_t)1023);
+    __half* hi = reinterpret_cast<__half*>(w);
+    __half* lo = hi + n_pad * k_cap;
+    Scalars* sc = reinterpret_cast<Scalars*>(lo + n_pad * k_cap);
+    const int dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
+    for (long long c0 = 0; c0 < sid.n; c0 += chunk) {
+        const long long ns = (c0 + chunk <= sid.n) ? chunk : sid.n - c0;
+        const long long k_pad = round_up(ns, BK);
+        pstb_axis sub = sid;
+        sub.n = ns;
+        if (sid.idx) sub.idx = sid.idx + c0; else sub.start = sid.start + c0 * sid.step;
+        double* st_chunk = d_stats + 2 * c0;
+        if (!use_stats) {
+            int rc = read_impl(d_packed, ld, iid_count, sid_count, iid, sub, count_a1, mode, a, b, 0, st_chunk, nullptr, PSTB_F32,
+                               PSTB_ORDER_F, stream);
+            if (rc) return rc;
+        }
+        PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+        k_absmax<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(st_chunk, ns, mode, a, b, lnB, sc);
+        PSTB_AFTER_LAUNCH("k_absmax");
+        PlaneParams pp{};
+        pp.packed = d_packed;
+        pp.ld = ld;
+        pp.iid_count = iid_count;
+        pp.sid_count = sid_count;
+        pp.iid = to_axis(iid);
+        pp.sid = to_axis(sub);
+        pp.count_a1 = count_a1 ? 1 : 0;
+        pp.mode = mode;
+        pp.a = a;
+        pp.b = b;
+        pp.lnB = lnB;
+        pp.stats = st_chunk;
+        pp.sc = sc;
+        pp.hi = hi;
+        pp.lo = lo;
+        pp.n_pad = n_pad;
+        pp.k_pad = k_pad;
+        pp.dense = dense;
+        pp.byte_off = dense ? iid.start / 4 : 0;
+        const long long ptiles = (k_pad / PT_S) * (n_pad / PT_I);
+        k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
+        PSTB_AFTER_LAUNCH("k_planes");
+        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st);
+        if (rc) return rc;
+    }
+    if (mirror) return pstb_mirror_lower(d_K, n, n, stream);
+    return 0;
+}

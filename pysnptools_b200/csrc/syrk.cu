@@ -12,8 +12,12 @@
 //      of scratch that is consumed from L2/HBM by TMA;
 //   4. k_syrk: persistent warp-specialised tcgen05 kernel over the lower-triangular 128x256 tiles:
 //      TMA (128B swizzle) -> 2-stage smem ring -> three MMAs per k-step (hi*hi + hi*lo + lo*hi; the dropped
-//      lo*lo term is 2^-22 relative) accumulating fp32 in tensor memory (two 256-column accumulators so the
-//      epilogue of tile t overlaps the MMAs of tile t+1) -> tcgen05.ld -> K (+)= acc / scale^2.
+//      lo*lo term is 2^-22 relative) accumulating fp32 in tensor memory.  The tensor core truncates (rounds
+//      toward zero) on every accumulate, which biases long positive sums (the diagonal of K) by about
+//      3e-8 per MMA; so TMEM only ever holds a short run (RUN_KB k-blocks), two 256-column accumulators
+//      alternate, and eight epilogue warps drain each finished run with tcgen05.ld into register-resident
+//      fp32 sums (round-to-nearest adds) while the next run is being multiplied.  One write of
+//      K (+)= sum / scale^2 per tile and chunk.
 //   5. k_mirror copies the lower triangle into the upper one.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -33,7 +37,8 @@ constexpr int A_BYTES = BM * BK * 2;                      // 16 KiB  (one fp16 p
 constexpr int B_BYTES = BN * BK * 2;                      // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // hi + lo of both operands: 96 KiB
 constexpr int SYRK_SMEM = STAGES * STAGE_BYTES + 1024;    // + slack for the 1024-byte alignment of swizzled tiles
-constexpr int SYRK_THREADS = 192;                         // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int SYRK_THREADS = 320;                         // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int RUN_KB = 4;                                 // k-blocks accumulated in TMEM before a drain (48 MMAs)
 constexpr int TMEM_COLS = 512;                            // two 128x256 fp32 accumulators
 constexpr int ROW_PAD = 256;                              // plane rows padded so every TMA box is in bounds
 constexpr int GROUP_I = 16, GROUP_J = 8;                  // tile rasterisation: 2048 x 2048 super-blocks stay L2 resident
@@ -236,7 +241,7 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 8); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -247,6 +252,7 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    const int num_runs = (p.num_kb + RUN_KB - 1) / RUN_KB;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -274,59 +280,80 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, tcount = 0;
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tcount) {
-                const uint32_t acc = tcount & 1u;
-                mbar_wait(&bar_tempty[acc], ((tcount >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(&bar_full[stage], phase);
+            uint32_t stage = 0, phase = 0, run = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                for (int r = 0; r < num_runs; ++r, ++run) {
+                    const uint32_t acc = run & 1u;
+                    mbar_wait(&bar_tempty[acc], ((run >> 1) & 1u) ^ 1u);
                     tc_fence_after();
-                    const uint32_t sb = tiles_base + stage * STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + A_BYTES);
-                    const uint64_t b_hi = make_smem_desc(sb + 2 * A_BYTES), b_lo = make_smem_desc(sb + 2 * A_BYTES + B_BYTES);
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const int kb_end = min(p.num_kb, (r + 1) * RUN_KB);
+                    for (int kb = r * RUN_KB; kb < kb_end; ++kb) {
+                        mbar_wait(&bar_full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sb = tiles_base + stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + A_BYTES);
+                        const uint64_t b_hi = make_smem_desc(sb + 2 * A_BYTES), b_lo = make_smem_desc(sb + 2 * A_BYTES + B_BYTES);
+                        const uint32_t first = (kb == r * RUN_KB) ? 0u : 1u;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 fp16 = 32 bytes along K inside the swizzle atom
-                        umma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                        umma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);   // 16 fp16 = 32 bytes along K inside the swizzle atom
+                            // small cross terms first: they are added while the accumulator is still small
+                            umma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, (k == 0) ? first : 1u);
+                            umma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, 1u);
+                            umma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                        }
+                        tc_commit(smem_u32(&bar_empty[stage]));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit(smem_u32(&bar_empty[stage]));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    tc_commit(smem_u32(&bar_tfull[acc]));
                 }
-                tc_commit(smem_u32(&bar_tfull[acc]));
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> K =====
+        // ===== epilogue: drain TMEM runs into registers, write K once per tile =====
         const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;                           // which 128 accumulator columns
         float scale = p.out_scale;
         if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
         const bool vec = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
-        uint32_t tcount = 0;
-        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++tcount) {
+        uint32_t run = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             const int2 tile = p.tiles[t];
-            const uint32_t acc = tcount & 1u;
-            mbar_wait(&bar_tfull[acc], (tcount >> 1) & 1u);
-            tc_fence_after();
+            float sum[128];
+#pragma unroll
+            for (int q = 0; q < 128; ++q) sum[q] = 0.0f;
+            for (int r = 0; r < num_runs; ++r, ++run) {
+                const uint32_t acc = run & 1u;
+                mbar_wait(&bar_tfull[acc], (run >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + acc * BN + half * 128 + c * 32 + ((uint32_t)(quad * 32) << 16);
+                    PSTB_TMEM_LD32(taddr, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) sum[c * 32 + q] += __uint_as_float(v[q]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            }
             const long long row = (long long)tile.x * BM + quad * 32 + lane;
-            const long long col0 = (long long)tile.y * BN;
+            const long long col0 = (long long)tile.y * BN + half * 128;
             const long long row_hi = (long long)tile.x * BM + quad * 32 + 31;   // last row of this warp
-            for (int c = 0; c < BN; c += 32) {
-                if (col0 + c > row_hi || col0 + c >= p.n) break;     // warp-uniform: nothing at or below the diagonal
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + acc * BN + c + ((uint32_t)(quad * 32) << 16);
-                PSTB_TMEM_LD32(taddr, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const long long cc = col0 + c * 32;
+                if (cc > row_hi || cc >= p.n) continue;              // warp-uniform: nothing at or below the diagonal
                 if (row < p.n) {
-                    float* dst = p.K + row * p.ldk + col0 + c;
-                    if (vec && col0 + c + 32 <= p.n) {
+                    float* dst = p.K + row * p.ldk + cc;
+                    if (vec && cc + 32 <= p.n) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
-                                                   __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+                            float4 o = make_float4(sum[c * 32 + 4 * q] * scale, sum[c * 32 + 4 * q + 1] * scale,
+                                                   sum[c * 32 + 4 * q + 2] * scale, sum[c * 32 + 4 * q + 3] * scale);
                             float4* d4 = reinterpret_cast<float4*>(dst) + q;
                             if (p.accumulate) { float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
                             *d4 = o;
@@ -334,8 +361,8 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
                     } else {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
-                            if (col0 + c + q < p.n) {
-                                float o = __uint_as_float(v[q]) * scale;
+                            if (cc + q < p.n) {
+                                float o = sum[c * 32 + q] * scale;
                                 if (p.accumulate) o += dst[q];
                                 dst[q] = o;
                             }
@@ -343,9 +370,6 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
         }
     }
     tc_fence_before();

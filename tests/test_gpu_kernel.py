@@ -1,0 +1,104 @@
+"""GPU parity: K3 kinship K = X X^T on tcgen05 vs the float64 oracle / the reference's golden kernels.
+
+Gate (north_star): relative Frobenius error <= 1e-5.  The fp16 hi/lo split lands near 1e-7.
+"""
+import numpy as np
+import pytest
+
+from conftest import fixture_packed
+
+pytestmark = pytest.mark.gpu
+K_TOL = 1e-5
+
+
+def rel_fro(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from pysnptools_b200 import device
+    assert torch.cuda.is_available()
+    return device
+
+
+@pytest.mark.parametrize("n,k", [(100, 64), (300, 128), (640, 448), (1000, 64)])
+def test_syrk_planes_tensor_core_stage(n, k, dev):
+    """The tcgen05 stage alone: K_lower = hi hi^T + hi lo^T + lo hi^T on given fp16 planes."""
+    import torch
+    from pysnptools_b200._lib import lib, check
+    g = torch.Generator(device="cuda").manual_seed(n + k)
+    n_pad = (n + 255) // 256 * 256
+    x = torch.randn((n_pad, k), generator=g, device="cuda", dtype=torch.float32) * 3.0
+    x[n:] = 0
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    K = torch.full((n, n), 7.0, device="cuda", dtype=torch.float32)
+    check(lib.pstb_syrk_planes(hi.data_ptr(), lo.data_ptr(), n, n_pad, k, K.data_ptr(), n, 0, 0.5, torch.cuda.current_stream().cuda_stream))
+    h64, l64 = hi[:n].double(), lo[:n].double()
+    ref = 0.5 * (h64 @ h64.T + h64 @ l64.T + l64 @ h64.T)
+    got = torch.tril(K).double().cpu().numpy()
+    want = torch.tril(ref).cpu().numpy()
+    assert rel_fro(got, want) < 3e-6, rel_fro(got, want)
+    # accumulate adds onto the existing lower triangle
+    check(lib.pstb_syrk_planes(hi.data_ptr(), lo.data_ptr(), n, n_pad, k, K.data_ptr(), n, 1, 0.5, torch.cuda.current_stream().cuda_stream))
+    assert rel_fro(torch.tril(K).double().cpu().numpy(), 2 * want) < 3e-6
+    check(lib.pstb_mirror_lower(K.data_ptr(), n, n, torch.cuda.current_stream().cuda_stream))
+    Kc = K.cpu().numpy()
+    assert np.array_equal(Kc, Kc.T)
+
+
+def test_kernel_goldens(golden, dev):
+    packed, n, m = fixture_packed("n300")
+    store = dev.PackedStore.from_host(packed, n)
+    K, st = dev.snp_kernel(store)
+    Kc = K.double().cpu().numpy()
+    assert rel_fro(Kc, golden["n300_unit_K"]) < K_TOL
+    assert abs(Kc[0, 0] - 901.421836) < 901.421836 * K_TOL                         # snpreader.py:308-313 doctest
+    np.testing.assert_allclose(st.cpu().numpy(), golden["n300_unit_stats"], rtol=1e-12)
+    Kb, _ = dev.snp_kernel(store, standardizer=("beta", 1, 25), chunk=512)
+    assert rel_fro(Kb.double().cpu().numpy(), golden["n300_beta_1_25_K"]) < K_TOL
+    pd, nd, md = fixture_packed("dbx")
+    Kd, _ = dev.snp_kernel(dev.PackedStore.from_host(pd, nd), chunk=64)            # 2 chunks, missing values
+    assert rel_fro(Kd.double().cpu().numpy(), golden["dbx_unit_K"]) < K_TOL
+    pt, nt, mt = fixture_packed("toydata")
+    Kt, _ = dev.snp_kernel(dev.PackedStore.from_host(pt, nt))
+    Ktc = Kt.double().cpu().numpy()
+    assert rel_fro(Ktc, golden["toydata_unit_K_shipped"]) < K_TOL
+    assert abs(np.trace(Ktc) - 5_000_000) < 50                                       # trace(K) = N * M for Unit
+    assert abs(Ktc[0, 0] * nt / np.trace(Ktc) - float(golden["toydata_unit_K_diagKtoN_00"])) < 1e-5
+
+
+@pytest.mark.parametrize("n,m,chunk", [(257, 300, 64), (1500, 2000, 1024), (2100, 700, None)])
+def test_kernel_random_vs_oracle(n, m, chunk, oracle, dev):
+    rng = np.random.default_rng(n)
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.05, seed=n)
+    store = dev.PackedStore.from_host(packed, n)
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        ref, rst = oracle.read_kernel(packed, n, **args)
+        K, st = dev.snp_kernel(store, standardizer=std, chunk=chunk)
+        Kc = K.double().cpu().numpy()
+        assert np.array_equal(Kc, Kc.T)
+        assert rel_fro(Kc, ref) < K_TOL, rel_fro(Kc, ref)
+        np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12)
+    # iid gather + sid subset + count_A1 + trained statistics
+    ii = rng.permutation(n)[: n // 2]
+    si = np.sort(rng.permutation(m)[: m // 2])
+    ref, rst = oracle.read_kernel(packed, n, iid_index=ii, sid_index=si, count_A1=True)
+    K, st = dev.snp_kernel(store, ii, si, count_A1=True, chunk=chunk)
+    assert rel_fro(K.double().cpu().numpy(), ref) < K_TOL
+    K2, _ = dev.snp_kernel(store, ii, si, count_A1=True, stats=st, chunk=chunk)
+    assert rel_fro(K2.double().cpu().numpy(), ref) < K_TOL
+    # SNP-sharded accumulation == one pass (what the multi-GPU path sums with NCCL)
+    half = len(si) // 2
+    Ka, _ = dev.snp_kernel(store, ii, si[:half], count_A1=True, chunk=chunk, mirror=False)
+    Ka, _ = dev.snp_kernel(store, ii, si[half:], count_A1=True, chunk=chunk, K=Ka, accumulate=True)
+    assert rel_fro(Ka.double().cpu().numpy(), ref) < K_TOL
+
+
+def test_convert_kernel(dev):
+    import torch
+    K = torch.randn((37, 37), device="cuda")
+    out = dev.convert_kernel(K, np.float64, scale=2.0)
+    assert out.dtype == torch.float64 and torch.allclose(out, K.double() * 2.0)

@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- the genotype hot path on B200: decode 2-bit .bed -> Unit standardize (float32), and SnpKernel.
+
+Contract line (one JSON object on stdout, rank 0):
+  metric  "genotypes/s decoded+standardized" on BASELINE.json configs[1]
+          (synthetic .bed, 10 000 iids x 1 000 000 SNPs, Unit, float32, F order, 1 B200 per rank).
+  value   whole-job throughput with the packed bytes resident in HBM (one fused kernel launch per step).
+  e2e     the same workload through the host-buffer C ABI (pstb_read_host: pinned host packed bytes in,
+          pinned host float32 matrix out, H2D and D2H inside the timed region).
+  roofline / cpu_baseline / clocks / gpu_launches as the build brief defines them.
+  kernel  (extra object) SnpKernel TFLOP/s on configs[2] (50 000 x 500 000, Unit, K fp32), 2*N^2*M convention.
+
+`--impl reference` times the reference's CPU path for the same metric: the plain-C/OpenMP port in oracle/
+(the reference's own native code is the external Rust wheel `bed-reader`, not in this tree and not
+buildable here -- DESIGN.md) on a bounded sample of the same workload, all host threads.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(n_iid=10_000, n_sid=1_000_000)
+CFG3 = dict(n_iid=50_000, n_sid=500_000)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# ------------------------------------------------------------------------------------------------------------
+def _oracle_lib():
+    so = os.path.join(ROOT, "oracle", "_build", "libpst_oracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(so)
+
+
+def synth_packed_host(n_iid, n_sid, seed=0):
+    """Synthetic packed records on the host (same distribution as the device generator)."""
+    rng = np.random.default_rng(seed)
+    rec = (n_iid + 3) // 4
+    out = np.empty((n_sid, rec), dtype=np.uint8)
+    code_of = np.array([0, 2, 3], dtype=np.uint8)
+    step = max(1, (64 << 20) // max(1, n_iid))
+    for s0 in range(0, n_sid, step):
+        s1 = min(n_sid, s0 + step)
+        p = rng.uniform(0.05, 0.5, size=(s1 - s0, 1)).astype(np.float32)
+        g = (rng.random((s1 - s0, n_iid), dtype=np.float32) < p).astype(np.uint8) + (rng.random((s1 - s0, n_iid), dtype=np.float32) < p)
+        c = np.zeros((s1 - s0, rec * 4), dtype=np.uint8)
+        c[:, :n_iid] = code_of[g]
+        c = c.reshape(s1 - s0, rec, 4)
+        out[s0:s1] = c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6)
+    return out
+
+
+def cpu_decode_standardize(lib, packed, n_iid, threads, reps=1):
+    """Reference CPU path: decode to a float32 F-order matrix, then standardize it in place (Unit)."""
+    n_sid = packed.shape[0]
+    out = np.empty((n_iid, n_sid), dtype=np.float32, order="F")
+    stats = np.empty((n_sid, 2), dtype=np.float64)
+    p = ctypes.c_void_p
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lib.pst_oracle_decode_f32(p(packed.ctypes.data), ctypes.c_int64(packed.shape[1]), ctypes.c_int64(n_iid), ctypes.c_int64(n_sid),
+                                  None, ctypes.c_int64(n_iid), None, ctypes.c_int64(n_sid), 0, 0, p(out.ctypes.data), threads)
+        lib.pst_oracle_standardize_f32(p(out.ctypes.data), ctypes.c_int64(n_iid), ctypes.c_int64(n_sid), 0, 0, ctypes.c_double(np.nan),
+                                       ctypes.c_double(np.nan), 0, p(stats.ctypes.data), threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, out, stats
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib = _oracle_lib()
+    threads = os.cpu_count() or 1
+    n_iid, sample_sid = CFG2["n_iid"], args.ref_sample_sid
+    packed = synth_packed_host(n_iid, sample_sid, seed=0)
+    for _ in range(args.warmup):
+        cpu_decode_standardize(lib, packed, n_iid, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_decode_standardize(lib, packed, n_iid, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_iid * sample_sid / dt
+    sample = "{0} iids x {1} SNPs (first {1} of the 1 000 000 SNP workload) per step".format(n_iid, sample_sid)
+    line = {
+        "impl": "reference", "metric": "genotypes/s decoded+standardized", "value": value, "unit": "genotypes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: synthetic .bed 10000 iids x 1000000 SNPs, decode + Unit standardize float32, F order",
+                   "reference_arm": "oracle/c/pst_oracle.c (plain C + OpenMP port of the reference CPU path; bed-reader Rust wheel absent)"},
+        "cpu_baseline": {"value": value, "unit": "genotypes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                for k, nm in enumerate(names):
+                    if f[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_store_device(dev, torch, n_iid, n_sid, seed, missing_rate=0.0):
+    """Synthetic packed store generated on the GPU and packed with the library's own pack kernel (K0)."""
+    ld = int(dev.lib.pstb_packed_ld(n_iid))
+    store_t = torch.zeros((n_sid, ld), dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    step = max(1, min(n_sid, (1 << 28) // max(1, n_iid)))
+    for s0 in range(0, n_sid, step):
+        s1 = min(n_sid, s0 + step)
+        p = torch.empty((s1 - s0, 1), device="cuda").uniform_(0.05, 0.5, generator=g)
+        val = (torch.rand((s1 - s0, n_iid), device="cuda", generator=g) < p).to(torch.int8)
+        val += (torch.rand((s1 - s0, n_iid), device="cuda", generator=g) < p).to(torch.int8)
+        if missing_rate > 0:
+            val[torch.rand((s1 - s0, n_iid), device="cuda", generator=g) < missing_rate] = -127
+        part = dev.pack(val.t())                                    # [n_iid, chunk] F-order view of the [chunk, n_iid] buffer
+        store_t[s0:s1].copy_(part.tensor)
+        del val, part
+    return dev.PackedStore(store_t, n_iid, n_sid)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from pysnptools_b200 import _lib, device as dev
+    lib = _lib.lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.require_gpu()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_iid, n_sid = CFG2["n_iid"], CFG2["n_sid"]
+    rec = (n_iid + 3) // 4
+    # every rank owns one full cfg2-sized SNP shard (weak scaling; no data-path collective -- DESIGN.md)
+    store = gen_store_device(dev, torch, n_iid, n_sid, seed=1000 + rank)
+    out = torch.empty((n_sid, n_iid), dtype=torch.float32, device="cuda")          # F order: [n_iid, n_sid] transposed
+    stats = torch.empty((n_sid, 2), dtype=torch.float64, device="cuda")
+    full = _lib.Axis(None, 0, 1, n_iid), _lib.Axis(None, 0, 1, n_sid)
+
+    def step():
+        _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n_iid, n_sid, full[0], full[1], 0, _lib.STD_UNIT,
+                                               float("nan"), float("nan"), 0, stats.data_ptr(), out.data_ptr(), _lib.F32, _lib.ORDER_F, stream))
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.pstb_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    launches = lib.pstb_launch_count() - launches0
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = total_ms / args.steps
+    value = world * n_iid * n_sid / (ms_per_step * 1e-3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = n_sid * rec + 4 * n_iid * n_sid + 16 * n_sid
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": args.ncu_traffic, "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
+                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+
+    # ---- spot parity of the timed configuration against the oracle (not timed) ----
+    lib_o = _oracle_lib()
+    sample_sid = min(args.cpu_sample_sid, n_sid)
+    packed_sample = store.tensor[:sample_sid, :rec].contiguous().cpu().numpy()
+    parity = None
+    e2e = None
+    cpu_baseline = None
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        cpu_s, cpu_out, cpu_stats = cpu_decode_standardize(lib_o, packed_sample, n_iid, threads, reps=2)
+        cpu_baseline = {"value": n_iid * sample_sid / cpu_s, "unit": "genotypes/s", "cores": threads, "kind": "port",
+                        "sample": "first {0} SNPs x {1} iids of the same synthetic store; oracle/c/pst_oracle.c decode+standardize (OpenMP)".format(sample_sid, n_iid)}
+        chk = min(sample_sid, 2048)
+        got = out[:chk].t().cpu().numpy()
+        parity = {"checked_snps": chk, "max_abs_diff_vs_oracle": float(np.max(np.abs(got - cpu_out[:, :chk]))),
+                  "stats_max_rel_diff": float(np.max(np.abs(stats[:chk].cpu().numpy() - cpu_stats[:chk]) / np.maximum(1e-300, np.abs(cpu_stats[:chk]))))}
+        del cpu_out
+
+    # ---- end to end through the host-buffer C ABI (every rank, pinned host buffers) ----
+    if args.e2e:
+        e2e = run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, barrier, max_over_ranks)
+    del out, store, stats
+    torch.cuda.empty_cache()
+    # ---- SnpKernel (cfg3) ----
+    kernel = None
+    if args.kernel:
+        kernel = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks)
+
+    if rank == 0:
+        line = {
+            "metric": "genotypes/s decoded+standardized", "value": value, "unit": "genotypes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: synthetic .bed 10000 iids x 1000000 SNPs per GPU, decode + Unit standardize float32, F order",
+                       "packed_bytes": n_sid * rec, "out_bytes": 4 * n_iid * n_sid, "l2": "inputs (2.5 GB) and outputs (40 GB) larger than L2; no flush needed",
+                       "sharding": "SNP ranges, one cfg2-sized shard per GPU, no collective"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "kernel_ms_per_launch": kern_ms, "parity_spot_check": parity,
+        }
+        if kernel is not None:
+            line["kernel"] = kernel
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, barrier, max_over_ranks):
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_out_p = lib.pstb_host_alloc(n_iid * n_sid * 4)
+    h_pk_p = lib.pstb_host_alloc(n_sid * rec)
+    if not h_out_p or not h_pk_p:
+        raise RuntimeError("pinned host allocation failed: " + _lib.last_error())
+    h_packed = np.ctypeslib.as_array(ctypes.cast(h_pk_p, ctypes.POINTER(ctypes.c_uint8)), shape=(n_sid, rec))
+    step_rows = max(1, (1 << 28) // rec)
+    for s0 in range(0, n_sid, step_rows):
+        h_packed[s0:s0 + step_rows] = store.tensor[s0:s0 + step_rows, :rec].cpu().numpy()
+    h_stats = np.empty((n_sid, 2), dtype=np.float64)
+
+    def e2e_step():
+        _lib.check(lib.pstb_read_host(h_pk_p, n_iid, n_sid, None, n_iid, None, n_sid, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
+                                      h_stats.ctypes.data, h_out_p, _lib.F32, _lib.ORDER_F))
+
+    e2e_step()                                                                      # warm-up (allocates the chunk ring)
+    barrier()
+    t0e = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt_e = max_over_ranks((time.perf_counter() - t0e) / e2e_steps)
+    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_float)), shape=(n_sid, n_iid))
+    e2e_ok = bool(np.array_equal(h_stats[:256], stats[:256].cpu().numpy())) and bool(np.isfinite(h_out[-1]).all())
+    res = {"value": world * n_iid * n_sid / dt_e, "unit": "genotypes/s", "h2d_bytes_per_step": n_sid * rec, "d2h_bytes_per_step": n_iid * n_sid * 4 + 16 * n_sid,
+           "ms_per_step": dt_e * 1e3, "steps": e2e_steps, "api": "pstb_read_host (host-buffer C ABI), pinned host buffers, 64 MiB chunks on 2 streams",
+           "stats_match_device_run": e2e_ok}
+    del h_out, h_packed
+    lib.pstb_host_free(h_out_p)
+    lib.pstb_host_free(h_pk_p)
+    return res
+
+
+
+def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks):
+    """cfg3: SnpKernel(Unit) on 50 000 x 500 000, SNP-sharded over the ranks, one NCCL all-reduce of K."""
+    n, m = (args.kernel_n, args.kernel_m)
+    m_lo, m_hi = rank * m // world, (rank + 1) * m // world
+    store = gen_store_device(dev, torch, n, m_hi - m_lo, seed=2000 + rank)
+    K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+    chunk = args.kernel_chunk
+
+    def step():
+        dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1))
+        if world > 1:
+            dist.all_reduce(K)                                                       # sum of partial K_r over NVLink
+            _lib.check(_lib.lib.pstb_mirror_lower(K.data_ptr(), n, n, torch.cuda.current_stream().cuda_stream))
+
+    step()
+    barrier()
+    l0 = _lib.lib.pstb_launch_count()
+    steps = max(1, min(args.steps, args.kernel_steps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
+    tiles = sum(1 for i in range((n + 127) // 128) for j in range((n + 255) // 256) if j * 256 <= i * 128 + 127)
+    executed = 3.0 * 2 * 128 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    diag = float(K.diagonal().double().mean().item())
+    return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
+            "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32, SNP-sharded + NCCL allreduce".format(n, m),
+                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "fp16 hi/lo, 3 MMA terms, lower-triangular tiles"},
+            "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
+                         "note": "executed MMA flops per rank (3 terms x lower-triangular 128x256 tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained"},
+            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-sid", type=int, default=100_000)
+    ap.add_argument("--ref-sample-sid", type=int, default=50_000)
+    ap.add_argument("--no-kernel", dest="kernel", action="store_false")
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--kernel-n", type=int, default=CFG3["n_iid"])
+    ap.add_argument("--kernel-m", type=int, default=CFG3["n_sid"])
+    ap.add_argument("--kernel-steps", type=int, default=1)
+    ap.add_argument("--kernel-chunk", type=int, default=None)
+    ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

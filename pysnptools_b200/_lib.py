@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpst_b200.so")
+LIB_PATH = os.environ.get("PSTB_LIB_PATH") or os.path.join(_HERE, "libpst_b200.so")   # override: kernel experiments only
 
 F32, F64, I8 = 0, 1, 2
 ORDER_F, ORDER_C = 0, 1

@@ -14,6 +14,12 @@
 // tile-transposing kernel writes 128-byte row segments.
 #include "pstb_common.cuh"
 
+#ifndef PSTB_ST_HINT
+#define PSTB_ST_HINT ".cs"   // streaming (evict-first) stores: the output is never re-read by this kernel
+#endif
+#ifndef PSTB_READ_MINB
+#define PSTB_READ_MINB 4
+#endif
 namespace pstb {
 
 struct ReadParams {
@@ -35,7 +41,7 @@ struct ReadParams {
     int nbuf;               // raw buffers per group (1 or 2)
     int direct;             // record too large for shared memory: gather straight from global, in segments
     long long seg_len;      // outputs per segment (multiple of 16) when direct
-    int vec_ok;             // output columns are 16-byte aligned
+    int vec_ok;             // output columns: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = neither
 };
 
 template <typename T>
@@ -83,12 +89,44 @@ __device__ __forceinline__ Lut4<T> make_code_lut(int mode, int count_a1, double 
 __device__ __forceinline__ long long clampll(long long v, long long hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); }
 
 // ---- emit one output column from a dense 2-bit record in shared memory ------------------------------
+// vec: 2 = column base and length are 32-byte multiples (256-bit stores, sm_100), 1 = 16-byte, 0 = scalar.
+// Every lane writes one 32-byte (or 16-byte) piece per instruction, adjacent lanes adjacent pieces, so each
+// warp store covers 1 KiB (512 B) of the column and every 32-byte sector is written exactly once.
+__device__ __forceinline__ void st256_f32(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+    asm volatile("st.global" PSTB_ST_HINT ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4),
+                 "f"(a5), "f"(a6), "f"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ void st256_f64(double* p, double a0, double a1, double a2, double a3) {
+    asm volatile("st.global" PSTB_ST_HINT ".v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a0), "d"(a1), "d"(a2), "d"(a3) : "memory");
+}
+__device__ __forceinline__ void st256_b32(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global" PSTB_ST_HINT ".v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 template <typename T>
-__device__ __forceinline__ void emit_column(const unsigned char* rec, T* o, long long n_out, const Lut4<T>& lut, int vec_ok, int gid, int gsize);
+__device__ __forceinline__ void emit_scalar(const unsigned char* rec, T* o, long long from, long long n_out, const Lut4<T>& lut, int gid, int gsize) {
+    for (long long a = from + gid; a < n_out; a += gsize) __stcs(o + a, lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u));
+}
+
+template <typename T>
+__device__ __forceinline__ void emit_column(const unsigned char* rec, T* o, long long n_out, const Lut4<T>& lut, int vec, int gid, int gsize);
 
 template <>
-__device__ __forceinline__ void emit_column<float>(const unsigned char* rec, float* o, long long n_out, const Lut4<float>& lut, int vec_ok, int gid, int gsize) {
-    if (vec_ok) {
+__device__ __forceinline__ void emit_column<float>(const unsigned char* rec, float* o, long long n_out, const Lut4<float>& lut, int vec, int gid, int gsize) {
+    if (vec == 2) {
+        const long long nh = n_out >> 3;                          // 8 genotypes = 2 packed bytes = 32 output bytes
+        const uint16_t* rec16 = reinterpret_cast<const uint16_t*>(rec);
+#pragma unroll 4
+        for (long long h = gid; h < nh; h += gsize) {
+            const uint32_t two = rec16[h];
+            st256_f32(o + (h << 3), lut.pick(two & 3u), lut.pick((two >> 2) & 3u), lut.pick((two >> 4) & 3u), lut.pick((two >> 6) & 3u),
+                      lut.pick((two >> 8) & 3u), lut.pick((two >> 10) & 3u), lut.pick((two >> 12) & 3u), lut.pick(two >> 14));
+        }
+        emit_scalar<float>(rec, o, nh << 3, n_out, lut, gid, gsize);
+    } else if (vec == 1) {
         const long long nq = n_out >> 2;
         float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll 4
@@ -101,16 +139,23 @@ __device__ __forceinline__ void emit_column<float>(const unsigned char* rec, flo
             v.w = lut.pick(byte >> 6);
             __stcs(o4 + q, v);
         }
-        long long a = (nq << 2) + gid;
-        if (a < n_out) __stcs(o + a, lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u));
+        emit_scalar<float>(rec, o, nq << 2, n_out, lut, gid, gsize);
     } else {
-        for (long long a = gid; a < n_out; a += gsize) __stcs(o + a, lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u));
+        emit_scalar<float>(rec, o, 0, n_out, lut, gid, gsize);
     }
 }
 
 template <>
-__device__ __forceinline__ void emit_column<double>(const unsigned char* rec, double* o, long long n_out, const Lut4<double>& lut, int vec_ok, int gid, int gsize) {
-    if (vec_ok) {
+__device__ __forceinline__ void emit_column<double>(const unsigned char* rec, double* o, long long n_out, const Lut4<double>& lut, int vec, int gid, int gsize) {
+    if (vec == 2) {
+        const long long nq = n_out >> 2;                          // 4 genotypes = 1 packed byte = 32 output bytes
+#pragma unroll 4
+        for (long long q = gid; q < nq; q += gsize) {
+            const uint32_t byte = rec[q];
+            st256_f64(o + (q << 2), lut.pick(byte & 3u), lut.pick((byte >> 2) & 3u), lut.pick((byte >> 4) & 3u), lut.pick(byte >> 6));
+        }
+        emit_scalar<double>(rec, o, nq << 2, n_out, lut, gid, gsize);
+    } else if (vec == 1) {
         const long long nh = n_out >> 1;
         double2* o2 = reinterpret_cast<double2*>(o);
 #pragma unroll 4
@@ -122,16 +167,35 @@ __device__ __forceinline__ void emit_column<double>(const unsigned char* rec, do
             v.y = lut.pick((byte >> (sh + 2)) & 3u);
             __stcs(o2 + h, v);
         }
-        long long a = (nh << 1) + gid;
-        if (a < n_out) __stcs(o + a, lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u));
+        emit_scalar<double>(rec, o, nh << 1, n_out, lut, gid, gsize);
     } else {
-        for (long long a = gid; a < n_out; a += gsize) __stcs(o + a, lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u));
+        emit_scalar<double>(rec, o, 0, n_out, lut, gid, gsize);
     }
 }
 
+__device__ __forceinline__ uint32_t i8x4(const Lut4<int8_t>& lut, uint32_t byte) {
+    uint32_t x0 = (uint8_t)lut.pick(byte & 3u), x1 = (uint8_t)lut.pick((byte >> 2) & 3u);
+    uint32_t x2 = (uint8_t)lut.pick((byte >> 4) & 3u), x3 = (uint8_t)lut.pick(byte >> 6);
+    return x0 | (x1 << 8) | (x2 << 16) | (x3 << 24);
+}
+
 template <>
-__device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, int8_t* o, long long n_out, const Lut4<int8_t>& lut, int vec_ok, int gid, int gsize) {
-    if (vec_ok) {
+__device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, int8_t* o, long long n_out, const Lut4<int8_t>& lut, int vec, int gid, int gsize) {
+    if (vec == 2 && ((reinterpret_cast<uintptr_t>(rec) & 7u) == 0)) {
+        const long long nw = n_out >> 5;                          // 32 genotypes = 8 packed bytes = 32 output bytes
+        const uint2* rec64 = reinterpret_cast<const uint2*>(rec);
+        for (long long w = gid; w < nw; w += gsize) {
+            const uint2 two = rec64[w];
+            uint32_t r[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                r[k] = i8x4(lut, (two.x >> (8 * k)) & 0xffu);
+                r[4 + k] = i8x4(lut, (two.y >> (8 * k)) & 0xffu);
+            }
+            st256_b32(o + (w << 5), r);
+        }
+        emit_scalar<int8_t>(rec, o, nw << 5, n_out, lut, gid, gsize);
+    } else if (vec >= 1) {
         const long long nw = n_out >> 4;
         const uint32_t* rec32 = reinterpret_cast<const uint32_t*>(rec);
         uint4* o16 = reinterpret_cast<uint4*>(o);
@@ -139,23 +203,18 @@ __device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, in
             uint32_t word = rec32[w];
             uint32_t r[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t byte = (word >> (8 * k)) & 0xffu;
-                uint32_t x0 = (uint8_t)lut.pick(byte & 3u), x1 = (uint8_t)lut.pick((byte >> 2) & 3u);
-                uint32_t x2 = (uint8_t)lut.pick((byte >> 4) & 3u), x3 = (uint8_t)lut.pick(byte >> 6);
-                r[k] = x0 | (x1 << 8) | (x2 << 16) | (x3 << 24);
-            }
+            for (int k = 0; k < 4; ++k) r[k] = i8x4(lut, (word >> (8 * k)) & 0xffu);
             __stcs(o16 + w, make_uint4(r[0], r[1], r[2], r[3]));
         }
-        for (long long a = (nw << 4) + gid; a < n_out; a += gsize) o[a] = lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u);
+        emit_scalar<int8_t>(rec, o, nw << 4, n_out, lut, gid, gsize);
     } else {
-        for (long long a = gid; a < n_out; a += gsize) o[a] = lut.pick((rec[a >> 2] >> (2 * (a & 3))) & 3u);
+        emit_scalar<int8_t>(rec, o, 0, n_out, lut, gid, gsize);
     }
 }
 
 // ---- K1/K2, F order -------------------------------------------------------------------------------
 template <typename T, bool kCta>
-__global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p) {
+__global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k_read_f(const ReadParams p) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     __shared__ unsigned int red[3][16];
 
@@ -304,6 +363,160 @@ __global__ void __launch_bounds__(kCta ? 512 : 256) k_read_f(const ReadParams p)
     }
 }
 
+// ---- K1/K2, F order, gathered individuals: S records per batch share one pass over the index vector ---------
+// The iid index vector costs 4 bytes per output genotype -- as much as the float32 output itself -- so it is read
+// once per batch of S staged records (TMA bulk copies on one mbarrier), every thread turning its 4 indices into
+// S re-packed bytes.  The raw records are dead after the re-pack, so the next batch's bulk copies are issued
+// before the counts / emit and overlap with the HBM writes.
+constexpr int kGatherMaxS = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, int S, unsigned dense_stride) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ unsigned int cnt[kGatherMaxS][3];
+    __shared__ double st_s[kGatherMaxS][2];
+    __shared__ double lut_d[kGatherMaxS][4];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_dyn);
+    unsigned char* raw0 = smem_dyn + 16;
+    unsigned char* dense0 = raw0 + (size_t)S * p.raw_stride;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long long n_out = p.iid.n;
+    const long long nbatch = (p.sid.n + S - 1) / S;
+    const long long nbytes = (n_out + 3) >> 2;
+    const bool idx_vec = p.iid.idx && ((reinterpret_cast<uintptr_t>(p.iid.idx) & 15u) == 0);
+
+    if (p.bulk_ok && tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](long long batch) {
+        const long long b0 = batch * S;
+        const int ns = (int)min((long long)S, p.sid.n - b0);
+        mbar_expect_tx(bar, (uint32_t)ns * p.copy_bytes);
+        for (int s = 0; s < ns; ++s) {
+            long long j = clampll(p.sid.at(b0 + s), p.sid_count);
+            bulk_g2s(raw0 + (size_t)s * p.raw_stride, p.packed + j * p.ld, p.copy_bytes, bar);
+        }
+    };
+    long long batch = blockIdx.x;
+    if (p.bulk_ok && tid == 0 && batch < nbatch) issue(batch);
+
+    for (uint32_t it = 0; batch < nbatch; batch += gridDim.x, ++it) {
+        const long long b0 = batch * S;
+        const int ns = (int)min((long long)S, p.sid.n - b0);
+        if (p.bulk_ok) {
+            mbar_wait(bar, it & 1u);
+        } else {
+            for (int s = 0; s < ns; ++s) {
+                const uint8_t* src = p.packed + clampll(p.sid.at(b0 + s), p.sid_count) * p.ld;
+                for (unsigned i = tid; i < p.rec_bytes; i += nt) raw0[(size_t)s * p.raw_stride + i] = __ldg(src + i);
+            }
+            __syncthreads();
+        }
+        if (tid < kGatherMaxS * 3) (&cnt[0][0])[tid] = 0;
+
+        for (long long q = tid; q < nbytes; q += nt) {
+            uint32_t boff[4], sh[4], keep = 0;
+            if (idx_vec && (q << 2) + 3 < n_out) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.iid.idx) + q);
+                const uint32_t iv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    uint32_t i = iv[t] < (uint32_t)p.iid_count ? iv[t] : (uint32_t)p.iid_count - 1u;
+                    boff[t] = i >> 2;
+                    sh[t] = 2u * (i & 3u);
+                }
+                keep = 0xffu;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const long long a = (q << 2) + t;
+                    long long i = 0;
+                    if (a < n_out) {
+                        i = clampll(p.iid.at(a), p.iid_count);
+                        keep |= 3u << (2 * t);
+                    }
+                    boff[t] = (uint32_t)(i >> 2);
+                    sh[t] = 2u * (uint32_t)(i & 3);
+                }
+            }
+            for (int s = 0; s < ns; ++s) {
+                const unsigned char* r = raw0 + (size_t)s * p.raw_stride;
+                uint32_t byte = ((uint32_t)(r[boff[0]] >> sh[0]) & 3u) | (((uint32_t)(r[boff[1]] >> sh[1]) & 3u) << 2) |
+                                (((uint32_t)(r[boff[2]] >> sh[2]) & 3u) << 4) | (((uint32_t)(r[boff[3]] >> sh[3]) & 3u) << 6);
+                dense0[(size_t)s * dense_stride + q] = (unsigned char)(byte & keep);
+            }
+        }
+        __syncthreads();
+        const long long nbt = batch + gridDim.x;
+        if (p.bulk_ok && tid == 0 && nbt < nbatch) issue(nbt);      // raw buffers are free again
+
+        if (p.mode != PSTB_STD_NONE) {
+            if (!p.use_stats) {
+                const long long nwords = (n_out + 15) >> 4;
+                for (int s = 0; s < ns; ++s) {
+                    const uint32_t* rec32 = reinterpret_cast<const uint32_t*>(dense0 + (size_t)s * dense_stride);
+                    unsigned int c1 = 0, c2 = 0, c3 = 0;
+                    for (long long w = tid; w < nwords; w += nt) {
+                        uint32_t word = rec32[w];
+                        if (w == nwords - 1) {
+                            unsigned rem = (unsigned)(n_out & 15);
+                            if (rem) word &= (1u << (2 * rem)) - 1u;
+                        }
+                        uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
+                        c1 += __popc(lo & ~hi);
+                        c2 += __popc(hi & ~lo);
+                        c3 += __popc(hi & lo);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                        c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+                    }
+                    if ((tid & 31) == 0) {
+                        atomicAdd(&cnt[s][0], c1);
+                        atomicAdd(&cnt[s][1], c2);
+                        atomicAdd(&cnt[s][2], c3);
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid < ns) {
+                double mean, sd;
+                if (p.use_stats) {
+                    mean = p.stats[2 * (b0 + tid)];
+                    sd = p.stats[2 * (b0 + tid) + 1];
+                } else {
+                    const long long c1 = cnt[tid][0], c2 = cnt[tid][1], c3 = cnt[tid][2], c0 = n_out - c1 - c2 - c3;
+                    stats_from_counts(p.count_a1 ? c3 : c0, c2, p.count_a1 ? c0 : c3, mean, sd);
+                    if (p.stats) {
+                        p.stats[2 * (b0 + tid)] = mean;
+                        p.stats[2 * (b0 + tid) + 1] = sd;
+                    }
+                }
+                st_s[tid][0] = mean;
+                st_s[tid][1] = sd;
+            }
+        }
+        if (tid < ns) {
+            const Lut4<T> l = make_code_lut<T>(p.mode, p.count_a1, p.a, p.b, p.lnB, st_s[tid][0], st_s[tid][1]);
+            lut_d[tid][0] = (double)l.c0; lut_d[tid][1] = (double)l.c1; lut_d[tid][2] = (double)l.c2; lut_d[tid][3] = (double)l.c3;
+        }
+        __syncthreads();
+        if (p.out) {
+            for (int s = 0; s < ns; ++s) {
+                Lut4<T> lut;
+                lut.c0 = (T)lut_d[s][0]; lut.c1 = (T)lut_d[s][1]; lut.c2 = (T)lut_d[s][2]; lut.c3 = (T)lut_d[s][3];
+                emit_column<T>(dense0 + (size_t)s * dense_stride, reinterpret_cast<T*>(p.out) + (b0 + s) * p.out_ld, n_out, lut,
+                               p.vec_ok, tid, nt);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- C order: tile-transposing emit ------------------------------------------------------------------
 constexpr int kTileS = 32;    // SNPs per tile (one per lane)
 constexpr int kTileI = 512;   // individuals per tile
@@ -402,13 +615,41 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         return 0;
     }
     p.out_ld = n_out;
-    p.vec_ok = p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && ((n_out * (long long)sizeof(T)) % 16 == 0);
+    p.vec_ok = 0;
+    if (p.out) {
+        const uintptr_t base = reinterpret_cast<uintptr_t>(p.out);
+        const long long col = n_out * (long long)sizeof(T);
+        p.vec_ok = ((base & 31u) == 0 && col % 32 == 0) ? 2 : (((base & 15u) == 0 && col % 16 == 0) ? 1 : 0);
+    }
     const unsigned rec16 = (p.rec_bytes + 15u) & ~15u;
     p.bulk_ok = ((reinterpret_cast<uintptr_t>(p.packed) & 15u) == 0) && (p.ld % 16 == 0) && (rec16 <= p.ld || p.sid_count == 0);
     p.copy_bytes = rec16;
     p.raw_stride = rec16;
     const unsigned dense_bytes = p.dense ? 0u : (unsigned)((((n_out + 3) >> 2) + 15) & ~15LL);
     const unsigned max_smem = 220u * 1024u;
+    if (!p.dense) {
+        // gathered individuals: batch S records per pass over the index vector when at least one fits
+        const unsigned per_snp = rec16 + dense_bytes;
+        int S = (int)((max_smem - 16u) / per_snp);
+        if (S > kGatherMaxS) S = kGatherMaxS;
+        if (S >= 1) {
+            int threads = n_out < 16384 ? 256 : (n_out < 65536 ? 512 : 1024);
+            // small records: leave room for several CTAs per SM
+            while (S > 4 && (unsigned)S * per_snp > 64u * 1024u) --S;
+            if ((long long)S > p.sid.n) S = (int)p.sid.n;
+            const unsigned smem = 16u + (unsigned)S * per_snp;
+            PSTB_CUDA(cudaFuncSetAttribute(k_read_f_gather<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int ctas_per_sm = 1;
+            PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f_gather<T>, threads, smem));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            const long long nbatch = (p.sid.n + S - 1) / S;
+            long long grid = (long long)sms * ctas_per_sm;
+            if (grid > nbatch) grid = nbatch;
+            k_read_f_gather<T><<<(unsigned)grid, threads, smem, st>>>(p, S, dense_bytes);
+            PSTB_AFTER_LAUNCH("k_read_f_gather");
+            return 0;
+        }
+    }
     // warp-per-record when two raw buffers + the gather record stay small, else CTA-per-record
     const unsigned warp_group = 16u + 2u * rec16 + dense_bytes;
     if (warp_group <= 12u * 1024u) {
@@ -416,14 +657,15 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         p.group_smem = warp_group;
         const int warps = 8;
         const unsigned smem = warps * p.group_smem;
-        int ctas_per_sm = (int)(max_smem / (smem + 1024u));
-        if (ctas_per_sm > 8) ctas_per_sm = 8;
+        PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // persistent grid: exactly the CTAs that are resident at once, so every warp streams the same number of records
+        int ctas_per_sm = 1;
+        PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f<T, false>, warps * 32, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         long long want = (p.sid.n + warps - 1) / warps;
         long long grid = (long long)sms * ctas_per_sm;
         if (grid > want) grid = want;
         if (grid < 1) grid = 1;
-        PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_read_f<T, false><<<(unsigned)grid, warps * 32, smem, st>>>(p);
         PSTB_AFTER_LAUNCH("k_read_f<warp>");
     } else {
@@ -438,13 +680,13 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
             if (p.seg_len > ((n_out + 15) & ~15LL)) p.seg_len = (n_out + 15) & ~15LL;
             p.group_smem = 16u + (unsigned)(p.seg_len / 4);
         }
-        int ctas_per_sm = (int)(max_smem / (p.group_smem + 1024u));
-        if (ctas_per_sm > 4) ctas_per_sm = 4;
+        PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.group_smem));
+        int ctas_per_sm = 1;
+        PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f<T, true>, 512, p.group_smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         long long grid = (long long)sms * ctas_per_sm;
         if (grid > p.sid.n) grid = p.sid.n;
         if (grid < 1) grid = 1;
-        PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.group_smem));
         k_read_f<T, true><<<(unsigned)grid, 512, p.group_smem, st>>>(p);
         PSTB_AFTER_LAUNCH("k_read_f<cta>");
     }

@@ -1,0 +1,65 @@
+"""Micro-benchmark of the read kernels (K1/K2) on one B200: cfg2 / cfg4 shapes, dtypes, orders."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pysnptools_b200 import _lib, device as dev
+lib = _lib.lib
+PEAK = 6550.7
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+def rand_store(n, m, missing=False):
+    ld = int(lib.pstb_packed_ld(n))
+    t = torch.randint(0, 256, (m, ld), dtype=torch.uint8, device="cuda")
+    if not missing:
+        lo = t & 0x55; hi = (t >> 1) & 0x55
+        t = t & ~(lo & ~hi)            # code 01 -> 00
+    return dev.PackedStore(t, n, m)
+
+def run(tag, n, m, dtype, order, std, isel=None, ssel=None, missing=False):
+    store = rand_store(n, m, missing)
+    I = dev.Selection(isel, n, "cuda"); S = dev.Selection(ssel, m, "cuda")
+    es = np.dtype(dtype).itemsize
+    code, base, view = dev._alloc_out(I.n, S.n, dtype, order, "cuda")
+    stats = torch.empty((S.n, 2), dtype=torch.float64, device="cuda")
+    mode, a, b = dev._mode_args(std)
+    st = torch.cuda.current_stream().cuda_stream
+    fn = lambda: _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n, m, I.axis(), S.axis(), 0, mode, a, b, 0,
+                                                        stats.data_ptr(), base.data_ptr(), code, dev._order_code(order), st))
+    ms = timeit(fn)
+    algo = S.n * ((n + 3) // 4) + es * I.n * S.n + (16 * S.n if std else 0)
+    print("%-34s n=%d m=%d out=%dx%d %s %s: %.3f ms  %.3e genotypes/s  %.0f GB/s algorithmic = %.1f%% of %.0f"
+          % (tag, n, m, I.n, S.n, np.dtype(dtype).name, order, ms, I.n * S.n / ms * 1e3, algo / ms / 1e6, 100 * algo / ms / 1e6 / PEAK, PEAK), flush=True)
+    del store, base, view
+
+which = sys.argv[1:] or ["cfg2", "cfg4", "variants"]
+if "peaks" in which:
+    a = torch.empty(10_000_000_000 // 4, dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    ms = timeit(lambda: a.fill_(1.0)); print("torch fill_ 10 GB (write only): %.3f ms  %.0f GB/s" % (ms, 10e9 / ms / 1e6))
+    ms = timeit(lambda: b.copy_(a)); print("torch copy_ 10 GB->10 GB: %.3f ms  %.0f GB/s (read+write)" % (ms, 20e9 / ms / 1e6))
+    ms = timeit(lambda: a.sum()); print("torch sum 10 GB (read only): %.3f ms  %.0f GB/s" % (ms, 10e9 / ms / 1e6), flush=True)
+    del a, b
+if "cfg2" in which:
+    run("cfg2 decode+Unit", 10000, 1000000, np.float32, "F", ("unit",))
+if "cfg4" in which:
+    rng = np.random.default_rng(1)
+    N, M = 100000, 200000
+    run("cfg4 Beta gather 1/2 x 1/2", N, M, np.float32, "F", ("beta", 1, 25), rng.permutation(N)[: N // 2], rng.permutation(M)[: M // 2], missing=True)
+    run("cfg4-like dense full", N, M // 2, np.float32, "F", ("beta", 1, 25), missing=True)
+if "variants" in which:
+    run("decode only f32 F", 10000, 500000, np.float32, "F", None)
+    run("decode+Unit f64 F", 10000, 400000, np.float64, "F", ("unit",))
+    run("decode i8 F", 10000, 1000000, np.int8, "F", None)
+    run("decode+Unit f32 C", 10000, 500000, np.float32, "C", ("unit",))
+    run("decode+Unit f64 C", 10000, 250000, np.float64, "C", ("unit",))
+    run("decode+Unit f32 F N=50k (cta)", 50000, 200000, np.float32, "F", ("unit",))
+    run("decode+Unit f32 F N=500k (cta)", 500000, 20000, np.float32, "F", ("unit",))
+    run("decode+Unit f32 F N=300", 300, 4000000, np.float32, "F", ("unit",))

@@ -1,0 +1,42 @@
+// write-bandwidth pattern probe (experiment; not part of the product)
+#include <cstdio>
+#include <cuda_runtime.h>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
+__global__ void fill_linear(float4* o, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x*blockDim.x+threadIdx.x; i < n4; i += (size_t)gridDim.x*blockDim.x) __stcs(o+i, make_float4(1,2,3,4));
+}
+// each warp owns column b (col4 float4s), grid-stride over columns
+__global__ void fill_warpcol(float4* o, size_t ncol, int col4) {
+  int lane = threadIdx.x & 31; size_t w = ((size_t)blockIdx.x*blockDim.x+threadIdx.x)>>5, nw = ((size_t)gridDim.x*blockDim.x)>>5;
+  for (size_t b = w; b < ncol; b += nw) { float4* c = o + b*col4;
+#pragma unroll 4
+    for (int q = lane; q < col4; q += 32) __stcs(c+q, make_float4(1,2,3,(float)q)); }
+}
+// each CTA owns column b
+__global__ void fill_ctacol(float4* o, size_t ncol, int col4) {
+  for (size_t b = blockIdx.x; b < ncol; b += gridDim.x) { float4* c = o + b*col4;
+#pragma unroll 4
+    for (int q = threadIdx.x; q < col4; q += blockDim.x) __stcs(c+q, make_float4(1,2,3,(float)q)); }
+}
+// warp columns + a read of col4/16 float4 (6%) per column from a second buffer, with a dependency like ours
+__global__ void fill_warpcol_rd(float4* o, const uint4* in, size_t ncol, int col4) {
+  int lane = threadIdx.x & 31; size_t w = ((size_t)blockIdx.x*blockDim.x+threadIdx.x)>>5, nw = ((size_t)gridDim.x*blockDim.x)>>5;
+  int in4 = col4/16;
+  for (size_t b = w; b < ncol; b += nw) { float4* c = o + b*col4; const uint4* r = in + b*in4; unsigned acc=0;
+    for (int q = lane; q < in4; q += 32) { uint4 v = __ldg(r+q); acc += __popc(v.x)+__popc(v.y)+__popc(v.z)+__popc(v.w); }
+    for (int s=16;s;s>>=1) acc += __shfl_xor_sync(~0u, acc, s);
+    float f = (float)acc;
+#pragma unroll 4
+    for (int q = lane; q < col4; q += 32) __stcs(c+q, make_float4(f,2,3,(float)q)); }
+}
+template<class F> float timeit(F f){ cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b); f(); f(); cudaDeviceSynchronize(); float best=1e9; for(int i=0;i<5;i++){cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms,a,b); if(ms<best)best=ms;} return best; }
+int main(){
+  size_t ncol = 1000000; int col4 = 2500; size_t n4 = ncol*col4; float4* o; uint4* in;
+  CK(cudaMalloc(&o, n4*16)); CK(cudaMalloc(&in, ncol*(col4/16)*16)); CK(cudaMemset(in, 0x5a, ncol*(col4/16)*16));
+  double gb = n4*16/1e9;
+  for (int bps : {2,4,8,16}) { float ms = timeit([&]{ fill_linear<<<148*bps,256>>>(o,n4); }); printf("linear grid=148x%d x256: %.3f ms %.0f GB/s\n", bps, ms, gb/ms*1e3); }
+  for (int bps : {1,2,4,5,8}) { float ms = timeit([&]{ fill_warpcol<<<148*bps,256>>>(o,ncol,col4); }); printf("warp-column 40KB grid=148x%d x256: %.3f ms %.0f GB/s\n", bps, ms, gb/ms*1e3); }
+  for (int bps : {1,2,4,8}) { float ms = timeit([&]{ fill_ctacol<<<148*bps,256>>>(o,ncol,col4); }); printf("cta-column 40KB grid=148x%d x256: %.3f ms %.0f GB/s\n", bps, ms, gb/ms*1e3); }
+  for (int bps : {2,4,8}) { float ms = timeit([&]{ fill_warpcol_rd<<<148*bps,256>>>(o,in,ncol,col4); }); printf("warp-column + 6%% dependent read grid=148x%d: %.3f ms %.0f GB/s (w+r)\n", bps, ms, gb*1.0625/ms*1e3); }
+  return 0;
+}

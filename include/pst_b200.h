@@ -110,6 +110,10 @@ int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int6
                     int mode, double a, double b, int use_stats, double* d_stats,
                     float* d_K, int accumulate, int mirror,
                     void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* K = V V^T for a float matrix V [n_iid, n_sid] already in HBM (float32 / float64, C or F order): replaces the
+ * val.dot(val.T) of SnpData._read_kernel (snpdata.py:203-206).  Same fp16 hi/lo tensor-core path and workspace. */
+int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
+                      int mirror, void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
 /* Test/bench hook for the tensor-core stage alone: K_lower (+)= (hi+lo)(hi+lo)^T minus lo*lo^T, on
  * fp16 planes [n_pad, k_pad] (row-major, k_pad % 64 == 0, n_pad % 128 == 0). */
 int pstb_syrk_planes(const void* d_hi, const void* d_lo, int64_t n, int64_t n_pad, int64_t k_pad,

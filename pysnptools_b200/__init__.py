@@ -1,0 +1,17 @@
+"""pysnptools_b200: PySnpTools' genotype hot path (decode .bed -> standardize -> kinship) on B200 (sm_100a).
+
+Same names as the reference for this path::
+
+    from pysnptools_b200 import Bed, SnpData, Unit, Beta, SnpKernel
+    snpdata = Bed("all.bed", count_A1=False).read(order="F", dtype="float32")
+    snpdata = snpdata.standardize(Unit())
+    K = SnpKernel(Bed("all.bed", count_A1=False), Unit()).read()
+"""
+from . import _lib
+from .kernelreader import KernelData, SnpKernel
+from .snpreader import Bed, SnpData, SnpReader
+from .standardizer import Beta, BetaTrained, DiagKtoN, Identity, Standardizer, Unit, UnitTrained
+
+__all__ = ["Bed", "SnpData", "SnpReader", "Unit", "Beta", "UnitTrained", "BetaTrained", "Identity", "DiagKtoN", "Standardizer",
+           "SnpKernel", "KernelData"]
+__version__ = "0.1.0"

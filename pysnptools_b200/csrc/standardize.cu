@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(256) k_std_f(T* val, long long n_iid, long lon
 
 // ---- C order: column sums with lanes along SNPs ---------------------------------------------------------
 // work layout (doubles): [0,m) sum  [m,2m) count  [2m,3m) sum of squared deviations  [3m,4m) mean  [4m,5m) sd  [5m,6m) factor
+//                        [6m, 6m + 2*kMaxSplits*m) per-row-split partials (summed in a fixed order: deterministic results)
+constexpr int kMaxSplits = 16;
+
 template <typename T, int kPass>
 __global__ void __launch_bounds__(256) k_colacc_c(const T* val, long long n_iid, long long n_sid, long long rows_per_block,
                                                   double* work) {
@@ -96,9 +99,24 @@ __global__ void __launch_bounds__(256) k_colacc_c(const T* val, long long n_iid,
     if (ty == 0 && j < n_sid) {
         double t0 = 0.0, t1 = 0.0;
         for (int k = 0; k < 8; ++k) { t0 += sh[0][k][tx]; t1 += sh[1][k][tx]; }
-        if (kPass == 0) { atomicAdd(work + j, t0); atomicAdd(work + n_sid + j, t1); }
-        else atomicAdd(work + 2 * n_sid + j, t0);
+        double* part = work + 6 * n_sid + (long long)blockIdx.y * 2 * n_sid;
+        part[j] = t0;
+        part[n_sid + j] = t1;
     }
+}
+
+template <int kPass>
+__global__ void k_colsum_partials(long long n_sid, int splits, double* work) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sid) return;
+    double t0 = 0.0, t1 = 0.0;
+    for (int s = 0; s < splits; ++s) {
+        const double* part = work + 6 * n_sid + (long long)s * 2 * n_sid;
+        t0 += part[j];
+        t1 += part[n_sid + j];
+    }
+    if (kPass == 0) { work[j] = t0; work[n_sid + j] = t1; }
+    else work[2 * n_sid + j] = t0;
 }
 
 __global__ void k_finalize_c(long long n_sid, int mode, double a, double b, double lnB, int use_stats, double* stats, double* work) {
@@ -144,17 +162,22 @@ static int standardize_impl(T* d_val, int order, int64_t n_iid, int64_t n_sid, i
     if (!d_work) return fail("C-order standardize needs d_work (pstb_standardize_work_bytes)");
     const unsigned gx = (unsigned)((n_sid + 31) / 32);
     if (!use_stats) {
-        PSTB_CUDA(cudaMemsetAsync(d_work, 0, 3 * n_sid * sizeof(double), st));
         long long splits = ((long long)sms * 8 + gx - 1) / gx;
         if (splits < 1) splits = 1;
-        if (splits > 65535) splits = 65535;
+        if (splits > kMaxSplits) splits = kMaxSplits;
         long long rows_per_block = (n_iid + splits - 1) / splits;
         if (rows_per_block < 8) rows_per_block = 8;
-        const unsigned gy = (unsigned)((n_iid + rows_per_block - 1) / rows_per_block);
+        unsigned gy = (unsigned)((n_iid + rows_per_block - 1) / rows_per_block);
+        if (gy < 1) gy = 1;
+        const unsigned gs = (unsigned)((n_sid + 255) / 256);
         k_colacc_c<T, 0><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
         PSTB_AFTER_LAUNCH("k_colacc_c<0>");
+        k_colsum_partials<0><<<gs, 256, 0, st>>>(n_sid, (int)gy, d_work);
+        PSTB_AFTER_LAUNCH("k_colsum_partials<0>");
         k_colacc_c<T, 1><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
         PSTB_AFTER_LAUNCH("k_colacc_c<1>");
+        k_colsum_partials<1><<<gs, 256, 0, st>>>(n_sid, (int)gy, d_work);
+        PSTB_AFTER_LAUNCH("k_colsum_partials<1>");
     }
     k_finalize_c<<<(unsigned)((n_sid + 255) / 256), 256, 0, st>>>(n_sid, mode, a, b, lnB, use_stats, d_stats, d_work);
     PSTB_AFTER_LAUNCH("k_finalize_c");
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(256) k_pack(const T* val, long long si, long l
 
 using namespace pstb;
 
-extern "C" int64_t pstb_standardize_work_bytes(int64_t n_sid) { return (int64_t)(6 * (n_sid > 0 ? n_sid : 1) * sizeof(double)); }
+extern "C" int64_t pstb_standardize_work_bytes(int64_t n_sid) { return (int64_t)((6 + 2 * kMaxSplits) * (n_sid > 0 ? n_sid : 1) * sizeof(double)); }
 
 extern "C" int pstb_standardize(void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int mode, double a, double b,
                                 int apply_in_place, int use_stats, double* d_stats, void* d_work, void* stream) {

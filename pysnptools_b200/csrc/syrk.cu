@@ -402,6 +402,48 @@ __global__ void __launch_bounds__(256) k_convert(const float* K, long long total
         out[e] = (T)((double)K[e] * scale);
 }
 
+// ---- float matrices (SnpData._read_kernel: val.dot(val.T), snpdata.py:203-206) -> operand planes ----------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_absmax_float(const T* val, long long total, Scalars* sc) {
+    float m = 0.0f;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        double v = fabs((double)val[e]);
+        if (v == v && v < 1e300) m = fmaxf(m, __double2float_ru(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&sc->absmax_bits, __float_as_uint(m));
+}
+
+// val[i * si + j * sj], columns [c0, c0 + ns) -> hi/lo planes [n_pad][k_pad] (zero padded), 32 x 32 tiles through smem
+template <typename T>
+__global__ void __launch_bounds__(256) k_split_planes(const T* val, long long si, long long sj, long long n, long long c0, long long ns,
+                                                      const Scalars* sc, __half* hi, __half* lo, long long n_pad, long long k_pad) {
+    __shared__ float th[32][33], tl[32][33];
+    const long long ti = blockIdx.y, tj = blockIdx.x;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double scale = ldexp(1.0, scale_exponent(sc->absmax_bits));
+    const bool row_fast = (si == 1);                       // F order: consecutive individuals are adjacent in memory
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = ti * 32 + (row_fast ? tx : r), j = tj * 32 + (row_fast ? r : tx);
+        double x = 0.0;
+        if (i < n && j < ns) x = (double)val[i * si + (c0 + j) * sj] * scale;
+        if (fabs(x) > 60000.0) x = 0.0;
+        const __half h = __float2half_rn((float)x);
+        const float hf = __half2float(h), lf = (float)(x - (double)hf);
+        if (row_fast) { th[r][tx] = hf; tl[r][tx] = lf; }       // [j_local][i_local]
+        else { th[tx][r] = hf; tl[tx][r] = lf; }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = ti * 32 + r, j = tj * 32 + tx;      // write with the SNP index fastest
+        if (i < n_pad && j < k_pad) {
+            hi[i * k_pad + j] = __float2half_rn(th[tx][r]);
+            lo[i * k_pad + j] = __float2half_rn(tl[tx][r]);
+        }
+    }
+}
+
 // ---- host helpers --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -615,6 +657,49 @@ extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_
         const long long ptiles = (k_pad / PT_S) * (n_pad / PT_I);
         k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
         PSTB_AFTER_LAUNCH("k_planes");
+        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st);
+        if (rc) return rc;
+    }
+    if (mirror) return pstb_mirror_lower(d_K, n, n, stream);
+    return 0;
+}
+
+extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
+                                 int mirror, void* d_work, int64_t work_bytes, int64_t chunk, void* stream) {
+    if (n_iid < 0 || n_sid < 0) return fail("negative shape");
+    if (n_iid == 0) return 0;
+    if (!d_K) return fail("d_K is NULL");
+    if (dtype != PSTB_F32 && dtype != PSTB_F64) return fail("float kernel needs float32 or float64 values");
+    if (order != PSTB_ORDER_C && order != PSTB_ORDER_F) return fail("bad order");
+    if (chunk < BK || chunk % BK) return fail("chunk must be a positive multiple of %d", BK);
+    if (work_bytes < pstb_kernel_workspace_bytes(n_iid, chunk) || !d_work) return fail("workspace too small (pstb_kernel_workspace_bytes)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long n = n_iid, n_pad = round_up(n, ROW_PAD);
+    if (n_sid == 0) {
+        if (!accumulate) PSTB_CUDA(cudaMemsetAsync(d_K, 0, (size_t)n * n * sizeof(float), st));
+        return 0;
+    }
+    if (!d_val) return fail("d_val is NULL");
+    const long long k_cap = round_up(chunk, BK);
+    char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_work) + 1023) & ~(uintptr_t)1023);
+    __half* hi = reinterpret_cast<__half*>(w);
+    __half* lo = hi + n_pad * k_cap;
+    Scalars* sc = reinterpret_cast<Scalars*>(lo + n_pad * k_cap);
+    const long long si = (order == PSTB_ORDER_C) ? n_sid : 1, sj = (order == PSTB_ORDER_C) ? 1 : n_iid;
+    const long long total = n * n_sid;
+    PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    long long g = (total + 255) / 256;
+    if (g > (long long)sm_count_cached() * 16) g = (long long)sm_count_cached() * 16;
+    if (dtype == PSTB_F32) k_absmax_float<float><<<(unsigned)g, 256, 0, st>>>((const float*)d_val, total, sc);
+    else k_absmax_float<double><<<(unsigned)g, 256, 0, st>>>((const double*)d_val, total, sc);
+    PSTB_AFTER_LAUNCH("k_absmax_float");
+    for (long long c0 = 0; c0 < n_sid; c0 += chunk) {
+        const long long ns = (c0 + chunk <= n_sid) ? chunk : n_sid - c0;
+        const long long k_pad = round_up(ns, BK);
+        dim3 grid((unsigned)(k_pad / 32), (unsigned)(n_pad / 32));
+        if (dtype == PSTB_F32) k_split_planes<float><<<grid, 256, 0, st>>>((const float*)d_val, si, sj, n, c0, ns, sc, hi, lo, n_pad, k_pad);
+        else k_split_planes<double><<<grid, 256, 0, st>>>((const double*)d_val, si, sj, n, c0, ns, sc, hi, lo, n_pad, k_pad);
+        PSTB_AFTER_LAUNCH("k_split_planes");
         int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st);
         if (rc) return rc;
     }

@@ -94,6 +94,8 @@ class PackedStore(object):
         """``packed``: uint8 ndarray ``[sid_count, ceil(iid_count/4)]`` (file bytes after the 3-byte header)."""
         _lib.require_gpu()
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if not packed.flags.writeable:
+            packed = packed.copy()                      # torch.from_numpy wants a writable buffer (memory-mapped files are not)
         sid_count, rec = packed.shape if packed.ndim == 2 else (0, 0)
         assert rec == (iid_count + 3) // 4 or sid_count == 0
         ld = int(lib.pstb_packed_ld(iid_count))
@@ -237,6 +239,31 @@ def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=(
                                   int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), K.data_ptr(),
                                   int(bool(accumulate)), int(bool(mirror)), work.data_ptr(), wbytes, chunk, _stream()))
     return K, d_stats
+
+
+def float_kernel(val, chunk=None, K=None, accumulate=False, mirror=True):
+    """``K = V V^T`` of a CUDA float tensor [n_iid, n_sid] (C- or F-contiguous) on the tensor cores (float32 result)."""
+    _lib.require_gpu()
+    n, m = val.shape
+    if val.is_contiguous():
+        order = _lib.ORDER_C
+    elif val.t().is_contiguous():
+        order = _lib.ORDER_F
+    else:
+        val, order = val.contiguous(), _lib.ORDER_C
+    code = {torch.float32: _lib.F32, torch.float64: _lib.F64}[val.dtype]
+    dev = val.device
+    with torch.cuda.device(dev):
+        if K is None:
+            K = torch.zeros((n, n), dtype=torch.float32, device=dev)
+            accumulate = False
+        if chunk is None:
+            chunk = default_kernel_chunk(n, m)
+        wbytes = int(lib.pstb_kernel_workspace_bytes(n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(lib.pstb_float_kernel(val.data_ptr(), code, order, n, m, K.data_ptr(), int(bool(accumulate)), int(bool(mirror)),
+                                    work.data_ptr(), wbytes, chunk, _stream()))
+    return K
 
 
 def default_kernel_chunk(n_iid, n_sid):

@@ -1,0 +1,172 @@
+"""SnpKernel / KernelData: the reference's ``pysnptools.kernelreader`` surface for the hot path.
+
+Mirrors ``SnpKernel`` (kernelreader/snpkernel.py:43-132), ``KernelReader.read`` (kernelreader.py:245-302) and
+``KernelData`` (kerneldata.py:71-159).  The kernel itself is computed by ``SnpReader._read_kernel`` on the GPU.
+"""
+import numpy as np
+
+from .snpreader import _compose, _resolve_indexer
+from .standardizer import DiagKtoN, Identity, _is_tensor
+
+
+class KernelData(object):
+    """In-memory kernel: ``val`` [iid0_count, iid1_count] + iids."""
+    _is_kernel = True
+
+    def __init__(self, iid=None, iid0=None, iid1=None, val=None, name=None, parent_string=None, xp=None):
+        assert (iid is None) != (iid0 is None and iid1 is None), "Either 'iid' or both 'iid0' 'iid1' must be provided."
+        assert val is not None, "'val' must not be None"
+        if iid is not None:
+            self._row = self._col = np.array(iid, dtype=str).reshape(-1, 2)
+        else:
+            self._row = np.array(iid0, dtype=str).reshape(-1, 2)
+            self._col = np.array(iid1, dtype=str).reshape(-1, 2)
+        assert tuple(val.shape) == (len(self._row), len(self._col)), "val shape must match the iid counts"
+        self._val = val
+        self._name = name or parent_string or ""
+        self._std_string_list = []
+
+    def __repr__(self):
+        parts = ([self._name] if self._name else []) + self._std_string_list
+        return "KernelData({0})".format(",".join(parts))
+
+    @property
+    def val(self):
+        return self._val
+
+    @val.setter
+    def val(self, new_value):
+        self._val = new_value
+
+    @property
+    def iid0(self):
+        return self._row
+
+    @property
+    def iid1(self):
+        return self._col
+
+    @property
+    def row(self):
+        return self._row
+
+    @property
+    def col(self):
+        return self._col
+
+    @property
+    def iid(self):
+        assert self._row is self._col or np.array_equal(self._row, self._col), "When 'iid' is used, iid0 must be the same as iid1"
+        return self._row
+
+    @property
+    def iid_count(self):
+        return len(self.iid)
+
+    @property
+    def iid0_count(self):
+        return len(self._row)
+
+    @property
+    def iid1_count(self):
+        return len(self._col)
+
+    @property
+    def shape(self):
+        return (self.iid0_count, self.iid1_count)
+
+    def read(self, order="A", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
+        val = self._val
+        if _is_tensor(val):
+            val = val.cpu().numpy()
+        dtype = np.dtype(dtype)
+        ok = order == "A" or val.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+        if not (view_ok and ok and val.dtype == dtype):
+            val = np.array(val, dtype=dtype, order=order)
+        return KernelData(iid0=self._row, iid1=self._col, val=val, name=str(self))
+
+    def __getitem__(self, indexer):
+        r, c = indexer if isinstance(indexer, tuple) else (indexer, indexer)
+        ri, ci = _resolve_indexer(r, self.iid0_count), _resolve_indexer(c, self.iid1_count)
+        val = self._val
+        if ri is not None:
+            val = val[ri]
+        if ci is not None:
+            val = val[:, ci]
+        return KernelData(iid0=self._row if ri is None else self._row[ri], iid1=self._col if ci is None else self._col[ci], val=val)
+
+    def standardize(self, standardizer=DiagKtoN(), return_trained=False, force_python_only=False, num_threads=None):
+        """In place; the diagonal sums to iid_count afterwards (kerneldata.py:136-159)."""
+        self._std_string_list.append(str(standardizer))
+        return standardizer.standardize(self, return_trained=return_trained, force_python_only=force_python_only, num_threads=num_threads)
+
+
+class SnpKernel(object):
+    """Lazy ``K = X X^T`` of a standardized :class:`SnpReader` (kernelreader/snpkernel.py)."""
+
+    def __init__(self, snpreader, standardizer=None, test=None, block_size=None):
+        assert standardizer is not None, "'standardizer' must be provided"
+        assert test is None, "test= (train x test kernels) is not on the GPU path yet"
+        self.snpreader = snpreader
+        self.standardizer = standardizer
+        self.block_size = block_size
+        self._index = None          # subset of the kernel's iids applied AFTER the kernel is computed
+
+    def __repr__(self):
+        s = "SnpKernel({0},standardizer={1}".format(self.snpreader, self.standardizer)
+        if self.block_size is not None:
+            s += ",block_size={0}".format(self.block_size)
+        return s + ")"
+
+    @property
+    def row(self):
+        iid = self.snpreader.iid
+        return iid if self._index is None else iid[self._index]
+
+    col = row
+    iid = row
+    iid0 = row
+    iid1 = row
+
+    @property
+    def iid_count(self):
+        return len(self.row)
+
+    @property
+    def shape(self):
+        return (self.iid_count, self.iid_count)
+
+    def __getitem__(self, indexer):
+        r, c = indexer if isinstance(indexer, tuple) else (indexer, indexer)
+        ri, ci = _resolve_indexer(r, self.iid_count), _resolve_indexer(c, self.iid_count)
+        same = (ri is None and ci is None) or (ri is not None and ci is not None and np.array_equal(ri, ci))
+        assert same, "SnpKernel supports the same indexer on both axes"
+        if ri is None:
+            return self
+        if self.standardizer.is_constant and self._index is None:
+            # constant standardizer: push the subset into the reader (snpkernel.py:90-101)
+            return SnpKernel(self.snpreader[ri, :], self.standardizer, block_size=self.block_size)
+        out = SnpKernel(self.snpreader, self.standardizer, block_size=self.block_size)
+        out._index = _compose(self._index, ri)
+        return out
+
+    def _read(self, order, dtype, force_python_only, view_ok, num_threads, return_trained=False):
+        res = self.snpreader._read_kernel(self.standardizer, self.block_size, order, dtype, force_python_only, view_ok,
+                                          return_trained=return_trained, num_threads=num_threads)
+        val, trained = res if return_trained else (res, None)
+        if self._index is not None:
+            # standardize on all iids, then slice (kernelreader/test.py:235-247)
+            val = np.array(val[self._index][:, self._index], order="F" if order == "F" else "C")
+        return (val, trained) if return_trained else val
+
+    def read(self, order="A", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
+        val = self._read(order, np.dtype(dtype), force_python_only, view_ok, num_threads)
+        return KernelData(iid=self.row, val=val, name=str(self))
+
+    def _read_with_standardizing(self, to_kerneldata, kernel_standardizer=DiagKtoN(), return_trained=False, num_threads=None):
+        """FaST-LMM's entry (snpkernel.py:104-132): kernel + trained SNP standardizer + trained kernel standardizer."""
+        assert to_kerneldata, "only the KernelData form is on the GPU path"
+        val, snp_trained = self._read("A", np.dtype(np.float64), False, False, num_threads, return_trained=True)
+        kernel = KernelData(iid=self.row, val=val, name=str(self))
+        kernel, kernel_trained = kernel.standardize(kernel_standardizer, return_trained=True, num_threads=num_threads)
+        return (kernel, snp_trained, kernel_trained) if return_trained else kernel

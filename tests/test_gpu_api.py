@@ -1,0 +1,230 @@
+"""GPU: the reference-facing API (Bed / SnpData / Unit / Beta / SnpKernel / bed_reader shim) against goldens + oracle.
+
+Reads like the reference's own tests (pysnptools/test.py, kernelreader/test.py) for the hot path.
+"""
+import os
+import pickle
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import DATA_DIR, ROOT, SHAPES, fixture_packed, i8_to_float
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter("ignore", DeprecationWarning)
+
+
+def _bed(name, **kw):
+    from pysnptools_b200 import Bed
+    kw.setdefault("count_A1", False)
+    return Bed(os.path.join(DATA_DIR, name + ".bed"), **kw)
+
+
+def rel_fro(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_bed_read_respects_inputs(name, golden):
+    """test_respect_read_inputs (test.py:912-1005) + test_bed_int8 (288-324): dtype / order contract and values."""
+    want = golden[name + "_decode_i8"]
+    bed = _bed(name)
+    for order in ("F", "C", "A"):
+        for dtype in (np.float32, np.float64):
+            d = bed.read(order=order, dtype=dtype)
+            assert d.val.dtype == dtype and d.val.flags["C_CONTIGUOUS" if order == "C" else "F_CONTIGUOUS"]
+            assert np.array_equal(d.val, i8_to_float(want, dtype), equal_nan=True)
+            assert d.iid.shape == (want.shape[0], 2) and len(d.sid) == want.shape[1]
+        d8 = bed.read(order=order, dtype="int8", _require_float32_64=False)
+        assert d8.val.dtype == np.int8 and np.array_equal(d8.val, want)
+    a1 = _bed(name, count_A1=True).read(dtype="int8", _require_float32_64=False).val
+    assert np.array_equal(a1, golden[name + "_decode_A1_i8"]) if name + "_decode_A1_i8" in golden.files else True
+    obs = want != -127
+    assert np.array_equal(a1[obs], 2 - want[obs])                                   # test.py:226-232: A1 == 2 - A2
+
+
+def test_bed_subsets(golden, oracle):
+    bed = _bed("n300")
+    packed, n, m = fixture_packed("n300")
+    sub = bed[::-2, [5, 3, 3, -1]][1:40:3, :].read(order="C", dtype=np.float32)
+    assert np.array_equal(sub.val, golden["n300_subset_rev_f32"], equal_nan=True)
+    assert np.array_equal(sub.sid, bed.sid[[5, 3, 3, 1014]])
+    rev = bed[::-1, ::-3].read()                                                    # reversed strides (test.py:812-862)
+    assert np.array_equal(rev.val, oracle.decode(packed, n, np.arange(n)[::-1], np.arange(m)[::-3]), equal_nan=True)
+    mask = np.arange(n) % 7 == 0
+    assert np.array_equal(bed[mask, 2:5].read().val, oracle.decode(packed, n, np.nonzero(mask)[0], [2, 3, 4]), equal_nan=True)
+    one = bed[np.int64(3), 4].read()                                                # test_scalar_index (test.py:326-331)
+    assert one.val.shape == (1, 1)
+    assert bed[[], :].read().val.shape == (0, m) and bed[:, []].read().val.shape == (n, 0)
+    with pytest.raises(IndexError):
+        bed[[n], :]
+    dev = bed[:, :10].read(dtype=np.float32, to_device=True)
+    assert dev.val.is_cuda and np.array_equal(dev.val.cpu().numpy(), oracle.decode(packed, n, None, np.arange(10), dtype=np.float32))
+    clone = pickle.loads(pickle.dumps(bed))
+    assert np.array_equal(clone[:5, :5].read().val, bed[:5, :5].read().val)
+
+
+def test_standardize_unit_and_beta(golden):
+    """test_standardize_bed (test.py:582-640), doctests unit.py:18-20 / beta.py:19-23 / unittrained.py:19-30."""
+    from pysnptools_b200 import Beta, Unit
+    bed = _bed("n300")
+    for tag, s in (("unit", Unit()), ("beta_1_25", Beta(1, 25)), ("beta_2_10", Beta(2, 10))):
+        want, wst = golden["n300_{0}_val".format(tag)], golden["n300_{0}_stats".format(tag)]
+        for order in ("F", "C"):
+            for dtype, tol in ((np.float64, 1e-11), (np.float32, 1e-5)):
+                d = bed.read(order=order, dtype=dtype)
+                out, trained = d.standardize(s, return_trained=True)
+                assert out is d and not np.isnan(d.val).any()
+                np.testing.assert_allclose(d.val[:, :want.shape[1]], want, rtol=tol, atol=tol)
+                np.testing.assert_allclose(trained.stats, wst, rtol=1e-12 if dtype == np.float64 else 1e-6)
+                assert trained.stats.dtype == dtype and trained.is_constant
+                arr = bed.read(order=order, dtype=dtype).val                         # bare ndarray (deprecated but used by the tests)
+                s.standardize(arr)
+                assert np.array_equal(arr, d.val)
+    d = bed.read().standardize(Unit())
+    assert "{0:.6f}".format(d.val[0, 0]) == "0.229416" and repr(d).endswith("Unit())")
+    assert "{0:.6f}".format(bed.read().standardize(Beta(1, 25)).val[0, 0]) == "0.680802"
+    train, trained = bed[10:, :].read().standardize(Unit(), return_trained=True)
+    assert "{0:.6f}".format(train.val[0, 0]) == "0.233550"
+    test = bed[:10, :].read().standardize(trained)
+    np.testing.assert_allclose(test.val, golden["n300_trained_unit_test_val"], rtol=1e-11, atol=1e-13)
+    testb = bed[:10, :].read().standardize(bed[10:, :].read().standardize(Beta(1, 25), return_trained=True)[1])
+    np.testing.assert_allclose(testb.val, golden["n300_trained_beta_test_val"], rtol=1e-11, atol=1e-13)
+    # trained standardizer re-indexed by sid
+    part = bed[:10, [7, 2]].read().standardize(trained)
+    np.testing.assert_allclose(part.val, golden["n300_trained_unit_test_val"][:, [7, 2]], rtol=1e-11, atol=1e-13)
+
+
+def test_nan_and_snc_cases(golden):
+    """NaNCNCTestCases (test.py:1296-1358) and kernelreader test_cpp_std (56-110)."""
+    from pysnptools_b200 import Beta, SnpData, Unit
+    x = golden["n300_nancnc_input"]
+    iid = [["0", "i{0}".format(k)] for k in range(x.shape[0])]
+    sid = ["s{0}".format(k) for k in range(x.shape[1])]
+    for tag, s in (("unit", Unit()), ("beta_1_25", Beta(1, 25))):
+        for dtype, rtol in ((np.float64, 1e-12), (np.float32, 1e-4)):
+            for order in ("C", "F"):
+                d = SnpData(iid=iid, sid=sid, val=np.array(x, dtype=dtype, order=order))
+                d, trained = d.standardize(s, return_trained=True)
+                assert d.val[0, 0] == 0 and np.all(d.val[:, 1] == 0) and np.isinf(trained.stats[1, 1])
+                np.testing.assert_allclose(d.val, golden["n300_nancnc_{0}_val".format(tag)], rtol=rtol, atol=1e-6 if dtype == np.float32 else 1e-13)
+                again = SnpData(iid=iid, sid=sid, val=np.array(x, dtype=dtype, order=order)).standardize(trained)
+                np.testing.assert_allclose(again.val, d.val, rtol=1e-12 if dtype == np.float64 else 1e-5, atol=1e-14 if dtype == np.float64 else 1e-6)   # f32 stats are rounded, as in the reference
+
+
+def test_snp_kernel(golden):
+    """doctests snpreader.py:308-313 / snpkernel.py:39-41, test_merge_std, test_respect_inputs, test_subset, test_some_std."""
+    from pysnptools_b200 import Beta, DiagKtoN, Identity, SnpKernel, Unit
+    bed = _bed("n300")
+    kd = bed.read_kernel(Unit())
+    assert kd.val.dtype == np.float64 and kd.iid_count == 300 and np.array_equal(kd.iid, bed.iid)
+    assert rel_fro(kd.val, golden["n300_unit_K"]) < 1e-5 and abs(kd.val[0, 0] - 901.421836) < 1e-2
+    for block_size in (None, 1, 100, 500):
+        for order in ("F", "C", "A"):
+            for dtype in (np.float64, np.float32):
+                k = SnpKernel(bed, Unit(), block_size=block_size).read(order=order, dtype=dtype)
+                assert k.val.dtype == dtype and k.val.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+                assert rel_fro(k.val.astype(np.float64), golden["n300_unit_K"]) < 1e-5
+    assert rel_fro(bed.read_kernel(Beta(1, 25), block_size=500).val, golden["n300_beta_1_25_K"]) < 1e-5
+    assert rel_fro(_bed("dbx").read_kernel(Unit(), block_size=10).val, golden["dbx_unit_K"]) < 1e-5
+    toy = SnpKernel(_bed("toydata"), Unit()).read()
+    assert rel_fro(toy.val, golden["toydata_unit_K_shipped"]) < 1e-5
+    toy.standardize(DiagKtoN())
+    assert abs(np.trace(toy.val) - 500) < 1e-6 and abs(toy.val[0, 0] - float(golden["toydata_unit_K_diagKtoN_00"])) < 1e-5
+    every2 = SnpKernel(bed, Unit())[::2].read()                                      # standardize on all iids, then slice
+    assert rel_fro(every2.val, golden["n300_unit_K_every2"]) < 1e-5 and every2.iid_count == 150
+    # in-memory SnpData kernel (val.dot(val.T)) == kernel from the file (test_some_std, test.py:530-553)
+    sd = bed.read().standardize(Unit())
+    k_mem = sd.read_kernel(Identity())
+    assert rel_fro(k_mem.val, golden["n300_unit_K"]) < 1e-5
+    k_mem2 = bed.read(dtype=np.float32, order="C").read_kernel(Unit())
+    assert rel_fro(k_mem2.val, golden["n300_unit_K"]) < 1e-5
+    kernel, snp_trained, kernel_trained = SnpKernel(bed, Unit(), block_size=300)._read_with_standardizing(True, return_trained=True)
+    np.testing.assert_allclose(snp_trained.stats, golden["n300_unit_stats"], rtol=1e-12)
+    assert abs(np.trace(kernel.val) - 300) < 1e-6 and abs(kernel_trained.factor - 300 / np.trace(golden["n300_unit_K"])) < 1e-7
+    # trained (constant) standardizer: subset pushed into the reader
+    ktr = SnpKernel(bed, snp_trained)[:10].read()
+    want = golden["n300_trained_unit_test_val"]
+    _, full_trained = bed[10:, :].read().standardize(Unit(), return_trained=True)
+    ktr2 = SnpKernel(bed, full_trained)[:10].read()
+    assert rel_fro(ktr2.val, want @ want.T) < 1e-5 and ktr.val.shape == (10, 10)
+
+
+def test_bed_write_round_trips(tmp_path, oracle):
+    """test_write_bed_f64cpp_* / test_write_x_x_cpp (test.py:671-765): 0/1/2/5 iids, NaN, both count_A1, illegal values."""
+    from pysnptools_b200 import Bed, SnpData
+    for n in (0, 1, 2, 5, 190):
+        for m in (0, 3, 20):
+            packed = oracle.synth_packed(n, 0, m, 0.2, seed=n + m) if n and m else np.zeros((m, (n + 3) // 4), np.uint8)
+            val = oracle.decode(packed, n) if n and m else np.zeros((n, m))
+            sd = SnpData(iid=[["f", "i{0}".format(k)] for k in range(n)], sid=["s{0}".format(k) for k in range(m)], val=val,
+                         pos=[[1, 0.5, 100 + k] for k in range(m)])
+            for a1 in (False, True):
+                back = Bed.write(str(tmp_path / "w_{0}_{1}_{2}".format(n, m, a1)), sd, count_A1=a1)
+                got = back.read()
+                assert got.val.shape == (n, m) and np.array_equal(got.val, val, equal_nan=True)
+                assert np.array_equal(got.iid, sd.iid) and np.array_equal(got.sid, sd.sid) and np.array_equal(got.pos, sd.pos)
+    bad = SnpData(iid=[["f", "a"], ["f", "b"]], sid=["s"], val=np.array([[5.0], [1.0]]))
+    with pytest.raises(ValueError):
+        Bed.write(str(tmp_path / "bad"), bad, count_A1=False)
+
+
+def test_bed_reader_shim(golden, oracle, tmp_path):
+    """The nine bed_reader symbols as the reference calls them (bed.py:337-343, standardizer.py:114,120, util/__init__.py:341-375)."""
+    sys.path.insert(0, os.path.join(ROOT, "pysnptools_b200", "compat"))
+    try:
+        import bed_reader
+    finally:
+        sys.path.pop(0)
+    packed, n, m = fixture_packed("dbx")
+    ob = bed_reader.open_bed(os.path.join(DATA_DIR, "dbx.bed"), properties={}, count_A1=False, num_threads=None, skip_format_check=False)
+    ii, si = np.arange(n, dtype=np.uintp)[::-1], np.array([3, 1, 99], dtype=np.uintp)
+    for order in ("F", "C"):
+        for dtype in (np.float32, np.float64, np.int8):
+            val = ob.read(index=(ii, si), order=order, dtype=dtype, force_python_only=False, num_threads=4)
+            assert val.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+            assert np.array_equal(val, oracle.decode(packed, n, ii, si, False, dtype), equal_nan=dtype != np.int8)
+    assert np.array_equal(ob.read(index=(None, None), dtype=np.int8), golden["dbx_decode_i8"])
+    raw = oracle.decode(packed, n)
+    for fn, dtype in ((bed_reader.standardize_f64, np.float64), (bed_reader.standardize_f32, np.float32)):
+        for order in ("F", "C"):
+            snps = np.array(raw, dtype=dtype, order=order)
+            stats = np.empty((m, 2), dtype=dtype, order=order)
+            fn(snps, True, 1.0, 25.0, True, False, stats, 2)
+            np.testing.assert_allclose(snps, golden["dbx_beta_1_25_val"], rtol=1e-11 if dtype == np.float64 else 1e-5, atol=1e-6 if dtype == np.float32 else 1e-13)
+            np.testing.assert_allclose(stats, golden["dbx_beta_1_25_stats"], rtol=1e-12 if dtype == np.float64 else 1e-6)
+            again = np.array(raw, dtype=dtype, order=order)
+            fn(again, True, 1.0, 25.0, True, True, stats, 2)
+            np.testing.assert_allclose(again, snps, rtol=1e-6, atol=1e-7)
+    v3 = np.random.default_rng(0).normal(size=(9, 7, 3))
+    rows, cols = np.array([8, 0, 3], dtype=np.uintp), np.array([6, 6, 1, 0], dtype=np.uintp)
+    out = np.full((3, 4, 3), np.nan, order="F")
+    bed_reader.subset_f64_f64(np.asfortranarray(v3), rows, cols, out, 1)
+    assert np.array_equal(out, v3[rows][:, cols])
+    out32 = np.full((3, 4, 3), np.nan, dtype=np.float64)
+    bed_reader.subset_f32_f64(v3.astype(np.float32), rows, cols, out32, 1)
+    assert np.array_equal(out32, v3.astype(np.float32)[rows][:, cols].astype(np.float64))
+    path = str(tmp_path / "shim.bed")
+    bed_reader.to_bed(path, raw, properties={"fid": ["f"] * n, "iid": ["i%d" % k for k in range(n)], "sid": ["s%d" % k for k in range(m)]}, count_A1=False)
+    back = bed_reader.open_bed(path, count_A1=False)
+    assert np.array_equal(back.read(dtype=np.float64), raw, equal_nan=True) and back.sid[3] == "s3"
+    with pytest.raises(ValueError):
+        bed_reader.to_bed(str(tmp_path / "bad.bed"), np.full((3, 2), 7.0), count_A1=False)
+
+
+def test_util_sub_matrix(oracle):
+    """test_sub_matrix (util/test.py:118-128) and PstReader test_every_read (pstreader/test.py:118-133)."""
+    from pysnptools_b200.util import sub_matrix
+    rng = np.random.default_rng(1)
+    for shape in ((11, 9), (11, 9, 1), (11, 9, 3)):
+        src = rng.normal(size=shape)
+        rows, cols = np.arange(10, -1, -2), np.arange(8, -1, -1)
+        for order_from in ("C", "F"):
+            for order_to in ("C", "F"):
+                for dt_from, dt_to in ((np.float64, np.float64), (np.float32, np.float64), (np.float32, np.float32)):
+                    a = np.array(src, dtype=dt_from, order=order_from)
+                    out = sub_matrix(a, rows, cols, order=order_to, dtype=dt_to)
+                    assert out.dtype == dt_to and out.flags["C_CONTIGUOUS" if order_to == "C" else "F_CONTIGUOUS"]
+                    assert np.array_equal(out, a[rows][:, cols].astype(dt_to))

@@ -1,0 +1,158 @@
+"""CPU: host-side logic of the reference-facing layer (no GPU): indexers, metadata, pickling, sharding over gloo."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import DATA_DIR, ROOT, fixture_packed
+
+
+def test_index_resolution_matches_numpy_semantics():
+    from pysnptools_b200.snpreader import _compose, _resolve_indexer
+    n = 37
+    base = np.arange(n)
+    cases = [slice(None), slice(2, 30, 3), slice(None, None, -2), [3, -1, 3], np.array([True, False] * 18 + [True]), 5, np.int64(-4),
+             np.array([], dtype=int), range(4, 9)]
+    for c in cases:
+        got = _resolve_indexer(list(c) if isinstance(c, range) else c, n)
+        want = base[[int(c)]] if isinstance(c, (int, np.integer)) else base[list(c) if isinstance(c, range) else c]
+        assert np.array_equal(base if got is None else got, want)
+    with pytest.raises(IndexError):
+        _resolve_indexer([n], n)
+    outer = _resolve_indexer(slice(None, None, -2), n)
+    inner = _resolve_indexer(slice(1, 15, 3), len(outer))
+    assert np.array_equal(_compose(outer, inner), base[::-2][1:15:3])
+    assert _compose(None, None) is None and np.array_equal(_compose(None, inner), inner)
+
+
+def test_bed_metadata_subsets_and_pickle():
+    with pytest.warns(FutureWarning):
+        from pysnptools_b200 import Bed
+        Bed(os.path.join(DATA_DIR, "n300.bed"))
+    from pysnptools_b200 import Bed
+    bed = Bed(os.path.join(DATA_DIR, "n300"), count_A1=False)
+    assert (bed.iid_count, bed.sid_count) == (300, 1015) and bed.shape == (300, 1015)
+    assert bed.iid.shape == (300, 2) and bed.iid.dtype.kind == "U" and bed.pos.shape == (1015, 3)
+    assert list(bed.iid[0]) == ["POP1", "0"] and bed.sid[0] == "1_12" and np.isnan(bed.pos[0, 2])
+    sub = bed[::-2, [5, 3, 3, -1]][1:40:3, :]
+    assert (sub.iid_count, sub.sid_count) == (13, 4)
+    root, ii, si = sub._root_and_indices()
+    assert root is bed and np.array_equal(ii, np.arange(300)[::-2][1:40:3]) and np.array_equal(si, [5, 3, 3, 1014])
+    assert np.array_equal(sub.iid, bed.iid[ii]) and np.array_equal(sub.sid, bed.sid[si]) and np.array_equal(sub.pos, bed.pos[si], equal_nan=True)
+    mask = np.zeros(300, dtype=bool)
+    mask[[2, 7]] = True
+    assert np.array_equal(bed[mask, :].iid, bed.iid[[2, 7]])
+    assert bed[3, np.int64(4)].shape == (1, 1)
+    clone = pickle.loads(pickle.dumps(bed))
+    assert repr(clone) == repr(bed) and clone.sid_count == 1015
+    assert np.array_equal(bed.sid_to_index(["1_34", "1_12"]), [1, 0])
+    given = Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=True, iid=bed.iid, sid=bed.sid, pos=bed.pos, skip_format_check=True)
+    assert given.sid_count == 1015 and given.count_A1 is True
+
+
+def test_bad_files_raise_value_error(tmp_path):
+    from pysnptools_b200 import Bed
+    packed, n, m = fixture_packed("gen1")
+    stem = str(tmp_path / "bad")
+    for ext in (".fam", ".bim"):
+        with open(os.path.join(DATA_DIR, "gen1" + ext)) as f, open(stem + ext, "w") as g:
+            g.write(f.read())
+    with open(stem + ".bed", "wb") as f:
+        f.write(b"\x00\x00\x00" + packed.tobytes())
+    with pytest.raises(ValueError):
+        Bed(stem, count_A1=False)._packed_host()
+    with open(stem + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + packed.tobytes()[:-1])
+    with pytest.raises(ValueError):
+        Bed(stem, count_A1=False)._packed_host()
+    with open(stem + ".bim", "w") as g:
+        g.write("Q7\ts1\t0\t1\tA\tC\n" * m)
+    with pytest.raises(ValueError):
+        Bed(stem, count_A1=False).pos
+
+
+def test_no_python_path_and_trained_stats_lookup():
+    from pysnptools_b200 import Beta, SnpData, Unit, UnitTrained
+    d = SnpData(iid=[["f", "a"], ["f", "b"]], sid=["s1", "s2"], val=np.array([[0.0, 1.0], [2.0, np.nan]]))
+    assert d.val.dtype == np.float64 and d.iid_count == 2 and repr(d) == "SnpData()"
+    for s in (Unit(), Beta(1, 25)):
+        with pytest.raises(NotImplementedError):
+            s.standardize(d, force_python_only=True)
+    t = UnitTrained(np.array(["s1", "s2", "s3"]), np.array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]))
+    assert t.is_constant and np.array_equal(t._trained_stats_for(np.array(["s3", "s1"])), [[5.0, 6.0], [1.0, 2.0]])
+    merged = Unit()._merge_trained([UnitTrained(np.array(["a"]), np.array([[0.0, 1.0]])), UnitTrained(np.array(["b"]), np.array([[2.0, 3.0]]))])
+    assert list(merged.sid) == ["a", "b"] and merged.stats.shape == (2, 2)
+    assert repr(Beta(1, 25)) == "Beta(a=1,b=25)" and repr(Unit()) == "Unit()"
+
+
+def test_compat_bed_reader_metadata():
+    sys.path.insert(0, os.path.join(ROOT, "pysnptools_b200", "compat"))
+    try:
+        import bed_reader
+    finally:
+        sys.path.pop(0)
+    for name in ("open_bed", "to_bed", "get_num_threads", "standardize_f32", "standardize_f64", "subset_f64_f64", "subset_f32_f64", "subset_f32_f32"):
+        assert hasattr(bed_reader, name)
+    props = {"father": None, "mother": None, "sex": None, "pheno": None, "allele_1": None, "allele_2": None}
+    ob = bed_reader.open_bed(os.path.join(DATA_DIR, "n300.bed"), properties=props, count_A1=False, num_threads=None, skip_format_check=False)
+    assert ob.shape == (300, 1015) and ob.fid[0] == "POP1" and ob.chromosome.dtype.kind == "U" and ob.bp_position.dtype == np.int64
+    with pytest.raises(AttributeError):
+        ob.father
+    assert pickle.loads(pickle.dumps(ob)).sid_count == 1015
+    os.environ["PST_NUM_THREADS"] = "3"
+    try:
+        assert bed_reader.get_num_threads() == 3 and bed_reader.get_num_threads(5) == 5
+    finally:
+        del os.environ["PST_NUM_THREADS"]
+
+
+def test_shard_ranges_partition():
+    from pysnptools_b200.parallel import shard_range
+    for count in (0, 1, 7, 1015, 500000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(count, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == count
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import bed_oracle
+    from pysnptools_b200.parallel import allgather_rows, allreduce_sum_, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, m = 300, 1015
+    packed = bed_oracle.read_packed(os.path.join(DATA_DIR, "n300.bed"), n, m)
+    lo, hi = shard_range(m, rank, world)
+    K_r, st_r = bed_oracle.read_kernel(packed[lo:hi], n)          # this rank's partial kernel (SNP shard)
+    K = allreduce_sum_(torch.from_numpy(K_r.copy()))
+    counts = [shard_range(m, r, world)[1] - shard_range(m, r, world)[0] for r in range(world)]
+    stats = allgather_rows(torch.from_numpy(st_r.copy()), counts)
+    if rank == 0:
+        q.put((K.numpy(), stats.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_snp_sharded_kernel_over_gloo(golden):
+    """world_size 2 on CPU: SNP-range shards + all-reduce of the partial kernels == the reference's golden K."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    K, stats = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(K, golden["n300_unit_K"], rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(stats, golden["n300_unit_stats"], rtol=1e-12)

@@ -196,6 +196,19 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.only_kernel:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        kernel = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks)
+        if rank == 0:
+            print(json.dumps(kernel))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     n_iid, n_sid = CFG2["n_iid"], CFG2["n_sid"]
     rec = (n_iid + 3) // 4
     # every rank owns one full cfg2-sized SNP shard (weak scaling; no data-path collective -- DESIGN.md)
@@ -372,6 +385,7 @@ def main():
     ap.add_argument("--cpu-sample-sid", type=int, default=100_000)
     ap.add_argument("--ref-sample-sid", type=int, default=50_000)
     ap.add_argument("--no-kernel", dest="kernel", action="store_false")
+    ap.add_argument("--only-kernel", action="store_true", help="experiments: run only the cfg3 SnpKernel leg and print its object")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--kernel-n", type=int, default=CFG3["n_iid"])
     ap.add_argument("--kernel-m", type=int, default=CFG3["n_sid"])

@@ -80,11 +80,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: a lost arrival traps instead of hanging the GPU box
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// bounded wait: a lost arrival traps after ~4 s instead of hanging the GPU box
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
+    for (uint32_t spin = 1;; ++spin) {
         if (mbar_try_wait(bar, parity)) return;
-    __trap();
+        if ((spin & 1023u) == 0 && global_ns() - t0 > 4000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

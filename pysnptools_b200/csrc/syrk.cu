@@ -21,6 +21,7 @@
 //   5. k_mirror copies the lower triangle into the upper one.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <vector>
 #include "pstb_common.cuh"
 
@@ -380,6 +381,223 @@ k_syrk(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUten
     }
 }
 
+// ---- K3, 2-CTA version: one 256x256 tile per CTA pair (tcgen05 cta_group::2) -----------------------------------
+// Each CTA of the pair owns 128 rows of the tile (its 128 TMEM lanes x 256 accumulator columns) and stages its own
+// 128 A rows plus HALF of the 256 B rows (hi + lo: 64 KiB per stage, 3 stages); the tensor cores of both SMs read the
+// B halves from each other's shared memory.  Per k-block the pair loads 128 KiB for 25 MFLOP (196 flop/B, vs 128 for the
+// 1-CTA 128x256 tile) and every SM reads a third less shared memory per MMA.  Protocol:
+//   full[stage]   lives in the leader (rank 0): leader arms 128 KiB expect-tx, both CTAs' TMA loads complete on it;
+//   empty[stage]  in both CTAs, released by a multicast tcgen05.commit from the leader's MMA thread;
+//   tfull[acc]    in both CTAs (multicast commit); tempty[acc] in the leader, 16 arrivals (8 epilogue warps x 2 CTAs).
+namespace v2 {
+constexpr int TM = 256, TN = 256;                          // tile of the pair
+constexpr int STAGES2 = 3;
+constexpr int T_BYTES = 128 * BK * 2;                      // 16 KiB: one 128-row fp16 plane tile
+constexpr int STAGE2_BYTES = 4 * T_BYTES;                  // A hi, A lo, B-half hi, B-half lo
+constexpr int SYRK2_SMEM = STAGES2 * STAGE2_BYTES + 1024;
+constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr int GROUP2 = 8;                                  // 8 x 8 tiles = 2048 x 2048 super-blocks
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_addr),
+        "r"(cta)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
+k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const SyrkParams p) {
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[STAGES2], bar_empty[STAGES2], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_hi);
+        prefetch_tmap(&map_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 16); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int num_runs = (p.num_kb + RUN_KB - 1) / RUN_KB;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+                const int2 tile = p.tiles[t];
+                const int row_a = tile.x * TM + (int)rank * 128, row_b = tile.y * TN + (int)rank * 128;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1u);
+                    const uint32_t sb = tiles_base + stage * STAGE2_BYTES;
+                    const uint32_t full = smem_u32(&bar_full[stage]) & 0xFEFFFFFFu;   // the leader CTA's barrier
+                    if (leader) mbar_expect_tx(&bar_full[stage], 2u * STAGE2_BYTES);
+                    const int kc = kb * BK;
+                    tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
+                    tma_load_2d_2sm(sb + T_BYTES, &map_lo, kc, row_a, full);
+                    tma_load_2d_2sm(sb + 2 * T_BYTES, &map_hi, kc, row_b, full);
+                    tma_load_2d_2sm(sb + 3 * T_BYTES, &map_lo, kc, row_b, full);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread of the leader CTA) =====
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, run = 0;
+            for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+                for (int r = 0; r < num_runs; ++r, ++run) {
+                    const uint32_t acc = run & 1u;
+                    mbar_wait(&bar_tempty[acc], ((run >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TN;
+                    const int kb_end = min(p.num_kb, (r + 1) * RUN_KB);
+                    for (int kb = r * RUN_KB; kb < kb_end; ++kb) {
+                        mbar_wait(&bar_full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sb = tiles_base + stage * STAGE2_BYTES;
+                        const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + T_BYTES);
+                        const uint64_t b_hi = make_smem_desc(sb + 2 * T_BYTES), b_lo = make_smem_desc(sb + 3 * T_BYTES);
+                        const uint32_t first = (kb == r * RUN_KB) ? 0u : 1u;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, kIdesc2, (k == 0) ? first : 1u);
+                            umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, kIdesc2, 1u);
+                            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, kIdesc2, 1u);
+                        }
+                        tc_commit_mc2(smem_u32(&bar_empty[stage]));
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit_mc2(smem_u32(&bar_tfull[acc]));
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): drain TMEM runs into registers, write K once per tile =====
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float scale = p.out_scale;
+        if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
+        const bool vec = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+        uint32_t run = 0;
+        for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+            const int2 tile = p.tiles[t];
+            float sum[128];
+#pragma unroll
+            for (int q = 0; q < 128; ++q) sum[q] = 0.0f;
+            for (int r = 0; r < num_runs; ++r, ++run) {
+                const uint32_t acc = run & 1u;
+                mbar_wait(&bar_tfull[acc], (run >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + acc * TN + half * 128 + c * 32 + ((uint32_t)(quad * 32) << 16);
+                    PSTB_TMEM_LD32(taddr, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) sum[c * 32 + q] += __uint_as_float(v[q]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(smem_u32(&bar_tempty[acc]), 0u);
+            }
+            const long long row = (long long)tile.x * TM + rank * 128 + quad * 32 + lane;
+            const long long col0 = (long long)tile.y * TN + half * 128;
+            const long long row_hi = (long long)tile.x * TM + rank * 128 + quad * 32 + 31;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const long long cc = col0 + c * 32;
+                if (cc > row_hi || cc >= p.n) continue;
+                if (row < p.n) {
+                    float* dst = p.K + row * p.ldk + cc;
+                    if (vec && cc + 32 <= p.n) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = make_float4(sum[c * 32 + 4 * q] * scale, sum[c * 32 + 4 * q + 1] * scale,
+                                                   sum[c * 32 + 4 * q + 2] * scale, sum[c * 32 + 4 * q + 3] * scale);
+                            float4* d4 = reinterpret_cast<float4*>(dst) + q;
+                            if (p.accumulate) { float4 old = *d4; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                            *d4 = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) {
+                            if (cc + q < p.n) {
+                                float o = sum[c * 32 + q] * scale;
+                                if (p.accumulate) o += dst[q];
+                                dst[q] = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+void build_tiles2(long long n, std::vector<int2>& out) {
+    out.clear();
+    const int t = (int)((n + TM - 1) / TM);
+    for (int gi = 0; gi < t; gi += GROUP2)
+        for (int gj = 0; gj <= gi; gj += GROUP2)
+            for (int I = gi; I < gi + GROUP2 && I < t; ++I)
+                for (int J = gj; J < gj + GROUP2 && J <= I; ++J) out.push_back(make_int2(I, J));
+}
+}  // namespace v2
+
 __global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long ldk) {
     __shared__ float tile[32][33];
     const long long bi = blockIdx.y, bj = blockIdx.x;
@@ -488,17 +706,18 @@ void build_tiles(long long n, std::vector<int2>& out) {
 struct TileCache {
     long long n = -1;
     int device = -1;
+    int version = 0;
     int2* d_tiles = nullptr;
     int ntiles = 0;
 };
 
-int get_tiles(long long n, cudaStream_t st, const int2** d_tiles, int* ntiles) {
+int get_tiles(long long n, int version, cudaStream_t st, const int2** d_tiles, int* ntiles) {
     static thread_local TileCache c;
     int dev = 0;
     PSTB_CUDA(cudaGetDevice(&dev));
-    if (c.n != n || c.device != dev) {
+    if (c.n != n || c.device != dev || c.version != version) {
         std::vector<int2> tiles;
-        build_tiles(n, tiles);
+        if (version == 2) v2::build_tiles2(n, tiles); else build_tiles(n, tiles);
         PSTB_CUDA(cudaStreamSynchronize(st));
         if (c.d_tiles) cudaFree(c.d_tiles);
         c.d_tiles = nullptr;
@@ -508,6 +727,7 @@ int get_tiles(long long n, cudaStream_t st, const int2** d_tiles, int* ntiles) {
         c.ntiles = (int)tiles.size();
         c.n = n;
         c.device = dev;
+        c.version = version;
     }
     *d_tiles = c.d_tiles;
     *ntiles = c.ntiles;
@@ -522,9 +742,10 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
     CUtensorMap map_hi, map_lo;
     if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
+    static const int version = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ? 1 : 2;   // 1-CTA 128x256 kept for A/B runs
     const int2* d_tiles = nullptr;
     int ntiles = 0;
-    if (get_tiles(n, st, &d_tiles, &ntiles)) return 1;
+    if (get_tiles(n, version, st, &d_tiles, &ntiles)) return 1;
     SyrkParams p{};
     p.tiles = d_tiles;
     p.ntiles = ntiles;
@@ -538,11 +759,19 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     static thread_local bool attr_set = false;
     if (!attr_set) {
         PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
+        PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
         attr_set = true;
+    }
+    if (ntiles < 1) return 0;
+    if (version == 2) {
+        int clusters = sm_count_cached() / 2;
+        if (clusters > ntiles) clusters = ntiles;
+        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, p);   // __cluster_dims__(2,1,1)
+        PSTB_AFTER_LAUNCH("k_syrk2");
+        return 0;
     }
     int grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
-    if (grid < 1) return 0;
     k_syrk<<<grid, SYRK_THREADS, SYRK_SMEM, st>>>(map_hi, map_lo, p);
     PSTB_AFTER_LAUNCH("k_syrk");
     return 0;

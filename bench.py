@@ -369,9 +369,9 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     diag = float(K.diagonal().double().mean().item())
     return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
             "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32, SNP-sharded + NCCL allreduce".format(n, m),
-                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "fp16 hi/lo, 3 MMA terms, lower-triangular tiles"},
+                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "fp16 hi/lo, 3 MMA terms, lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)"},
             "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
-                         "note": "executed MMA flops per rank (3 terms x lower-triangular 128x256 tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained"},
+                         "note": "executed MMA flops per rank (3 terms x lower-triangular tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained"},
             "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m}
 
 

@@ -12,6 +12,7 @@
 // read once.
 // C-order output (sid fastest): statistics come from the same kernel run with no output, then a
 // tile-transposing kernel writes 128-byte row segments.
+#include <cstdlib>
 #include "pstb_common.cuh"
 
 #ifndef PSTB_ST_HINT
@@ -633,9 +634,14 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         int S = (int)((max_smem - 16u) / per_snp);
         if (S > kGatherMaxS) S = kGatherMaxS;
         if (S >= 1) {
-            int threads = n_out < 16384 ? 256 : (n_out < 65536 ? 512 : 1024);
-            // small records: leave room for several CTAs per SM
-            while (S > 4 && (unsigned)S * per_snp > 64u * 1024u) --S;
+            // two CTAs per SM (the re-pack of one overlaps the HBM writes of the other) beat one big CTA: measured on
+            // cfg4 S=3 x 512 threads x 2 CTAs = 67 % of the HBM roofline vs 58 % for S=4 x 1024 threads x 1 CTA
+            int threads = n_out < 16384 ? 256 : 512;
+            const unsigned half_sm = (227u * 1024u) / 2u - 1024u - 16u;
+            while (S > 1 && (unsigned)S * per_snp > half_sm) --S;
+            while (S > 4 && (unsigned)S * per_snp > 64u * 1024u) --S;      // small records: room for several CTAs per SM
+            if (const char* e = getenv("PSTB_GATHER_S")) { int v = atoi(e); if (v >= 1 && v <= S) S = v; }          // tuning experiments
+            if (const char* e = getenv("PSTB_GATHER_THREADS")) { int v = atoi(e); if (v >= 64 && v <= 1024 && v % 32 == 0) threads = v; }
             if ((long long)S > p.sid.n) S = (int)p.sid.n;
             const unsigned smem = 16u + (unsigned)S * per_snp;
             PSTB_CUDA(cudaFuncSetAttribute(k_read_f_gather<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

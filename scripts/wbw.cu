@@ -29,6 +29,25 @@ __global__ void fill_warpcol_rd(float4* o, const uint4* in, size_t ncol, int col
 #pragma unroll 4
     for (int q = lane; q < col4; q += 32) __stcs(c+q, make_float4(f,2,3,(float)q)); }
 }
+// clumped reads: the CTA loads the packed records of NB adjacent columns in one go (contiguous NB*in4 uint4), syncs,
+// then each warp writes its columns.  Same bytes as fill_warpcol_rd, different read granularity.
+template <int NB>
+__global__ void fill_ctabatch_rd(float4* o, const uint4* in, size_t ncol, int col4) {
+  extern __shared__ uint4 sm[];
+  int in4 = col4/16; int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (size_t b0 = (size_t)blockIdx.x * NB; b0 < ncol; b0 += (size_t)gridDim.x * NB) {
+    const uint4* r = in + b0*in4;
+    for (int q = threadIdx.x; q < NB*in4; q += blockDim.x) sm[q] = __ldg(r+q);
+    __syncthreads();
+    for (int c = warp; c < NB; c += nw) { unsigned acc=0;
+      for (int q = lane; q < in4; q += 32) { uint4 v = sm[c*in4+q]; acc += __popc(v.x)+__popc(v.y)+__popc(v.z)+__popc(v.w); }
+      for (int s=16;s;s>>=1) acc += __shfl_xor_sync(~0u, acc, s);
+      float f = (float)acc; float4* cc = o + (b0+c)*col4;
+#pragma unroll 4
+      for (int q = lane; q < col4; q += 32) __stcs(cc+q, make_float4(f,2,3,(float)q)); }
+    __syncthreads();
+  }
+}
 template<class F> float timeit(F f){ cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b); f(); f(); cudaDeviceSynchronize(); float best=1e9; for(int i=0;i<5;i++){cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms,a,b); if(ms<best)best=ms;} return best; }
 int main(){
   size_t ncol = 1000000; int col4 = 2500; size_t n4 = ncol*col4; float4* o; uint4* in;
@@ -38,5 +57,9 @@ int main(){
   for (int bps : {1,2,4,5,8}) { float ms = timeit([&]{ fill_warpcol<<<148*bps,256>>>(o,ncol,col4); }); printf("warp-column 40KB grid=148x%d x256: %.3f ms %.0f GB/s\n", bps, ms, gb/ms*1e3); }
   for (int bps : {1,2,4,8}) { float ms = timeit([&]{ fill_ctacol<<<148*bps,256>>>(o,ncol,col4); }); printf("cta-column 40KB grid=148x%d x256: %.3f ms %.0f GB/s\n", bps, ms, gb/ms*1e3); }
   for (int bps : {2,4,8}) { float ms = timeit([&]{ fill_warpcol_rd<<<148*bps,256>>>(o,in,ncol,col4); }); printf("warp-column + 6%% dependent read grid=148x%d: %.3f ms %.0f GB/s (w+r)\n", bps, ms, gb*1.0625/ms*1e3); }
+  { auto k = fill_ctabatch_rd<32>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 32*(col4/16)*16);
+    for (int thr : {256, 512, 1024}) for (int bps : {1,2}) { float ms = timeit([&]{ k<<<148*bps,thr,32*(col4/16)*16>>>(o,in,ncol,col4); }); printf("cta-batch32 clumped read, grid=148x%d x%d: %.3f ms %.0f GB/s (w+r)\n", bps, thr, ms, gb*1.0625/ms*1e3); } }
+  { auto k = fill_ctabatch_rd<8>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8*(col4/16)*16);
+    for (int bps : {2,4,8}) { float ms = timeit([&]{ k<<<148*bps,256,8*(col4/16)*16>>>(o,in,ncol,col4); }); printf("cta-batch8 clumped read, grid=148x%d x256: %.3f ms %.0f GB/s (w+r)\n", bps, ms, gb*1.0625/ms*1e3); } }
   return 0;
 }

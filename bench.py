@@ -276,7 +276,7 @@ def run_gpu(args):
 
     # ---- end to end through the host-buffer C ABI (every rank, pinned host buffers) ----
     if args.e2e:
-        e2e = run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, barrier, max_over_ranks)
+        e2e = run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank, barrier, max_over_ranks)
     del out, store, stats
     torch.cuda.empty_cache()
     # ---- SnpKernel (cfg3) ----
@@ -302,20 +302,25 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, barrier, max_over_ranks):
+def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank, barrier, max_over_ranks):
+    """cfg2 through the host-buffer C ABI.  One GPU: the whole 10 000 x 1 000 000 workload (2.5 GB in, 40 GB out, pinned).
+    N GPUs: the same single workload split by SNP range over the ranks (rank r streams SNPs [r*M/N, (r+1)*M/N) of its
+    shard), so the host holds one 40 GB result in total instead of N of them."""
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_out_p = lib.pstb_host_alloc(n_iid * n_sid * 4)
-    h_pk_p = lib.pstb_host_alloc(n_sid * rec)
+    lo, hi = rank * n_sid // world, (rank + 1) * n_sid // world
+    m = hi - lo
+    h_out_p = lib.pstb_host_alloc(n_iid * m * 4)
+    h_pk_p = lib.pstb_host_alloc(m * rec)
     if not h_out_p or not h_pk_p:
         raise RuntimeError("pinned host allocation failed: " + _lib.last_error())
-    h_packed = np.ctypeslib.as_array(ctypes.cast(h_pk_p, ctypes.POINTER(ctypes.c_uint8)), shape=(n_sid, rec))
+    h_packed = np.ctypeslib.as_array(ctypes.cast(h_pk_p, ctypes.POINTER(ctypes.c_uint8)), shape=(m, rec))
     step_rows = max(1, (1 << 28) // rec)
-    for s0 in range(0, n_sid, step_rows):
-        h_packed[s0:s0 + step_rows] = store.tensor[s0:s0 + step_rows, :rec].cpu().numpy()
-    h_stats = np.empty((n_sid, 2), dtype=np.float64)
+    for s0 in range(0, m, step_rows):
+        h_packed[s0:s0 + step_rows] = store.tensor[lo + s0:lo + min(m, s0 + step_rows), :rec].cpu().numpy()
+    h_stats = np.empty((m, 2), dtype=np.float64)
 
     def e2e_step():
-        _lib.check(lib.pstb_read_host(h_pk_p, n_iid, n_sid, None, n_iid, None, n_sid, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
+        _lib.check(lib.pstb_read_host(h_pk_p, n_iid, m, None, n_iid, None, m, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
                                       h_stats.ctypes.data, h_out_p, _lib.F32, _lib.ORDER_F))
 
     e2e_step()                                                                      # warm-up (allocates the chunk ring)
@@ -325,16 +330,16 @@ def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, barr
         e2e_step()
     torch.cuda.synchronize()
     dt_e = max_over_ranks((time.perf_counter() - t0e) / e2e_steps)
-    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_float)), shape=(n_sid, n_iid))
-    e2e_ok = bool(np.array_equal(h_stats[:256], stats[:256].cpu().numpy())) and bool(np.isfinite(h_out[-1]).all())
-    res = {"value": world * n_iid * n_sid / dt_e, "unit": "genotypes/s", "h2d_bytes_per_step": n_sid * rec, "d2h_bytes_per_step": n_iid * n_sid * 4 + 16 * n_sid,
+    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_float)), shape=(m, n_iid))
+    e2e_ok = bool(np.array_equal(h_stats[:256], stats[lo:lo + 256].cpu().numpy())) and bool(np.isfinite(h_out[-1]).all())
+    res = {"value": n_iid * n_sid / dt_e, "unit": "genotypes/s", "h2d_bytes_per_step": n_sid * rec, "d2h_bytes_per_step": n_iid * n_sid * 4 + 16 * n_sid,
            "ms_per_step": dt_e * 1e3, "steps": e2e_steps, "api": "pstb_read_host (host-buffer C ABI), pinned host buffers, 64 MiB chunks on 2 streams",
+           "work": "one cfg2 workload in total" + ("" if world == 1 else ", SNP ranges split over the {0} ranks; bytes are totals over ranks".format(world)),
            "stats_match_device_run": e2e_ok}
     del h_out, h_packed
     lib.pstb_host_free(h_out_p)
     lib.pstb_host_free(h_pk_p)
     return res
-
 
 
 def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks):

@@ -518,6 +518,219 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
     }
 }
 
+// ---- gathered individuals, 4 records at a time, byte-interleaved in shared memory ---------------------------------
+// The re-pack above is bound by shared-memory wavefronts (one random byte load per output code, ~3.5-way bank
+// conflicts).  Here the four records of a batch are interleaved while they are loaded -- word B of the tile holds
+// byte B of all four SNPs -- so ONE random 32-bit load serves an individual for four SNPs, and the values are written
+// straight from the gather (no dense intermediate): pass 1 counts, pass 2 emits 16 contiguous bytes per lane and SNP.
+template <typename T>
+__device__ __forceinline__ void store4(T* o, T a, T b, T c, T d, int vec);
+template <>
+__device__ __forceinline__ void store4<float>(float* o, float a, float b, float c, float d, int vec) {
+    if (vec) __stcs(reinterpret_cast<float4*>(o), make_float4(a, b, c, d));
+    else { __stcs(o, a); __stcs(o + 1, b); __stcs(o + 2, c); __stcs(o + 3, d); }
+}
+template <>
+__device__ __forceinline__ void store4<double>(double* o, double a, double b, double c, double d, int vec) {
+    if (vec == 2) st256_f64(o, a, b, c, d);
+    else if (vec == 1) { __stcs(reinterpret_cast<double2*>(o), make_double2(a, b)); __stcs(reinterpret_cast<double2*>(o) + 1, make_double2(c, d)); }
+    else { __stcs(o, a); __stcs(o + 1, b); __stcs(o + 2, c); __stcs(o + 3, d); }
+}
+template <>
+__device__ __forceinline__ void store4<int8_t>(int8_t* o, int8_t a, int8_t b, int8_t c, int8_t d, int vec) {
+    if (vec) *reinterpret_cast<uint32_t*>(o) = (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24);
+    else { o[0] = a; o[1] = b; o[2] = c; o[3] = d; }
+}
+
+// kStaged: the 4 raw records of the NEXT batch are fetched by TMA bulk copies into a staging area while the current
+// batch is counted and written (reads queue behind the write flood for microseconds; they must never be waited for).
+template <typename T, bool kStaged>
+__global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_f_gather4(const ReadParams p) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t stage_bar;
+    __shared__ unsigned int cnt[4][3];
+    __shared__ double st_s[4][2];
+    __shared__ double lut_d[4][4];
+    uint32_t* inter32 = reinterpret_cast<uint32_t*>(smem_dyn);     // inter32[B] = byte B of SNPs 0..3 of the batch
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const long long n_out = p.iid.n;
+    const long long nbatch = (p.sid.n + 3) >> 2;
+    const long long nq = (n_out + 3) >> 2;
+    const unsigned rec_words = (p.rec_bytes + 3u) >> 2;
+    const bool word_ok = kStaged || (((reinterpret_cast<uintptr_t>(p.packed) & 3u) == 0) && (p.ld % 4 == 0));
+    const bool idx_vec = p.iid.idx && ((reinterpret_cast<uintptr_t>(p.iid.idx) & 15u) == 0);
+    unsigned char* raw0 = smem_dyn + 16u * (size_t)rec_words;     // staging area (kStaged): 4 records of raw_stride bytes
+    auto issue = [&](long long batch) {
+        const long long bb = batch << 2;
+        const int nn = (int)min(4LL, p.sid.n - bb);
+        mbar_expect_tx(&stage_bar, 4u * p.copy_bytes);
+        for (int s = 0; s < 4; ++s)
+            bulk_g2s(raw0 + (size_t)s * p.raw_stride, p.packed + clampll(p.sid.at(bb + min(s, nn - 1)), p.sid_count) * p.ld, p.copy_bytes, &stage_bar);
+    };
+    if (kStaged) {
+        if (tid == 0) {
+            mbar_init(&stage_bar, 1);
+            fence_mbar_init();
+            if ((long long)blockIdx.x < nbatch) issue(blockIdx.x);
+        }
+        __syncthreads();
+    }
+    uint32_t iter = 0;
+
+    // the 4 iid indices of output quad q (fetched one iteration ahead: the index vector lives in L2) ...
+    auto fetch_quad = [&](long long q) -> uint4 {
+        if (q >= nq) return make_uint4(0, 0, 0, 0);
+        if (idx_vec && (q << 2) + 3 < n_out) return __ldg(reinterpret_cast<const uint4*>(p.iid.idx) + q);
+        uint32_t iv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) iv[t] = ((q << 2) + t < n_out) ? (uint32_t)clampll(p.iid.at((q << 2) + t), p.iid_count) : 0u;
+        return make_uint4(iv[0], iv[1], iv[2], iv[3]);
+    };
+    // ... -> word offsets and shifts (clamped: memory safe for any device index vector)
+    auto decode_quad = [&](long long q, const uint4& v, uint32_t (&boff)[4], uint32_t (&sh)[4]) -> int {
+        const uint32_t iv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t i = iv[t] < (uint32_t)p.iid_count ? iv[t] : (uint32_t)p.iid_count - 1u;
+            boff[t] = i >> 2;
+            sh[t] = 2u * (i & 3u);
+        }
+        return (int)min(4LL, n_out - (q << 2));
+    };
+
+    for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const long long b0 = batch << 2;
+        const int ns = (int)min(4LL, p.sid.n - b0);
+        const uint8_t* src[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            src[s] = kStaged ? (const uint8_t*)(raw0 + (size_t)s * p.raw_stride) : p.packed + clampll(p.sid.at(b0 + min(s, ns - 1)), p.sid_count) * p.ld;
+        if (tid < 12) (&cnt[0][0])[tid] = 0;
+        if (kStaged) mbar_wait(&stage_bar, iter & 1u);
+        ++iter;
+        // ---- load + interleave ----
+#pragma unroll 2
+        for (unsigned w = tid; w < rec_words; w += nt) {
+            uint32_t x[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (kStaged) {
+                    x[s] = reinterpret_cast<const uint32_t*>(src[s])[w];
+                } else if (word_ok) {
+                    x[s] = __ldg(reinterpret_cast<const uint32_t*>(src[s]) + w);
+                } else {
+                    x[s] = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if (4 * w + k < p.rec_bytes) x[s] |= (uint32_t)__ldg(src[s] + 4 * w + k) << (8 * k);
+                }
+            }
+            const uint32_t lo01 = __byte_perm(x[0], x[1], 0x5140), lo23 = __byte_perm(x[2], x[3], 0x5140);
+            const uint32_t hi01 = __byte_perm(x[0], x[1], 0x7362), hi23 = __byte_perm(x[2], x[3], 0x7362);
+            reinterpret_cast<uint4*>(smem_dyn)[w] = make_uint4(__byte_perm(lo01, lo23, 0x5410), __byte_perm(lo01, lo23, 0x7632),
+                                                               __byte_perm(hi01, hi23, 0x5410), __byte_perm(hi01, hi23, 0x7632));
+        }
+        __syncthreads();
+        if (kStaged && tid == 0 && batch + gridDim.x < nbatch) issue(batch + gridDim.x);   // staging area is free again
+        // ---- pass 1: dosage counts of the 4 SNPs over the selected individuals ----
+        if (p.mode != PSTB_STD_NONE) {
+            if (!p.use_stats) {
+                unsigned int tot[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) tot[k] = 0;
+                uint32_t a1 = 0, a2 = 0, a3 = 0, pending = 0;           // 4 x 8-bit counters each (one per SNP)
+                auto flush = [&]() {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        tot[3 * s] += (a1 >> (8 * s)) & 0xffu;
+                        tot[3 * s + 1] += (a2 >> (8 * s)) & 0xffu;
+                        tot[3 * s + 2] += (a3 >> (8 * s)) & 0xffu;
+                    }
+                    a1 = a2 = a3 = 0;
+                    pending = 0;
+                };
+                uint4 nxt = fetch_quad(tid);
+                for (long long q = tid; q < nq; q += nt) {
+                    uint32_t boff[4], sh[4];
+                    const uint4 cur = nxt;
+                    nxt = fetch_quad(q + nt);
+                    const int valid = decode_quad(q, cur, boff, sh);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (t < valid) {
+                            const uint32_t c4 = (inter32[boff[t]] >> sh[t]) & 0x03030303u;
+                            const uint32_t lo = c4 & 0x01010101u, hi = (c4 >> 1) & 0x01010101u;
+                            a1 += lo & ~hi;
+                            a2 += hi & ~lo;
+                            a3 += hi & lo;
+                        }
+                    }
+                    pending += 4;
+                    if (pending >= 252) flush();
+                }
+                flush();
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const unsigned int r = __reduce_add_sync(0xffffffffu, tot[k]);
+                    if ((tid & 31) == 0 && r) atomicAdd(&cnt[k / 3][k % 3], r);
+                }
+                __syncthreads();
+            }
+            if (tid < ns) {
+                double mean, sd;
+                if (p.use_stats) {
+                    mean = p.stats[2 * (b0 + tid)];
+                    sd = p.stats[2 * (b0 + tid) + 1];
+                } else {
+                    const long long c1 = cnt[tid][0], c2 = cnt[tid][1], c3 = cnt[tid][2], c0 = n_out - c1 - c2 - c3;
+                    stats_from_counts(p.count_a1 ? c3 : c0, c2, p.count_a1 ? c0 : c3, mean, sd);
+                    if (p.stats) {
+                        p.stats[2 * (b0 + tid)] = mean;
+                        p.stats[2 * (b0 + tid) + 1] = sd;
+                    }
+                }
+                st_s[tid][0] = mean;
+                st_s[tid][1] = sd;
+            }
+        }
+        if (tid < ns) {                                                 // each thread reads only the statistics it wrote itself
+            const Lut4<T> l = make_code_lut<T>(p.mode, p.count_a1, p.a, p.b, p.lnB, st_s[tid][0], st_s[tid][1]);
+            lut_d[tid][0] = (double)l.c0; lut_d[tid][1] = (double)l.c1; lut_d[tid][2] = (double)l.c2; lut_d[tid][3] = (double)l.c3;
+        }
+        __syncthreads();
+        // ---- pass 2: emit ----
+        if (p.out) {
+            Lut4<T> lut[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { lut[s].c0 = (T)lut_d[s][0]; lut[s].c1 = (T)lut_d[s][1]; lut[s].c2 = (T)lut_d[s][2]; lut[s].c3 = (T)lut_d[s][3]; }
+            T* o = reinterpret_cast<T*>(p.out) + b0 * p.out_ld;
+            uint4 nxt = fetch_quad(tid);
+            for (long long q = tid; q < nq; q += nt) {
+                uint32_t boff[4], sh[4], c4[4];
+                const uint4 cur = nxt;
+                nxt = fetch_quad(q + nt);
+                const int valid = decode_quad(q, cur, boff, sh);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) c4[t] = (inter32[boff[t]] >> sh[t]) & 0x03030303u;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (s < ns) {
+                        T* oc = o + (long long)s * p.out_ld + (q << 2);
+                        const T v0 = lut[s].pick((c4[0] >> (8 * s)) & 3u), v1 = lut[s].pick((c4[1] >> (8 * s)) & 3u);
+                        const T v2 = lut[s].pick((c4[2] >> (8 * s)) & 3u), v3 = lut[s].pick((c4[3] >> (8 * s)) & 3u);
+                        if (valid == 4) store4<T>(oc, v0, v1, v2, v3, p.vec_ok);
+                        else {
+                            if (valid > 0) oc[0] = v0;
+                            if (valid > 1) oc[1] = v1;
+                            if (valid > 2) oc[2] = v2;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- C order: tile-transposing emit ------------------------------------------------------------------
 constexpr int kTileS = 32;    // SNPs per tile (one per lane)
 constexpr int kTileI = 512;   // individuals per tile
@@ -629,7 +842,40 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     const unsigned dense_bytes = p.dense ? 0u : (unsigned)((((n_out + 3) >> 2) + 15) & ~15LL);
     const unsigned max_smem = 220u * 1024u;
     if (!p.dense) {
-        // gathered individuals: batch S records per pass over the index vector when at least one fits
+        const unsigned inter_bytes = 16u * ((p.rec_bytes + 3u) >> 2);
+        if (inter_bytes <= max_smem && !getenv("PSTB_GATHER_V1")) {
+            const long long nq = (n_out + 3) >> 2;
+            const long long nbatch = (p.sid.n + 3) / 4;
+            const unsigned staged_bytes = inter_bytes + 4u * rec16;
+            const bool staged = p.bulk_ok && staged_bytes <= max_smem && !getenv("PSTB_GATHER_NOSTAGE");
+            if (staged) {
+                // one CTA per SM: TMA-staged raw records for batch b+1 while batch b is counted and written
+                int threads = nq >= 1024 ? 1024 : (int)(((nq + 31) / 32) * 32);
+                if (threads < 64) threads = 64;
+                PSTB_CUDA(cudaFuncSetAttribute(k_read_f_gather4<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
+                int ctas_per_sm = 1;
+                PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f_gather4<T, true>, threads, staged_bytes));
+                if (ctas_per_sm < 1) ctas_per_sm = 1;
+                long long grid = (long long)sms * ctas_per_sm;
+                if (grid > nbatch) grid = nbatch;
+                k_read_f_gather4<T, true><<<(unsigned)grid, threads, staged_bytes, st>>>(p);
+                PSTB_AFTER_LAUNCH("k_read_f_gather4<staged>");
+                return 0;
+            }
+            // 4 byte-interleaved records per batch loaded straight from global; two CTAs per SM when the tile is <= ~110 KiB
+            int threads = nq >= 512 ? 512 : (int)(((nq + 31) / 32) * 32);
+            if (threads < 64) threads = 64;
+            PSTB_CUDA(cudaFuncSetAttribute(k_read_f_gather4<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inter_bytes));
+            int ctas_per_sm = 1;
+            PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f_gather4<T, false>, threads, inter_bytes));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            long long grid = (long long)sms * ctas_per_sm;
+            if (grid > nbatch) grid = nbatch;
+            k_read_f_gather4<T, false><<<(unsigned)grid, threads, inter_bytes, st>>>(p);
+            PSTB_AFTER_LAUNCH("k_read_f_gather4");
+            return 0;
+        }
+        // larger records: batch S records per pass over the index vector when at least one fits
         const unsigned per_snp = rec16 + dense_bytes;
         int S = (int)((max_smem - 16u) / per_snp);
         if (S > kGatherMaxS) S = kGatherMaxS;

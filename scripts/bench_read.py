@@ -40,6 +40,7 @@ def run(tag, n, m, dtype, order, std, isel=None, ssel=None, missing=False):
           % (tag, n, m, I.n, S.n, np.dtype(dtype).name, order, ms, I.n * S.n / ms * 1e3, algo / ms / 1e6, 100 * algo / ms / 1e6 / PEAK, PEAK), flush=True)
     del store, base, view
 
+import signal; signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 which = sys.argv[1:] or ["cfg2", "cfg4", "variants"]
 if "peaks" in which:
     a = torch.empty(10_000_000_000 // 4, dtype=torch.float32, device="cuda"); b = torch.empty_like(a)

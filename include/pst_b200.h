@@ -110,6 +110,20 @@ int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int6
                     int mode, double a, double b, int use_stats, double* d_stats,
                     float* d_K, int accumulate, int mirror,
                     void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* K-tile sharding for kernels that do not fit one GPU (BASELINE cfg5: 500 000 iids -> K = 1 TB): the lower triangle is cut
+ * into 256 x 256 tiles, rank r of `world` owns every world-th tile of a fixed rasterisation and computes them for ALL
+ * selected SNPs from its own copy of the packed store -- no reduction, no collective.
+ * pstb_kernel_tile_count / pstb_kernel_tile_coords: how many tiles `rank` owns and their (I, J) block coordinates
+ * (rows [256 I, +256), columns [256 J, +256), J <= I; host array int32 [count][2]).
+ * pstb_snp_kernel_tiles: like pstb_snp_kernel, but writes d_tiles [count][256][256] float32 (each owned tile stored whole,
+ * diagonal tiles with both triangles; entries beyond iid.n are left untouched). */
+int64_t pstb_kernel_tile_count(int64_t n_iid, int rank, int world);
+int pstb_kernel_tile_coords(int64_t n_iid, int rank, int world, int32_t* h_ij);
+int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                          pstb_axis iid, pstb_axis sid, int count_a1,
+                          int mode, double a, double b, int use_stats, double* d_stats,
+                          float* d_tiles, int rank, int world, int accumulate,
+                          void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
 /* K = V V^T for a float matrix V [n_iid, n_sid] already in HBM (float32 / float64, C or F order): replaces the
  * val.dot(val.T) of SnpData._read_kernel (snpdata.py:203-206).  Same fp16 hi/lo tensor-core path and workspace. */
 int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,

@@ -225,6 +225,7 @@ struct SyrkParams {
     int accumulate;
     const Scalars* sc;      // NULL -> out_scale is used as is
     float out_scale;
+    int compact;            // K is tile storage [ntiles][256][256] (K-tile sharding: this rank's tiles only), 2-CTA kernel only
 };
 
 __global__ void __launch_bounds__(SYRK_THREADS, 1)
@@ -551,13 +552,17 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
             const long long row = (long long)tile.x * TM + rank * 128 + quad * 32 + lane;
             const long long col0 = (long long)tile.y * TN + half * 128;
             const long long row_hi = (long long)tile.x * TM + rank * 128 + quad * 32 + 31;
+            // compact: tile t of this rank's list is stored whole (256 x 256, ld 256), diagonal tiles included in full
+            float* kbase = p.compact ? p.K + (long long)t * (TM * TN) + (long long)(rank * 128 + quad * 32 + lane) * TN + half * 128
+                                     : p.K + row * p.ldk + col0;
+            const bool vec_t = p.compact || vec;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const long long cc = col0 + c * 32;
-                if (cc > row_hi || cc >= p.n) continue;
+                if ((!p.compact && cc > row_hi) || cc >= p.n) continue;
                 if (row < p.n) {
-                    float* dst = p.K + row * p.ldk + cc;
-                    if (vec && cc + 32 <= p.n) {
+                    float* dst = kbase + c * 32;
+                    if (vec_t && cc + 32 <= p.n) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 o = make_float4(sum[c * 32 + 4 * q] * scale, sum[c * 32 + 4 * q + 1] * scale,
@@ -706,18 +711,28 @@ void build_tiles(long long n, std::vector<int2>& out) {
 struct TileCache {
     long long n = -1;
     int device = -1;
-    int version = 0;
+    int version = 0, rank = 0, world = 1;
     int2* d_tiles = nullptr;
     int ntiles = 0;
 };
 
-int get_tiles(long long n, int version, cudaStream_t st, const int2** d_tiles, int* ntiles) {
+// tiles of the lower triangle owned by `rank` of `world`: every world-th tile of the rasterised list (balanced, and the
+// tiles a rank works on concurrently stay inside one super-block)
+void owned_tiles(long long n, int version, int rank, int world, std::vector<int2>& out) {
+    std::vector<int2> all;
+    if (version == 2) v2::build_tiles2(n, all); else build_tiles(n, all);
+    if (world <= 1) { out.swap(all); return; }
+    out.clear();
+    for (size_t t = (size_t)rank; t < all.size(); t += (size_t)world) out.push_back(all[t]);
+}
+
+int get_tiles(long long n, int version, int rank, int world, cudaStream_t st, const int2** d_tiles, int* ntiles) {
     static thread_local TileCache c;
     int dev = 0;
     PSTB_CUDA(cudaGetDevice(&dev));
-    if (c.n != n || c.device != dev || c.version != version) {
+    if (c.n != n || c.device != dev || c.version != version || c.rank != rank || c.world != world) {
         std::vector<int2> tiles;
-        if (version == 2) v2::build_tiles2(n, tiles); else build_tiles(n, tiles);
+        owned_tiles(n, version, rank, world, tiles);
         PSTB_CUDA(cudaStreamSynchronize(st));
         if (c.d_tiles) cudaFree(c.d_tiles);
         c.d_tiles = nullptr;
@@ -728,6 +743,8 @@ int get_tiles(long long n, int version, cudaStream_t st, const int2** d_tiles, i
         c.n = n;
         c.device = dev;
         c.version = version;
+        c.rank = rank;
+        c.world = world;
     }
     *d_tiles = c.d_tiles;
     *ntiles = c.ntiles;
@@ -737,15 +754,16 @@ int get_tiles(long long n, int version, cudaStream_t st, const int2** d_tiles, i
 long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad, long long k_pad, float* K, long long ldk,
-                int accumulate, const Scalars* sc, float out_scale, cudaStream_t st) {
+                int accumulate, const Scalars* sc, float out_scale, cudaStream_t st, int rank = 0, int world = 1, int compact = 0) {
     if (n_pad % ROW_PAD || k_pad % BK || n_pad < n) return fail("planes must be padded to %d rows / %d columns", ROW_PAD, BK);
     if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
     CUtensorMap map_hi, map_lo;
     if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
-    static const int version = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ? 1 : 2;   // 1-CTA 128x256 kept for A/B runs
+    static const int env_version = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ? 1 : 2;   // 1-CTA 128x256 kept for A/B runs
+    const int version = compact ? 2 : env_version;
     const int2* d_tiles = nullptr;
     int ntiles = 0;
-    if (get_tiles(n, version, st, &d_tiles, &ntiles)) return 1;
+    if (get_tiles(n, version, rank, world, st, &d_tiles, &ntiles)) return 1;
     SyrkParams p{};
     p.tiles = d_tiles;
     p.ntiles = ntiles;
@@ -756,6 +774,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.accumulate = accumulate;
     p.sc = sc;
     p.out_scale = out_scale;
+    p.compact = compact;
     static thread_local bool attr_set = false;
     if (!attr_set) {
         PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
@@ -822,10 +841,10 @@ extern "C" int pstb_convert_kernel(const float* d_K, int64_t n, void* d_out, int
     return 0;
 }
 
-extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
-                               pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
-                               float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
-                               void* stream) {
+static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
+                           pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
+                           float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
+                           void* stream, int rank, int world, int compact) {
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
@@ -837,7 +856,7 @@ extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long n = iid.n, n_pad = round_up(n, ROW_PAD);
     if (sid.n == 0) {
-        if (!accumulate) PSTB_CUDA(cudaMemsetAsync(d_K, 0, (size_t)n * n * sizeof(float), st));
+        if (!accumulate && !compact) PSTB_CUDA(cudaMemsetAsync(d_K, 0, (size_t)n * n * sizeof(float), st));
         return 0;
     }
     const double lnB = (mode == PSTB_STD_BETA) ? lgamma(a) + lgamma(b) - lgamma(a + b) : 0.0;
@@ -886,11 +905,46 @@ extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_
         const long long ptiles = (k_pad / PT_S) * (n_pad / PT_I);
         k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
         PSTB_AFTER_LAUNCH("k_planes");
-        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st);
+        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact);
         if (rc) return rc;
     }
-    if (mirror) return pstb_mirror_lower(d_K, n, n, stream);
+    if (mirror && !compact) return pstb_mirror_lower(d_K, n, n, stream);
     return 0;
+}
+
+
+extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
+                               pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
+                               float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
+                               void* stream) {
+    return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate,
+                           mirror, d_work, work_bytes, chunk, stream, 0, 1, 0);
+}
+
+// ---- K-tile sharding (cfg5: N = 500 000, K = 1 TB does not fit one GPU) -----------------------------------------
+extern "C" int64_t pstb_kernel_tile_count(int64_t n_iid, int rank, int world) {
+    if (n_iid <= 0 || world < 1 || rank < 0 || rank >= world) return 0;
+    std::vector<int2> tiles;
+    owned_tiles(n_iid, 2, rank, world, tiles);
+    return (int64_t)tiles.size();
+}
+
+extern "C" int pstb_kernel_tile_coords(int64_t n_iid, int rank, int world, int32_t* h_ij) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+    if (!h_ij) return fail("h_ij is NULL");
+    std::vector<int2> tiles;
+    if (n_iid > 0) owned_tiles(n_iid, 2, rank, world, tiles);
+    for (size_t t = 0; t < tiles.size(); ++t) { h_ij[2 * t] = tiles[t].x; h_ij[2 * t + 1] = tiles[t].y; }
+    return 0;
+}
+
+extern "C" int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
+                                     pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
+                                     float* d_tiles, int rank, int world, int accumulate, void* d_work, int64_t work_bytes,
+                                     int64_t chunk, void* stream) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+    return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_tiles, accumulate,
+                           0, d_work, work_bytes, chunk, stream, rank, world, 1);
 }
 
 extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,

@@ -241,6 +241,49 @@ def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=(
     return K, d_stats
 
 
+def kernel_tile_coords(n_iid, rank=0, world=1):
+    """(I, J) block coordinates of the 256 x 256 lower-triangular tiles owned by ``rank`` of ``world`` (int32 [count, 2])."""
+    count = int(lib.pstb_kernel_tile_count(n_iid, rank, world))
+    ij = np.zeros((count, 2), dtype=np.int32)
+    if count:
+        check(lib.pstb_kernel_tile_coords(n_iid, rank, world, ij.ctypes.data))
+    return ij
+
+
+def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
+                     rank=0, world=1, tiles=None, accumulate=False):
+    """K-tile sharded kinship: this rank's 256 x 256 tiles of ``K = X X^T`` over ALL selected SNPs (cfg5; no collective).
+
+    Returns ``(tiles, coords, stats)``: float32 CUDA tensor [count, 256, 256], the (I, J) of each tile, per-SNP statistics.
+    """
+    _lib.require_gpu()
+    dev = store.device
+    isel = iid_sel if isinstance(iid_sel, Selection) else Selection(iid_sel, store.iid_count, dev)
+    ssel = sid_sel if isinstance(sid_sel, Selection) else Selection(sid_sel, store.sid_count, dev)
+    mode, a, b = _mode_args(standardizer)
+    n = isel.n
+    coords = kernel_tile_coords(n, rank, world)
+    with torch.cuda.device(dev):
+        if tiles is None:
+            tiles = torch.zeros((len(coords), 256, 256), dtype=torch.float32, device=dev)
+            accumulate = False
+        assert tiles.dtype == torch.float32 and tiles.is_contiguous() and tuple(tiles.shape) == (len(coords), 256, 256)
+        use_stats = 0
+        if stats is not None:
+            d_stats = torch.as_tensor(stats, dtype=torch.float64, device=dev).contiguous()
+            use_stats = 1
+        else:
+            d_stats = torch.empty((ssel.n, 2), dtype=torch.float64, device=dev)
+        if chunk is None:
+            chunk = default_kernel_chunk(n, ssel.n)
+        wbytes = int(lib.pstb_kernel_workspace_bytes(n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(lib.pstb_snp_kernel_tiles(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
+                                        int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), tiles.data_ptr(), rank, world,
+                                        int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _stream()))
+    return tiles, coords, d_stats
+
+
 def float_kernel(val, chunk=None, K=None, accumulate=False, mirror=True):
     """``K = V V^T`` of a CUDA float tensor [n_iid, n_sid] (C- or F-contiguous) on the tensor cores (float32 result)."""
     _lib.require_gpu()

@@ -102,3 +102,29 @@ def test_convert_kernel(dev):
     K = torch.randn((37, 37), device="cuda")
     out = dev.convert_kernel(K, np.float64, scale=2.0)
     assert out.dtype == torch.float64 and torch.allclose(out, K.double() * 2.0)
+
+
+@pytest.mark.parametrize("n,m,world", [(700, 300, 1), (1500, 700, 3), (2100, 400, 8)])
+def test_kernel_tile_sharding(n, m, world, oracle, dev):
+    """K-tile sharding (cfg5 path): every rank's tiles together are exactly K; no tile is owned twice."""
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + world)
+    store = dev.PackedStore.from_host(packed, n)
+    ref, rst = oracle.read_kernel(packed, n)
+    K = np.full((n, n), np.nan)
+    seen = set()
+    T = (n + 255) // 256
+    for rank in range(world):
+        tiles, coords, st = dev.snp_kernel_tiles(store, rank=rank, world=world, chunk=256)   # two chunks: accumulate path
+        np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12)
+        th = tiles.double().cpu().numpy()
+        for t, (I, J) in enumerate(coords):
+            assert J <= I and (I, J) not in seen
+            seen.add((int(I), int(J)))
+            r0, c0 = I * 256, J * 256
+            r1, c1 = min(n, r0 + 256), min(n, c0 + 256)
+            K[r0:r1, c0:c1] = th[t, : r1 - r0, : c1 - c0]
+            if I != J:
+                K[c0:c1, r0:r1] = th[t, : r1 - r0, : c1 - c0].T
+    assert len(seen) == T * (T + 1) // 2 and not np.isnan(K).any()
+    assert np.linalg.norm(K - ref) / np.linalg.norm(ref) < K_TOL
+    assert np.allclose(K, K.T, rtol=0, atol=1e-3 * np.abs(ref).max())      # diagonal tiles are stored whole (both triangles)

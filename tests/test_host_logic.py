@@ -156,3 +156,22 @@ def test_snp_sharded_kernel_over_gloo(golden):
         assert p.exitcode == 0
     np.testing.assert_allclose(K, golden["n300_unit_K"], rtol=1e-11, atol=1e-9)
     np.testing.assert_allclose(stats, golden["n300_unit_stats"], rtol=1e-12)
+
+
+def test_kernel_tile_ownership_partitions_lower_triangle():
+    """K-tile sharding (cfg5): every lower-triangular 256x256 tile is owned by exactly one rank; loads are balanced."""
+    from pysnptools_b200 import _lib
+    for n in (1, 255, 256, 257, 5000, 70001):
+        T = (n + 255) // 256
+        for world in (1, 2, 3, 8):
+            seen, sizes = set(), []
+            for rank in range(world):
+                count = int(_lib.lib.pstb_kernel_tile_count(n, rank, world))
+                ij = np.zeros((count, 2), dtype=np.int32)
+                if count:
+                    assert _lib.lib.pstb_kernel_tile_coords(n, rank, world, ij.ctypes.data) == 0
+                for I, J in ij:
+                    assert 0 <= J <= I < T and (int(I), int(J)) not in seen
+                    seen.add((int(I), int(J)))
+                sizes.append(count)
+            assert len(seen) == T * (T + 1) // 2 and max(sizes) - min(sizes) <= 1

@@ -48,6 +48,34 @@ __global__ void fill_ctabatch_rd(float4* o, const uint4* in, size_t ncol, int co
     __syncthreads();
   }
 }
+// V_a: our emit loop (LDS.U16 + 8 register selects + 256-bit store) on a static smem record: no global reads at all
+__device__ __forceinline__ float pick4(unsigned c, float a, float b, float cc, float d) { float lo = (c & 1u) ? b : a; float hi = (c & 1u) ? d : cc; return (c & 2u) ? hi : lo; }
+__global__ void emit_like(float* o, size_t ncol, int col_f, int prefetch, const unsigned char* in, int rec16) {
+  extern __shared__ __align__(16) unsigned char smx[];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5; size_t gw = ((size_t)blockIdx.x*blockDim.x+threadIdx.x)>>5, nw = ((size_t)gridDim.x*blockDim.x)>>5;
+  unsigned char* raw = smx + (size_t)w * (2*rec16 + 16);
+  unsigned long long* bar = (unsigned long long*)(raw + 2*rec16);
+  unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+  for (int i = lane; i < 2*rec16; i += 32) raw[i] = (unsigned char)(i * 37 + w);
+  if (prefetch && lane == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a)); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncwarp();
+  unsigned it = 0;
+  if (prefetch && lane == 0 && gw < ncol) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(rec16)); asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"((unsigned)__cvta_generic_to_shared(raw)), "l"(in + gw*rec16), "r"(rec16), "r"(bar_a) : "memory"); }
+  for (size_t b = gw; b < ncol; b += nw, ++it) {
+    unsigned char* rec = raw + (it & 1) * rec16;
+    if (prefetch) {
+      unsigned ok = 0; while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p; }" : "=r"(ok) : "r"(bar_a), "r"(it & 1) : "memory");
+      if (lane == 0 && b + nw < ncol) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(rec16)); asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"((unsigned)__cvta_generic_to_shared(raw + ((it+1)&1)*rec16)), "l"(in + (b+nw)*rec16), "r"(rec16), "r"(bar_a) : "memory"); }
+    }
+    float l0 = (float)b, l1 = 0.f, l2 = l0 + 1.f, l3 = l0 + 2.f;
+    const unsigned short* r16 = (const unsigned short*)rec; float* c = o + b * (size_t)col_f; int nh = col_f >> 3;
+#pragma unroll 4
+    for (int h = lane; h < nh; h += 32) { unsigned two = r16[h];
+      float a0=pick4(two&3,l0,l1,l2,l3),a1=pick4((two>>2)&3,l0,l1,l2,l3),a2=pick4((two>>4)&3,l0,l1,l2,l3),a3=pick4((two>>6)&3,l0,l1,l2,l3),a4=pick4((two>>8)&3,l0,l1,l2,l3),a5=pick4((two>>10)&3,l0,l1,l2,l3),a6=pick4((two>>12)&3,l0,l1,l2,l3),a7=pick4(two>>14,l0,l1,l2,l3);
+      asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(c + 8*h), "f"(a0),"f"(a1),"f"(a2),"f"(a3),"f"(a4),"f"(a5),"f"(a6),"f"(a7) : "memory"); }
+    __syncwarp();
+  }
+}
 template<class F> float timeit(F f){ cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b); f(); f(); cudaDeviceSynchronize(); float best=1e9; for(int i=0;i<5;i++){cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b); float ms; cudaEventElapsedTime(&ms,a,b); if(ms<best)best=ms;} return best; }
 int main(){
   size_t ncol = 1000000; int col4 = 2500; size_t n4 = ncol*col4; float4* o; uint4* in;
@@ -61,5 +89,8 @@ int main(){
     for (int thr : {256, 512, 1024}) for (int bps : {1,2}) { float ms = timeit([&]{ k<<<148*bps,thr,32*(col4/16)*16>>>(o,in,ncol,col4); }); printf("cta-batch32 clumped read, grid=148x%d x%d: %.3f ms %.0f GB/s (w+r)\n", bps, thr, ms, gb*1.0625/ms*1e3); } }
   { auto k = fill_ctabatch_rd<8>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8*(col4/16)*16);
     for (int bps : {2,4,8}) { float ms = timeit([&]{ k<<<148*bps,256,8*(col4/16)*16>>>(o,in,ncol,col4); }); printf("cta-batch8 clumped read, grid=148x%d x256: %.3f ms %.0f GB/s (w+r)\n", bps, ms, gb*1.0625/ms*1e3); } }
+  { int rec16 = 2512; unsigned char* pk; cudaMalloc(&pk, ncol*(size_t)rec16); cudaMemset(pk, 0x9c, ncol*(size_t)rec16);
+    cudaFuncSetAttribute(emit_like, cudaFuncAttributeMaxDynamicSharedMemorySize, 8*(2*rec16+16));
+    for (int pf : {0, 1}) for (int bps : {1,2,4,5}) { float ms = timeit([&]{ emit_like<<<148*bps,256,8*(2*rec16+16)>>>((float*)o,ncol,10000,pf,pk,rec16); }); printf("emit-like (LDS+select+st.v8) prefetch=%d grid=148x%d: %.3f ms %.0f GB/s\n", pf, bps, ms, (gb + (pf? ncol*2512e-9:0))/ms*1e3); } }
   return 0;
 }

@@ -43,6 +43,8 @@ struct ReadParams {
     int direct;             // record too large for shared memory: gather straight from global, in segments
     long long seg_len;      // outputs per segment (multiple of 16) when direct
     int vec_ok;             // output columns: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = neither
+    const uint32_t* sel_mask;   // gather: 2 bits per individual (0b01 = selected), built once per call; word [mask_words] = "index vector has repeats"
+    long long mask_words;
 };
 
 template <typename T>
@@ -518,6 +520,20 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
     }
 }
 
+// Selection mask for the statistics of gathered reads: bit 2*(i%16) of word i/16 is set when individual i is selected.
+// Per-SNP dosage counts over the selected individuals then are masked popcounts over the raw record -- a coalesced
+// sweep instead of a second random gather.  A repeated index (the counts would need multiplicities) raises the flag in
+// the extra last word and the kernels fall back to counting through the gather.
+__global__ void k_build_sel_mask(Axis iid, long long iid_count, uint32_t* mask, long long mask_words) {
+    for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < iid.n; a += (long long)gridDim.x * blockDim.x) {
+        long long i = iid.at(a);
+        i = i < 0 ? 0 : (i >= iid_count ? iid_count - 1 : i);
+        const uint32_t bit = 1u << (2 * (i & 15));
+        const uint32_t old = atomicOr(mask + (i >> 4), bit);
+        if (old & bit) mask[mask_words] = 1u;
+    }
+}
+
 // ---- gathered individuals, 4 records at a time, byte-interleaved in shared memory ---------------------------------
 // The re-pack above is bound by shared-memory wavefronts (one random byte load per output code, ~3.5-way bank
 // conflicts).  Here the four records of a batch are interleaved while they are loaded -- word B of the tile holds
@@ -576,6 +592,10 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
         __syncthreads();
     }
     uint32_t iter = 0;
+    // statistics of gathered reads without a second gather: masked popcounts over the raw records (see k_build_sel_mask)
+    const bool mask_count = kStaged && p.mode != PSTB_STD_NONE && !p.use_stats && p.sel_mask != nullptr && __ldg(p.sel_mask + p.mask_words) == 0u;
+    if (tid < 12) (&cnt[0][0])[tid] = 0;
+    __syncthreads();
 
     // the 4 iid indices of output quad q (fetched one iteration ahead: the index vector lives in L2) ...
     auto fetch_quad = [&](long long q) -> uint4 {
@@ -605,10 +625,12 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
 #pragma unroll
         for (int s = 0; s < 4; ++s)
             src[s] = kStaged ? (const uint8_t*)(raw0 + (size_t)s * p.raw_stride) : p.packed + clampll(p.sid.at(b0 + min(s, ns - 1)), p.sid_count) * p.ld;
-        if (tid < 12) (&cnt[0][0])[tid] = 0;
         if (kStaged) mbar_wait(&stage_bar, iter & 1u);
         ++iter;
         // ---- load + interleave ----
+        unsigned int mc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) mc[k] = 0;
 #pragma unroll 2
         for (unsigned w = tid; w < rec_words; w += nt) {
             uint32_t x[4];
@@ -624,16 +646,33 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
                         if (4 * w + k < p.rec_bytes) x[s] |= (uint32_t)__ldg(src[s] + 4 * w + k) << (8 * k);
                 }
             }
+            if (mask_count) {
+                const uint32_t sel = __ldg(p.sel_mask + w);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t lo = x[s] & sel, hi = (x[s] >> 1) & sel;
+                    mc[3 * s] += __popc(lo & ~hi);
+                    mc[3 * s + 1] += __popc(hi & ~lo);
+                    mc[3 * s + 2] += __popc(hi & lo);
+                }
+            }
             const uint32_t lo01 = __byte_perm(x[0], x[1], 0x5140), lo23 = __byte_perm(x[2], x[3], 0x5140);
             const uint32_t hi01 = __byte_perm(x[0], x[1], 0x7362), hi23 = __byte_perm(x[2], x[3], 0x7362);
             reinterpret_cast<uint4*>(smem_dyn)[w] = make_uint4(__byte_perm(lo01, lo23, 0x5410), __byte_perm(lo01, lo23, 0x7632),
                                                                __byte_perm(hi01, hi23, 0x5410), __byte_perm(hi01, hi23, 0x7632));
         }
+        if (mask_count) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const unsigned int r = __reduce_add_sync(0xffffffffu, mc[k]);
+                if ((tid & 31) == 0 && r) atomicAdd(&cnt[k / 3][k % 3], r);
+            }
+        }
         __syncthreads();
         if (kStaged && tid == 0 && batch + gridDim.x < nbatch) issue(batch + gridDim.x);   // staging area is free again
         // ---- pass 1: dosage counts of the 4 SNPs over the selected individuals ----
         if (p.mode != PSTB_STD_NONE) {
-            if (!p.use_stats) {
+            if (!p.use_stats && !mask_count) {
                 unsigned int tot[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) tot[k] = 0;
@@ -697,6 +736,7 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
             lut_d[tid][0] = (double)l.c0; lut_d[tid][1] = (double)l.c1; lut_d[tid][2] = (double)l.c2; lut_d[tid][3] = (double)l.c3;
         }
         __syncthreads();
+        if (tid < 12) (&cnt[0][0])[tid] = 0;                            // ready for the next batch (ordered by the barrier below)
         // ---- pass 2: emit ----
         if (p.out) {
             Lut4<T> lut[4];
@@ -890,6 +930,20 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
             const unsigned staged_bytes = inter_bytes + 4u * rec16;
             const bool staged = p.bulk_ok && staged_bytes <= max_smem && !getenv("PSTB_GATHER_NOSTAGE");
             if (staged) {
+                uint32_t* d_mask = nullptr;
+                if (p.mode != PSTB_STD_NONE && !p.use_stats) {
+                    p.mask_words = (p.iid_count + 15) / 16;
+                    if (cudaMallocAsync(reinterpret_cast<void**>(&d_mask), (size_t)(p.mask_words + 1) * 4, st) == cudaSuccess) {
+                        PSTB_CUDA(cudaMemsetAsync(d_mask, 0, (size_t)(p.mask_words + 1) * 4, st));
+                        long long g = (n_out + 255) / 256;
+                        if (g > (long long)sms * 8) g = (long long)sms * 8;
+                        k_build_sel_mask<<<(unsigned)g, 256, 0, st>>>(p.iid, p.iid_count, d_mask, p.mask_words);
+                        PSTB_AFTER_LAUNCH("k_build_sel_mask");
+                        p.sel_mask = d_mask;
+                    } else {
+                        cudaGetLastError();                       // no pool memory: count through the gather instead
+                    }
+                }
                 // one CTA per SM: TMA-staged raw records for batch b+1 while batch b is counted and written
                 int threads = nq >= 1024 ? 1024 : (int)(((nq + 31) / 32) * 32);
                 if (threads < 64) threads = 64;
@@ -901,6 +955,7 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
                 if (grid > nbatch) grid = nbatch;
                 k_read_f_gather4<T, true><<<(unsigned)grid, threads, staged_bytes, st>>>(p);
                 PSTB_AFTER_LAUNCH("k_read_f_gather4<staged>");
+                if (d_mask) PSTB_CUDA(cudaFreeAsync(d_mask, st));
                 return 0;
             }
             // 4 byte-interleaved records per batch loaded straight from global; two CTAs per SM when the tile is <= ~110 KiB

@@ -310,3 +310,20 @@ def test_launch_counter_moves(dev, oracle):
     packed = oracle.synth_packed(64, 0, 8, 0.0, seed=0)
     dev.read(dev.PackedStore.from_host(packed, 64), dtype=np.float32)
     assert _lib.lib.pstb_launch_count() > before
+
+
+@pytest.mark.parametrize("n,m", [(203, 31), (4099, 21), (70001, 9)])
+def test_standardize_with_repeated_and_reversed_indices(n, m, oracle, dev):
+    """Statistics are over the SELECTED individuals with multiplicity: a repeated index must count twice
+    (the selection-mask shortcut of the gather kernel has to fall back)."""
+    rng = np.random.default_rng(n)
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.1, seed=n + 7)
+    store = dev.PackedStore.from_host(packed, n)
+    for ii in (rng.integers(0, n, size=n // 2 + 3), np.arange(n)[::-3], np.concatenate([rng.permutation(n)[:50], [0, 0, n - 1]])):
+        raw = oracle.decode(packed, n, ii)
+        for std, args in ((("unit",), (False, np.nan, np.nan)), (("beta", 2, 10), (True, 2, 10))):
+            ref, rst = oracle.standardize(raw, *args)
+            for dtype, order in ((np.float64, "F"), (np.float32, "F"), (np.float64, "C")):
+                val, st = dev.read(store, ii, None, dtype=dtype, order=order, standardizer=std)
+                np.testing.assert_allclose(_np(st), rst, rtol=1e-12)
+                np.testing.assert_allclose(_np(val), ref, rtol=STD_RTOL, atol=1e-6 if dtype == np.float32 else 1e-12)

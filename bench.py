@@ -357,14 +357,25 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
     chunk = args.kernel_chunk
 
+    marks = []
+
     def step():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
         dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1))
+        ev[1].record()
         if world > 1:
             dist.all_reduce(K)                                                       # sum of partial K_r over NVLink
+            ev[2].record()
             _lib.check(_lib.lib.pstb_mirror_lower(K.data_ptr(), n, n, torch.cuda.current_stream().cuda_stream))
+        else:
+            ev[2].record()
+        ev[3].record()
+        marks.append(ev)
 
     step()
     barrier()
+    marks.clear()
     l0 = _lib.lib.pstb_launch_count()
     steps = max(1, min(args.steps, args.kernel_steps))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,6 +385,9 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    breakdown = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
+                 "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
+                 "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks]))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
     tiles = sum(1 for i in range((n + 127) // 128) for j in range((n + 255) // 256) if j * 256 <= i * 128 + 127)
     executed = 3.0 * 2 * 128 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
@@ -384,7 +398,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                        "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "fp16 hi/lo, 3 MMA terms, lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)"},
             "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
                          "note": "executed MMA flops per rank (3 terms x lower-triangular tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained"},
-            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m}
+            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown}
 
 
 def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks):

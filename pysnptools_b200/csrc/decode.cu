@@ -176,14 +176,19 @@ __device__ __forceinline__ void emit_column<double>(const unsigned char* rec, do
     }
 }
 
-__device__ __forceinline__ uint32_t i8x4(const Lut4<int8_t>& lut, uint32_t byte) {
-    uint32_t x0 = (uint8_t)lut.pick(byte & 3u), x1 = (uint8_t)lut.pick((byte >> 2) & 3u);
-    uint32_t x2 = (uint8_t)lut.pick((byte >> 4) & 3u), x3 = (uint8_t)lut.pick(byte >> 6);
-    return x0 | (x1 << 8) | (x2 << 16) | (x3 << 24);
+// int8 output: the four table values fit one 32-bit word, so PRMT (byte permute) looks up all four genotypes of a packed
+// byte at once -- the selector nibbles are the 2-bit codes themselves.
+__device__ __forceinline__ uint32_t i8_lutword(const Lut4<int8_t>& lut) {
+    return (uint32_t)(uint8_t)lut.c0 | ((uint32_t)(uint8_t)lut.c1 << 8) | ((uint32_t)(uint8_t)lut.c2 << 16) | ((uint32_t)(uint8_t)lut.c3 << 24);
+}
+__device__ __forceinline__ uint32_t i8x4(uint32_t lutword, uint32_t byte) {
+    const uint32_t sel = (byte & 0x3u) | ((byte & 0xcu) << 2) | ((byte & 0x30u) << 4) | ((byte & 0xc0u) << 6);
+    return __byte_perm(lutword, 0u, sel);
 }
 
 template <>
 __device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, int8_t* o, long long n_out, const Lut4<int8_t>& lut, int vec, int gid, int gsize) {
+    const uint32_t lw = i8_lutword(lut);
     if (vec == 2 && ((reinterpret_cast<uintptr_t>(rec) & 7u) == 0)) {
         const long long nw = n_out >> 5;                          // 32 genotypes = 8 packed bytes = 32 output bytes
         const uint2* rec64 = reinterpret_cast<const uint2*>(rec);
@@ -192,8 +197,8 @@ __device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, in
             uint32_t r[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                r[k] = i8x4(lut, (two.x >> (8 * k)) & 0xffu);
-                r[4 + k] = i8x4(lut, (two.y >> (8 * k)) & 0xffu);
+                r[k] = i8x4(lw, (two.x >> (8 * k)) & 0xffu);
+                r[4 + k] = i8x4(lw, (two.y >> (8 * k)) & 0xffu);
             }
             st256_b32(o + (w << 5), r);
         }
@@ -206,7 +211,7 @@ __device__ __forceinline__ void emit_column<int8_t>(const unsigned char* rec, in
             uint32_t word = rec32[w];
             uint32_t r[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) r[k] = i8x4(lut, (word >> (8 * k)) & 0xffu);
+            for (int k = 0; k < 4; ++k) r[k] = i8x4(lw, (word >> (8 * k)) & 0xffu);
             __stcs(o16 + w, make_uint4(r[0], r[1], r[2], r[3]));
         }
         emit_scalar<int8_t>(rec, o, nw << 4, n_out, lut, gid, gsize);

@@ -227,20 +227,38 @@ __device__ __forceinline__ int code_of(T x, int count_a1, int* bad) {
     return 1;
 }
 
+// One thread packs 16 genotypes of one SNP into a 32-bit word.  F order (individuals contiguous) reads them with 128-bit
+// loads when the column is 16-byte aligned; every other layout walks the strides.
 template <typename T>
 __global__ void __launch_bounds__(256) k_pack(const T* val, long long si, long long sj, long long n_iid, long long n_sid,
                                               int count_a1, uint8_t* packed, long long ld, int32_t* d_bad) {
-    const long long rec = (n_iid + 3) / 4, total = rec * n_sid;
+    const long long rec = (n_iid + 3) / 4, words = (n_iid + 15) / 16, total = words * n_sid;
+    const bool word_store = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(packed) & 3u) == 0);
     int bad = 0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long j = e / rec, q = e % rec;
-        uint32_t byte = 0;
+        // adjacent threads read adjacent memory: next 16-genotype word of the same SNP (F order) or next SNP (C order)
+        const long long j = (sj == 1) ? e % n_sid : e / words, w = (sj == 1) ? e / n_sid : e % words, i0 = w * 16;
+        const T* src = val + i0 * si + j * sj;
+        uint32_t word = 0;
+        if (si == 1 && i0 + 16 <= n_iid && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            T v[16];
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(v);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            long long i = 4 * q + t;
-            if (i < n_iid) byte |= (uint32_t)code_of<T>(val[i * si + j * sj], count_a1, &bad) << (2 * t);
+            for (int k = 0; k < (int)sizeof(T); ++k) d4[k] = __ldg(s4 + k);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) word |= (uint32_t)code_of<T>(v[t], count_a1, &bad) << (2 * t);
+        } else {
+            for (int t = 0; t < 16; ++t)
+                if (i0 + t < n_iid) word |= (uint32_t)code_of<T>(src[t * si], count_a1, &bad) << (2 * t);
         }
-        packed[j * ld + q] = (uint8_t)byte;
+        uint8_t* dst = packed + j * ld + 4 * w;
+        if (word_store && 4 * w + 4 <= rec) {
+            *reinterpret_cast<uint32_t*>(dst) = word;
+        } else {
+            for (int k = 0; k < 4; ++k)
+                if (4 * w + k < rec) dst[k] = (uint8_t)(word >> (8 * k));
+        }
     }
     if (bad && d_bad) *d_bad = 1;
 }
@@ -321,7 +339,7 @@ extern "C" int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid,
     else if (order == PSTB_ORDER_F) { si = 1; sj = n_iid; }
     else return fail("bad order");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    long long grid = (rec * n_sid + 255) / 256;
+    long long grid = (((n_iid + 15) / 16) * n_sid + 255) / 256;
     const long long cap = (long long)sm_count_cached() * 16;
     if (grid > cap) grid = cap;
     if (dtype == PSTB_F32) k_pack<float><<<(unsigned)grid, 256, 0, st>>>((const float*)d_val, si, sj, n_iid, n_sid, count_a1, d_packed, ld, d_bad);

@@ -64,3 +64,12 @@ if "variants" in which:
     run("decode+Unit f32 F N=50k (cta)", 50000, 200000, np.float32, "F", ("unit",))
     run("decode+Unit f32 F N=500k (cta)", 500000, 20000, np.float32, "F", ("unit",))
     run("decode+Unit f32 F N=300", 300, 4000000, np.float32, "F", ("unit",))
+if "pack" in which:
+    for dt, es in ((torch.int8, 1), (torch.float32, 4)):
+        n, m = 10000, 200000
+        v = torch.randint(0, 3, (m, n), device="cuda").to(dt).t()       # F-order [n, m]
+        ms = timeit(lambda: dev.pack(v))
+        print("pack %s F n=%d m=%d: %.3f ms  %.0f GB/s (read %d B + write 0.25 B per genotype)" % (str(dt), n, m, ms, n * m * (es + 0.25) / ms / 1e6, es), flush=True)
+        vc = v.contiguous()
+        ms = timeit(lambda: dev.pack(vc))
+        print("pack %s C n=%d m=%d: %.3f ms  %.0f GB/s" % (str(dt), n, m, ms, n * m * (es + 0.25) / ms / 1e6), flush=True)

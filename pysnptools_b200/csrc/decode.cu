@@ -802,8 +802,7 @@ struct VecStore<int8_t, 4> {
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_emit_c(const ReadParams p, long long tiles_i) {
     constexpr int TS = kTileS * V;
-    // row pitch: V * pitch == 4 (mod 128) bytes, so the rows V*lane + k of the 32 lanes fall into 32 different banks
-    constexpr int kPitch = kTileI / 4 + (V == 1 ? 4 : (V == 2 ? 2 : 1));
+    constexpr int kPitch = kTileI / 4 + 4;          // 33 words: word-aligned rows; lanes V apart cost at most a V-way bank conflict
     __shared__ __align__(16) unsigned char codes[TS][kPitch];
     __shared__ T lut_s[TS][4];
     // consecutive CTAs take consecutive 512-individual blocks of the SAME records: their 128-byte packed reads are adjacent
@@ -814,30 +813,38 @@ __global__ void __launch_bounds__(256) k_emit_c(const ReadParams p, long long ti
     const long long n_out = p.iid.n;
     const int rows = (int)min((long long)kTileI, n_out - i0);
     const int nsnp = (int)min((long long)TS, p.sid.n - b0);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    // packed bytes of the tile -> shared memory (one byte = 4 consecutive output individuals)
+    // packed bytes of the tile -> shared memory (one byte = 4 consecutive output individuals); one warp per record:
+    // 32 lanes x 32-bit loads = the record's 128-byte fragment in one coalesced request
     const int nbytes = (rows + 3) >> 2;
-    for (int e = threadIdx.x; e < nsnp * (kTileI / 4); e += blockDim.x) {
-        const int s = e / (kTileI / 4), q = e % (kTileI / 4);
-        if (q >= nbytes) continue;
+    const bool word_ok = p.dense && (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.packed) & 3u) == 0) && (p.byte_off % 4 == 0);
+    for (int s = warp; s < nsnp; s += nwarps) {
         const long long j = clampll(p.sid.at(b0 + s), p.sid_count);
         const uint8_t* src = p.packed + j * p.ld;
-        uint32_t byte;
-        if (p.dense) {
-            byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+        if (word_ok) {
+            // the fragment may run up to 3 bytes past the record inside its ld padding; those codes are never emitted
+            const uint8_t* frag = src + p.byte_off + (i0 >> 2);
+            if (4 * lane < nbytes) *reinterpret_cast<uint32_t*>(&codes[s][4 * lane]) = __ldg(reinterpret_cast<const uint32_t*>(frag) + lane);
         } else {
-            byte = 0;
+            for (int q = lane; q < nbytes; q += 32) {
+                uint32_t byte;
+                if (p.dense) {
+                    byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+                } else {
+                    byte = 0;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                long long a = i0 + 4 * q + t;
-                if (a < n_out) {
-                    long long i = clampll(p.iid.at(a), p.iid_count);
-                    byte |= ((uint32_t)(__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u) << (2 * t);
+                    for (int t = 0; t < 4; ++t) {
+                        long long a = i0 + 4 * q + t;
+                        if (a < n_out) {
+                            long long i = clampll(p.iid.at(a), p.iid_count);
+                            byte |= ((uint32_t)(__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u) << (2 * t);
+                        }
+                    }
                 }
+                codes[s][q] = (unsigned char)byte;
             }
         }
-        codes[s][q] = (unsigned char)byte;
     }
     for (int s = threadIdx.x; s < nsnp; s += blockDim.x) {
         double mean = 0.0, sd = 1.0;
@@ -851,27 +858,35 @@ __global__ void __launch_bounds__(256) k_emit_c(const ReadParams p, long long ti
     __syncthreads();
     if (V * lane >= nsnp) return;
     Lut4<T> lut[V];
+    const unsigned char* crow[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int s = min(V * lane + k, nsnp - 1);
         lut[k].c0 = lut_s[s][0]; lut[k].c1 = lut_s[s][1]; lut[k].c2 = lut_s[s][2]; lut[k].c3 = lut_s[s][3];
+        crow[k] = codes[s];
     }
-    T* o = reinterpret_cast<T*>(p.out) + i0 * p.out_ld + b0 + V * lane;
-    const int nwarps = blockDim.x >> 5;
     const bool full = V * lane + V <= nsnp;
-#pragma unroll 4
-    for (int r = warp; r < rows; r += nwarps) {
-        T v[V];
+    // one shared-memory byte serves 4 consecutive rows: each warp takes row quads q = warp, warp + nwarps, ...
+    T* dst = reinterpret_cast<T*>(p.out) + (i0 + 4LL * warp) * p.out_ld + b0 + V * lane;
+    const long long dstep = 4LL * nwarps * p.out_ld;
+    for (int q = warp; q < nbytes; q += nwarps, dst += dstep) {
+        uint32_t byte[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const int s = min(V * lane + k, TS - 1);
-            v[k] = lut[k].pick(((uint32_t)codes[s][r >> 2] >> (2 * (r & 3))) & 3u);
+        for (int k = 0; k < V; ++k) byte[k] = crow[k][q];
+        const int nr = min(4, rows - 4 * q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < nr) {
+                T v[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = lut[k].pick((byte[k] >> (2 * t)) & 3u);
+                T* d = dst + (long long)t * p.out_ld;
+                if (full) VecStore<T, V>::st(d, v);
+                else
+                    for (int k = 0; k < V; ++k)
+                        if (V * lane + k < nsnp) d[k] = v[k];
+            }
         }
-        T* dst = o + (long long)r * p.out_ld;
-        if (full) VecStore<T, V>::st(dst, v);
-        else
-            for (int k = 0; k < V; ++k)
-                if (V * lane + k < nsnp) dst[k] = v[k];
     }
 }
 

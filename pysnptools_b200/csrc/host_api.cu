@@ -5,6 +5,7 @@
 // output overlap, so the call runs at the speed of the device->host link.  Pinned caller buffers
 // (pstb_host_alloc) are copied directly; pageable ones go through internal pinned staging.
 #include <cstring>
+#include <thread>
 #include <vector>
 #include "pstb_common.cuh"
 
@@ -78,6 +79,33 @@ bool is_pinned(const void* p) {
         return false;
     }
     return at.type == cudaMemoryTypeHost;
+}
+
+// pageable destinations: copy out of the pinned ring with several host threads (a single memcpy stream tops out near
+// 10 GB/s and first-touch page faults of a fresh NumPy array are serial otherwise)
+int host_copy_threads() {
+    static int n = [] {
+        unsigned hc = std::thread::hardware_concurrency();
+        int v = hc ? (int)hc / 2 : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return n;
+}
+
+template <typename F>
+void parallel_ranges(size_t count, size_t min_per_thread, F&& body) {
+    int nt = host_copy_threads();
+    if (count < 2 * min_per_thread) nt = 1;
+    if ((size_t)nt > count / min_per_thread) nt = (int)(count / min_per_thread);
+    if (nt <= 1) { body((size_t)0, count); return; }
+    std::vector<std::thread> th;
+    const size_t per = (count + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) {
+        const size_t lo = (size_t)t * per, hi = lo + per < count ? lo + per : count;
+        if (lo < hi) th.emplace_back([&body, lo, hi] { body(lo, hi); });
+    }
+    body((size_t)0, per < count ? per : count);
+    for (auto& x : th) x.join();
 }
 
 size_t esize_of(int dtype) { return dtype == PSTB_F64 ? 8 : (dtype == PSTB_F32 ? 4 : 1); }
@@ -172,10 +200,13 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         const int64_t b0 = pend[slot].b0, ns = pend[slot].ns;
         const char* src = (const char*)c.h_out[slot].p;
         if (order == PSTB_ORDER_F) {
-            memcpy((char*)h_out + (size_t)b0 * col_bytes, src, (size_t)ns * col_bytes);
+            char* dst = (char*)h_out + (size_t)b0 * col_bytes;
+            parallel_ranges((size_t)ns * col_bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
         } else {
-            for (int64_t i = 0; i < n_iid; ++i)
-                memcpy((char*)h_out + ((size_t)i * n_sid + b0) * es, src + (size_t)i * ns * es, (size_t)ns * es);
+            parallel_ranges((size_t)n_iid, 256, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i)
+                    memcpy((char*)h_out + (i * (size_t)n_sid + (size_t)b0) * es, src + i * (size_t)ns * es, (size_t)ns * es);
+            });
         }
         return 0;
     };
@@ -197,10 +228,12 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         } else {
             if (c.h_in[slot].ensure((size_t)chunk * ld)) return 1;
             char* stage = (char*)c.h_in[slot].p;
-            for (int64_t k = 0; k < ns; ++k) {
-                const int64_t j = h_sid_idx ? h_sid_idx[b0 + k] : b0 + k;
-                memcpy(stage + (size_t)k * ld, h_packed + (size_t)j * rec, (size_t)rec);
-            }
+            parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) {
+                for (size_t k = lo; k < hi; ++k) {
+                    const int64_t j = h_sid_idx ? h_sid_idx[b0 + (int64_t)k] : b0 + (int64_t)k;
+                    memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
+                }
+            });
             PSTB_CUDA(cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
         }
         // ---- kernel ----

@@ -110,11 +110,27 @@ class SnpReader(object):
 
     # --- reading ---
     def read(self, order="F", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None,
-             _require_float32_64=True, to_device=False):
-        """Read into a :class:`SnpData`.  ``to_device=True`` keeps ``val`` as a CUDA tensor (extension)."""
+             _require_float32_64=True, to_device=False, standardizer=None, return_trained=False):
+        """Read into a :class:`SnpData`.
+
+        Extensions over the reference signature: ``to_device=True`` keeps ``val`` as a CUDA tensor; ``standardizer=Unit()``
+        (or Beta / a trained one) fuses ``read(...).standardize(standardizer)`` into ONE pass on the GPU, so the raw matrix
+        never exists and the values cross PCIe once (``return_trained=True`` also returns the trained standardizer).
+        """
         dtype = np.dtype(dtype)
-        val = self._read(None, None, order, dtype, force_python_only, view_ok, num_threads, to_device=to_device)
-        return SnpData(self.iid, self.sid, val, pos=self.pos, name=str(self), _require_float32_64=_require_float32_64)
+        if standardizer is None or isinstance(standardizer, Identity):
+            val = self._read(None, None, order, dtype, force_python_only, view_ok, num_threads, to_device=to_device)
+            data = SnpData(self.iid, self.sid, val, pos=self.pos, name=str(self), _require_float32_64=_require_float32_64)
+            return (data, standardizer) if return_trained else data
+        spec = standardizer._device_spec()
+        stats_in = standardizer._trained_stats_for(self.sid)
+        val, stats = self._read(None, None, order, dtype, force_python_only, view_ok, num_threads, to_device=to_device,
+                                _standardize=(spec, stats_in))
+        data = SnpData(self.iid, self.sid, val, pos=self.pos, name=str(self))
+        data._std_string_list.append(str(standardizer))
+        if return_trained:
+            return data, standardizer._make_trained(self.sid, np.asarray(stats, dtype=dtype))
+        return data
 
     def read_kernel(self, standardizer=None, block_size=None, order="A", dtype=np.float64, force_python_only=False,
                     view_ok=False, num_threads=None):
@@ -205,9 +221,11 @@ class _SnpSubset(SnpReader):
     def sid_count(self):
         return self._internal.sid_count if self._sid_index is None else len(self._sid_index)
 
-    def _read(self, iid_index_or_none, sid_index_or_none, order, dtype, force_python_only, view_ok, num_threads, to_device=False):
+    def _read(self, iid_index_or_none, sid_index_or_none, order, dtype, force_python_only, view_ok, num_threads, to_device=False,
+              _standardize=None):
+        kw = {} if _standardize is None else {"_standardize": _standardize}
         return self._internal._read(_compose(self._iid_index, iid_index_or_none), _compose(self._sid_index, sid_index_or_none),
-                                    order, dtype, force_python_only, view_ok, num_threads, to_device=to_device)
+                                    order, dtype, force_python_only, view_ok, num_threads, to_device=to_device, **kw)
 
     def _root_and_indices(self):
         root, ii, si = self._internal._root_and_indices()
@@ -338,11 +356,15 @@ class Bed(SnpReader):
             raise ValueError("dtype must be float32, float64 or int8")
         if order == "A":
             order = "F"
+        spec, stats_in = _standardize if _standardize is not None else (None, None)
+        if spec is not None and dtype == np.int8:
+            raise ValueError("standardizing needs a float32 / float64 read")
         if to_device:
             from . import device
             store, ssel = self._store_for(sid_index_or_none)
-            val, _ = device.read(store, iid_index_or_none, ssel, count_A1=self.count_A1, dtype=dtype, order=order)
-            return val
+            val, st = device.read(store, iid_index_or_none, ssel, count_A1=self.count_A1, dtype=dtype, order=order,
+                                  standardizer=spec, stats=stats_in)
+            return val if spec is None else (val, st.cpu().numpy())
         packed = self._packed_host()
         n, m = self.iid_count, self.sid_count
         ii = None if iid_index_or_none is None else np.ascontiguousarray(iid_index_or_none, dtype=np.int64)
@@ -352,12 +374,22 @@ class Bed(SnpReader):
                 raise IndexError("index out of range for axis of size {0}".format(cnt))
         ni, ns = (n if ii is None else len(ii)), (m if si is None else len(si))
         val = np.empty((ni, ns), dtype=dtype, order=order)
+        mode, a, b, use_stats = _lib.STD_NONE, 0.0, 0.0, 0
+        stats = None
+        if spec is not None:
+            mode = _lib.STD_UNIT if spec[0] == "unit" else _lib.STD_BETA
+            a, b = (float(spec[1]), float(spec[2])) if spec[0] == "beta" else (float("nan"), float("nan"))
+            stats = np.empty((ns, 2), dtype=np.float64)
+            if stats_in is not None:
+                stats[...] = np.asarray(stats_in, dtype=np.float64)
+                use_stats = 1
         if ni and ns:
             _lib.require_gpu()
             _lib.check(_lib.lib.pstb_read_host(packed.ctypes.data, n, m, ii.ctypes.data if ii is not None else None, ni,
                                                si.ctypes.data if si is not None else None, ns, int(bool(self.count_A1)),
-                                               _lib.STD_NONE, 0.0, 0.0, 0, None, val.ctypes.data, _DT_CODE[dtype], _order_code(order)))
-        return val
+                                               mode, a, b, use_stats, stats.ctypes.data if stats is not None else None,
+                                               val.ctypes.data, _DT_CODE[dtype], _order_code(order)))
+        return val if spec is None else (val, stats)
 
     # --- write (bed.py:229-316 -> to_bed) ---
     @staticmethod

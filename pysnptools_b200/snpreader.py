@@ -152,6 +152,13 @@ class SnpReader(object):
         from . import device
         dtype = np.dtype(dtype)
         root, iid_idx, sid_idx = self._root_and_indices()
+        if hasattr(root, "_read_kernel_pieces"):                  # DistributedBed: one packed store per piece, K accumulated
+            if not isinstance(standardizer, Standardizer) or (standardizer._device_spec() is None and not isinstance(standardizer, Identity)):
+                raise NotImplementedError("read_kernel on the GPU supports Unit, Beta, their trained forms and Identity")
+            res = root._read_kernel_pieces(iid_idx, sid_idx, standardizer, block_size, dtype, return_trained)
+            val = res[0] if return_trained else res
+            val = np.asarray(val, order="F" if order == "F" else "C")
+            return (val, res[1]) if return_trained else val
         store, ssel_local = root._store_for(sid_idx)
         sid_labels = self.sid
         spec = standardizer._device_spec() if isinstance(standardizer, Standardizer) else None

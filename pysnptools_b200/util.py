@@ -42,3 +42,75 @@ def sub_matrix(val, row_index_list, col_index_list, order="A", dtype=np.float64,
                                              len(rows), cols.ctypes.data, len(cols), out.ctypes.data, _CODE[dtype],
                                              _lib.ORDER_C if order == "C" else _lib.ORDER_F))
     return out
+
+
+# ---- intersect_apply (util/__init__.py:18-198): caller-side bookkeeping either side of the hot path ----------------
+def intersect_ids(idslist):
+    """For id lists [n_k, 2] (None entries allowed) -> int array [n_common, len(idslist)]: row r gives, for each list, the
+    position of the r-th id common to all non-None lists (-1 column for a None list)."""
+    lookups = []
+    for ids in idslist:
+        lookups.append(None if ids is None else {tuple(x): k for k, x in enumerate(np.asarray(ids))})
+    live = [d for d in lookups if d is not None]
+    if not live:
+        return np.zeros((0, len(idslist)), dtype=np.int64)
+    first = live[0]
+    common = [key for key in first if all(key in d for d in live[1:])]           # order of the first non-None list
+    out = np.full((len(common), len(idslist)), -1, dtype=np.int64)
+    for c, d in enumerate(lookups):
+        if d is not None:
+            out[:, c] = [d[key] for key in common]
+    return out
+
+
+def _same_ids(iid_list):
+    live = [np.asarray(x) for x in iid_list if x is not None]
+    return all(a.shape == live[0].shape and np.array_equal(a, live[0]) for a in live[1:])
+
+
+def intersect_apply(data_list, sort_by_dataset=True, intersect_before_standardize=True, is_test=False):
+    """Give every dataset the same individuals in the same order (reference: util/__init__.py:18-173).
+
+    Understood: ``None``; SnpReader-like (``.iid`` + ``[iid_idx, :]``); SnpKernel (the subset is pushed INTO its reader
+    before standardizing when ``intersect_before_standardize``); square kernels (``[iid_idx]``); ``{'iid':..,'vals':..}``
+    dictionaries (changed in place); ``(val, iid)`` tuples.  Unchanged inputs are returned when the ids already agree.
+    """
+    from .kernelreader import KernelData, SnpKernel
+    if len(data_list) == 0:
+        raise Exception("Expect a least one input item")
+    iid_list, reindex_list = [], []
+    for data in data_list:
+        if data is None:
+            iid, reindex = None, (lambda d, idx: None)
+        elif isinstance(data, SnpKernel):
+            iid = data.iid
+            if intersect_before_standardize:
+                reindex = lambda d, idx: SnpKernel(d.snpreader[idx, :], d.standardizer, block_size=d.block_size) if d._index is None else d[idx]
+            else:
+                reindex = lambda d, idx: d[idx]
+        elif isinstance(data, KernelData):
+            iid = data.iid1 if is_test else data.iid0
+            reindex = (lambda d, idx: d[:, idx]) if (is_test and not np.array_equal(data.iid0, data.iid1)) else (lambda d, idx: d[idx])
+        elif isinstance(data, dict):
+            iid = data["iid"]
+
+            def reindex(d, idx):
+                d["iid"] = np.asarray(d["iid"])[idx]
+                d["vals"] = np.asarray(d["vals"])[idx]
+                return d
+        elif hasattr(data, "iid"):
+            iid, reindex = data.iid, (lambda d, idx: d[idx, :])
+        else:
+            iid, reindex = data[1], (lambda d, idx: (np.asarray(d[0])[idx], np.asarray(d[1])[idx]))
+        iid_list.append(iid)
+        reindex_list.append(reindex)
+    if _same_ids(iid_list):
+        return data_list
+    indarr = intersect_ids(iid_list)
+    assert indarr.shape[0] > 0, "no individuals remain after intersection, check that ids match in files"
+    if sort_by_dataset:
+        for c, iid in enumerate(iid_list):
+            if iid is not None:
+                indarr = indarr[np.argsort(indarr[:, c], kind="stable")]
+                break
+    return [reindex_list[c](data_list[c], indarr[:, c]) for c in range(len(data_list))]

@@ -64,6 +64,16 @@ def main():
             shutil.copyfile(os.path.join(REF, stem + ext), dst)
             os.chmod(dst, 0o644)
 
+    # DistributedBed fixture (snpreader/distributedbed.py:296-311): pieces written with count_A1=True == distributed_bed_test1_X
+    dst_dir = os.path.join(data, "distributed_bed_test1")
+    if os.path.isdir(dst_dir):
+        shutil.rmtree(dst_dir)
+    shutil.copytree(os.path.join(REF, "tests/datasets/distributed_bed_test1"), dst_dir)
+    for root_, _dirs, files in os.walk(dst_dir):
+        os.chmod(root_, 0o755)
+        for f_ in files:
+            os.chmod(os.path.join(root_, f_), 0o644)
+
     g = {}
     # ---------------- decode goldens (values the reference ships) ----------------
     n300 = Bed(os.path.join(REF, FILES["n300"] + ".bed"), count_A1=False)

@@ -250,3 +250,36 @@ def test_fused_read_standardize_extension(golden):
     _, trained = bed[10:, :].read(standardizer=Unit(), return_trained=True)
     test = bed[:10, :].read(standardizer=trained)
     np.testing.assert_allclose(test.val, golden["n300_trained_unit_test_val"], rtol=1e-11, atol=1e-13)
+
+
+def test_distributed_bed(golden, tmp_path):
+    """TestDistributedBed.test1 (snpreader/distributedbed.py:296-311): pieces == distributed_bed_test1_X; K over pieces."""
+    from pysnptools_b200 import DistributedBed, Unit
+    d = DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1"))
+    want = i8_to_float(golden["dbx_decode_i8"])
+    for order in ("F", "C"):
+        assert np.array_equal(d.read(order=order).val, want, equal_nan=True)
+    sub = d[::-3, [99, 0, 50, 1, 98]].read(dtype=np.float32)
+    assert np.array_equal(sub.val, want[::-3][:, [99, 0, 50, 1, 98]].astype(np.float32), equal_nan=True)
+    K, trained = d._read_kernel(Unit(), block_size=10, return_trained=True)
+    assert rel_fro(K, golden["dbx_unit_K"]) < 1e-5
+    np.testing.assert_allclose(trained.stats, golden["dbx_unit_stats"], rtol=1e-12)
+    assert rel_fro(d.read_kernel(Unit()).val, golden["dbx_unit_K"]) < 1e-5
+    back = DistributedBed.write(str(tmp_path / "dist"), _bed("dbx"), piece_per_chrom_count=2)
+    assert back.sid_count == 100 and np.array_equal(back.read().val, want, equal_nan=True)
+    assert np.array_equal(back.sid, d.sid)
+
+
+def test_intersect_apply_with_kernel(golden):
+    from pysnptools_b200 import SnpKernel, Unit
+    from pysnptools_b200.util import intersect_apply
+    bed = _bed("n300")
+    ids = bed.iid[np.arange(298, -1, -2)]                                     # every second individual, reversed
+    kern, (vals, iid) = intersect_apply([SnpKernel(bed, Unit()), (np.arange(150.0).reshape(-1, 1), ids)])
+    assert np.array_equal(kern.iid, bed.iid[::2]) and np.array_equal(iid, bed.iid[::2]) and vals[0, 0] == 149.0
+    packed, n, m = fixture_packed("n300")
+    from oracle import bed_oracle
+    ref, _ = bed_oracle.read_kernel(packed, n, iid_index=np.arange(0, 300, 2))     # standardized on the 150 kept individuals
+    assert rel_fro(kern.read().val, ref) < 1e-5
+    late, _ = intersect_apply([SnpKernel(bed, Unit()), (vals, ids)], intersect_before_standardize=False)
+    assert rel_fro(late.read().val, golden["n300_unit_K_every2"]) < 1e-5

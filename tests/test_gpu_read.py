@@ -327,3 +327,23 @@ def test_standardize_with_repeated_and_reversed_indices(n, m, oracle, dev):
                 val, st = dev.read(store, ii, None, dtype=dtype, order=order, standardizer=std)
                 np.testing.assert_allclose(_np(st), rst, rtol=1e-12)
                 np.testing.assert_allclose(_np(val), ref, rtol=STD_RTOL, atol=1e-6 if dtype == np.float32 else 1e-12)
+
+
+def test_all_missing_and_constant_snps(oracle, dev):
+    """Unpinned edges, python-twin behaviour: an all-missing SNP gives zeros with NaN statistics; an SNC SNP gives sd = inf."""
+    n, m = 77, 6
+    packed = oracle.synth_packed(n, 0, m, 0.1, seed=1)
+    packed[2, :] = 0x55                                            # every code 01 = missing
+    packed[4, :] = 0x00                                            # every dosage 0: no variation
+    store = dev.PackedStore.from_host(packed, n)
+    for std in (("unit",), ("beta", 1, 25)):
+        for order in ("F", "C"):
+            val, st = dev.read(store, dtype=np.float64, order=order, standardizer=std)
+            v, s = _np(val), _np(st)
+            assert np.all(v[:, 2] == 0) and np.isnan(s[2]).all()
+            assert np.all(v[:, 4] == 0) and s[4, 0] == 0 and np.isinf(s[4, 1])
+            assert not np.isnan(v).any()
+    K, _ = dev.snp_kernel(store, chunk=64)
+    x, _ = oracle.standardize(oracle.decode(packed[[0, 1, 3, 5]], n))
+    ref = x @ x.T
+    assert np.linalg.norm(_np(K).astype(np.float64) - ref) / np.linalg.norm(ref) < 1e-5

@@ -175,3 +175,39 @@ def test_kernel_tile_ownership_partitions_lower_triangle():
                     seen.add((int(I), int(J)))
                 sizes.append(count)
             assert len(seen) == T * (T + 1) // 2 and max(sizes) - min(sizes) <= 1
+
+
+def test_intersect_apply_host_side():
+    """util.intersect_apply semantics (util/__init__.py:18-173) on host-only datasets."""
+    from pysnptools_b200 import SnpData, SnpKernel, Unit, Bed
+    from pysnptools_b200.util import intersect_apply
+    iid_a = np.array([["f", "a"], ["f", "b"], ["f", "c"], ["f", "d"]])
+    a = SnpData(iid=iid_a, sid=["s1", "s2"], val=np.arange(8.0).reshape(4, 2))
+    tup = (np.array([[10.0], [20.0], [30.0]]), np.array([["f", "d"], ["f", "a"], ["f", "c"]]))
+    dic = {"iid": np.array([["f", "c"], ["f", "z"], ["f", "a"], ["f", "d"]]), "vals": np.array([[1.0], [2.0], [3.0], [4.0]])}
+    none_out, a2, tup2, dic2 = intersect_apply([None, a, tup, dic])
+    want = np.array([["f", "a"], ["f", "c"], ["f", "d"]])                    # order of the first non-None dataset
+    assert none_out is None and dic2 is dic
+    assert np.array_equal(a2.iid, want) and np.array_equal(tup2[1], want) and np.array_equal(dic2["iid"], want)
+    assert np.array_equal(tup2[0].ravel(), [20.0, 30.0, 10.0]) and np.array_equal(dic2["vals"].ravel(), [3.0, 1.0, 4.0])
+    same = intersect_apply([a, (np.zeros((4, 1)), iid_a)])
+    assert same[0] is a                                                      # ids already agree: inputs returned unchanged
+    bed = Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    kern = SnpKernel(bed, Unit(), block_size=100)
+    pheno = (np.zeros((3, 1)), bed.iid[[7, 2, 250]])
+    k2, p2 = intersect_apply([kern, pheno])
+    assert isinstance(k2, SnpKernel) and k2.iid_count == 3 and np.array_equal(k2.iid, bed.iid[[2, 7, 250]])
+    assert k2.snpreader.iid_count == 3                                       # subset pushed into the reader (before standardizing)
+    k3, _ = intersect_apply([kern, pheno], intersect_before_standardize=False)
+    assert k3.snpreader.iid_count == 300 and k3.iid_count == 3
+    with pytest.raises(AssertionError):
+        intersect_apply([a, (np.zeros((1, 1)), np.array([["q", "q"]]))])
+
+
+def test_distributed_bed_metadata():
+    from pysnptools_b200 import DistributedBed
+    d = DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1"))
+    assert (d.iid_count, d.sid_count) == (100, 100) and d.sid[0] == "sid_0" and d.pos.shape == (100, 3)
+    sid, parts = d._split(np.array([99, 0, 50, 1]))
+    assert sum(len(w) for _, _, w in parts) == 4 and all(len(local) == len(w) for _, local, w in parts)
+    assert pickle.loads(pickle.dumps(d)).sid_count == 100

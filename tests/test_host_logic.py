@@ -211,3 +211,15 @@ def test_distributed_bed_metadata():
     sid, parts = d._split(np.array([99, 0, 50, 1]))
     assert sum(len(w) for _, _, w in parts) == 4 and all(len(local) == len(w) for _, local, w in parts)
     assert pickle.loads(pickle.dumps(d)).sid_count == 100
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference (the CPU port of the reference path) runs without a GPU and prints one JSON line."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-sample-sid", "300"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "genotypes/s decoded+standardized" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True

@@ -43,6 +43,7 @@ struct ReadParams {
     int direct;             // record too large for shared memory: gather straight from global, in segments
     long long seg_len;      // outputs per segment (multiple of 16) when direct
     int vec_ok;             // output columns: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = neither
+    unsigned int* miss_flag;    // optional: set to 1 when any selected genotype of any processed SNP is missing (K3 picks its GEMM by it)
     const uint32_t* sel_mask;   // gather: 2 bits per individual (0b01 = selected), built once per call; word [mask_words] = "index vector has repeats"
     long long mask_words;
 };
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
                 }
                 const long long c0 = n_out - (long long)c1 - (long long)c2 - (long long)c3;
                 stats_from_counts(p.count_a1 ? (long long)c3 : c0, (long long)c2, p.count_a1 ? c0 : (long long)c3, mean, sd);
+                if (gid == 0 && c1 && p.miss_flag) *p.miss_flag = 1u;
                 if (gid == 0 && p.stats) {
                     p.stats[2 * b] = mean;
                     p.stats[2 * b + 1] = sd;
@@ -499,6 +501,7 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
                 } else {
                     const long long c1 = cnt[tid][0], c2 = cnt[tid][1], c3 = cnt[tid][2], c0 = n_out - c1 - c2 - c3;
                     stats_from_counts(p.count_a1 ? c3 : c0, c2, p.count_a1 ? c0 : c3, mean, sd);
+                    if (c1 && p.miss_flag) *p.miss_flag = 1u;
                     if (p.stats) {
                         p.stats[2 * (b0 + tid)] = mean;
                         p.stats[2 * (b0 + tid) + 1] = sd;
@@ -727,6 +730,7 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
                 } else {
                     const long long c1 = cnt[tid][0], c2 = cnt[tid][1], c3 = cnt[tid][2], c0 = n_out - c1 - c2 - c3;
                     stats_from_counts(p.count_a1 ? c3 : c0, c2, p.count_a1 ? c0 : c3, mean, sd);
+                    if (c1 && p.miss_flag) *p.miss_flag = 1u;
                     if (p.stats) {
                         p.stats[2 * (b0 + tid)] = mean;
                         p.stats[2 * (b0 + tid) + 1] = sd;
@@ -1065,9 +1069,20 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     return 0;
 }
 
+int read_impl_ex(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+                 int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
+                 void* stream, unsigned int* d_miss_flag);
+
 int read_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
               int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
               void* stream) {
+    return read_impl_ex(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_out, dtype, order, stream,
+                        nullptr);
+}
+
+int read_impl_ex(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+                 int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
+                 void* stream, unsigned int* d_miss_flag) {
     if (iid_count < 0 || sid_count < 0) return fail("negative iid_count / sid_count");
     const int64_t rec = (iid_count + 3) / 4;
     if (ld < rec) return fail("ld (%lld) smaller than ceil(iid_count/4) (%lld)", (long long)ld, (long long)rec);
@@ -1098,6 +1113,7 @@ int read_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t si
     p.lnB = (mode == PSTB_STD_BETA) ? lgamma(a) + lgamma(b) - lgamma(a + b) : 0.0;
     p.stats = d_stats;
     p.out = d_out;
+    p.miss_flag = d_miss_flag;
     p.dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 16) == 0) ? 1 : 0;
     p.byte_off = p.dense ? iid.start / 4 : 0;
     p.rec_bytes = (unsigned)rec;

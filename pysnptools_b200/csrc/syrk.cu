@@ -26,9 +26,9 @@
 #include "pstb_common.cuh"
 
 namespace pstb {
-int read_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
-              int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
-              void* stream);
+int read_impl_ex(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+                 int count_a1, int mode, double a, double b, int use_stats, double* d_stats, void* d_out, int dtype, int order,
+                 void* stream, unsigned int* d_miss_flag);
 
 namespace {
 
@@ -46,9 +46,23 @@ constexpr int GROUP_I = 16, GROUP_J = 8;                  // tile rasterisation:
 
 // scalars block in the workspace
 struct Scalars {
-    unsigned int absmax_bits;   // float bits of max |v| over the chunk (atomicMax on positive floats)
-    unsigned int pad[63];
+    unsigned int absmax_bits;    // float bits of max |x| over the chunk (atomicMax on positive floats): 3-term split of x
+    unsigned int absmax_w_bits;  // float bits of max |w * h| over the chunk: exact-dosage path
+    unsigned int any_missing;    // != 0: some selected genotype of the chunk is missing (or the statistics were given): 3-term path
+    unsigned int pad[61];
 };
+
+// Exact-dosage path (chunks without missing data): x = (g - mu) * f with f = 1/sd (Unit) or BetaPDF (Beta).  Round mu to 10
+// fractional bits, mu' = mu + delta: h = g - mu' is EXACT in fp16 (|h| <= 2, 10 fractional bits) and centred, so
+//   K = sum_j w_j h_i h_k  +  (u_i + u_k)  +  c,   w = f^2,  u_i = sum_j w_j delta_j h_ij,  c = sum_j w_j delta_j^2.
+// The GEMM is h * (w h)^T with only the right operand split hi + lo: 2 MMAs per k-step instead of 3, no dropped term; the
+// rank-one part is accumulated in fp64 by k_planes and added once per call by k_apply_rank1.
+__device__ __forceinline__ double round_mu(double mean) { return rint(mean * 1024.0) * (1.0 / 1024.0); }
+__device__ __forceinline__ double weight_of(int mode, double mean, double sd, double a, double b, double lnB) {
+    if (!(sd == sd) || isinf(sd) || !(mean == mean)) return 0.0;
+    const double f = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 1.0 / sd;
+    return f * f;
+}
 
 __device__ __forceinline__ int scale_exponent(unsigned int absmax_bits) {
     // scale = 2^(14 - e) with absmax < 2^e, clamped so 1/scale^2 stays a normal float
@@ -61,7 +75,7 @@ __device__ __forceinline__ int scale_exponent(unsigned int absmax_bits) {
 
 __global__ void k_absmax(const double* stats, long long ns, int mode, double a, double b, double lnB, Scalars* sc) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.0f;
+    float m = 0.0f, mw = 0.0f;
     if (s < ns) {
         const double mean = stats[2 * s], sd = stats[2 * s + 1];
         const double f = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
@@ -69,10 +83,17 @@ __global__ void k_absmax(const double* stats, long long ns, int mode, double a, 
             double v = fabs(std_value(mode, (double)g, mean, sd, f));
             if (v == v && v < 1e300) m = fmaxf(m, __double2float_ru(v));
         }
+        const double w = weight_of(mode, mean, sd, a, b, lnB), mu = round_mu(mean);
+        const double hv = w * fmax(fabs(mu), fabs(2.0 - mu));
+        if (hv == hv && hv < 1e300) mw = fmaxf(mw, __double2float_ru(hv));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    }
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&sc->absmax_bits, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && mw > 0.0f) atomicMax(&sc->absmax_w_bits, __float_as_uint(mw));
 }
 
 // ---- operand planes --------------------------------------------------------------------------------------
@@ -86,8 +107,11 @@ struct PlaneParams {
     double a, b, lnB;
     const double* stats;    // [ns][2] of the chunk
     const Scalars* sc;
-    __half* hi;
-    __half* lo;
+    __half* hi;             // plane 0: x_hi   (exact-dosage path: h)
+    __half* lo;             // plane 1: x_lo   (exact-dosage path: (w h)_hi)
+    __half* p2;             // plane 2: unused (exact-dosage path: (w h)_lo)
+    double* u;              // [n_pad] rank-one vector of the exact-dosage path, accumulated over chunks
+    double* csum;           // scalar c of the exact-dosage path
     long long n_pad, k_pad;
     int dense;
     long long byte_off;
@@ -128,45 +152,86 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         }
         codes[s][q] = (unsigned char)byte;
     }
+    const bool fast = p.sc->any_missing == 0u;
+    __shared__ __half lut_p2[PT_S][4];
+    __shared__ float lut_u[PT_S][4];
     if (threadIdx.x < PT_S) {
         const int s = threadIdx.x;
-        double v[4] = {0.0, 0.0, 0.0, 0.0};                     // by 2-bit code
+        double v[4] = {0.0, 0.0, 0.0, 0.0};                     // by 2-bit code (code 1 = missing stays 0)
+        double hv[4] = {0.0, 0.0, 0.0, 0.0}, wd = 0.0;
         if (b0 + s < p.sid.n) {
             const double mean = p.stats[2 * (b0 + s)], sd = p.stats[2 * (b0 + s) + 1];
-            const double f = (p.mode == PSTB_STD_BETA) ? beta_factor(mean, p.a, p.b, p.lnB) : 0.0;
-            const double scale = ldexp(1.0, scale_exponent(p.sc->absmax_bits));
-            const double v0 = std_value(p.mode, 0.0, mean, sd, f) * scale, v1 = std_value(p.mode, 1.0, mean, sd, f) * scale,
-                         v2 = std_value(p.mode, 2.0, mean, sd, f) * scale;
-            v[0] = p.count_a1 ? v2 : v0;
-            v[2] = v1;
-            v[3] = p.count_a1 ? v0 : v2;
+            if (!fast) {
+                const double f = (p.mode == PSTB_STD_BETA) ? beta_factor(mean, p.a, p.b, p.lnB) : 0.0;
+                const double scale = ldexp(1.0, scale_exponent(p.sc->absmax_bits));
+                const double v0 = std_value(p.mode, 0.0, mean, sd, f) * scale, v1 = std_value(p.mode, 1.0, mean, sd, f) * scale,
+                             v2 = std_value(p.mode, 2.0, mean, sd, f) * scale;
+                v[0] = p.count_a1 ? v2 : v0;
+                v[2] = v1;
+                v[3] = p.count_a1 ? v0 : v2;
+            } else {
+                const double w = weight_of(p.mode, mean, sd, p.a, p.b, p.lnB), mu = round_mu(mean);
+                const double scale = ldexp(1.0, scale_exponent(p.sc->absmax_w_bits));
+                const double h0 = 0.0 - mu, h1 = 1.0 - mu, h2 = 2.0 - mu;
+                hv[0] = p.count_a1 ? h2 : h0;
+                hv[2] = h1;
+                hv[3] = p.count_a1 ? h0 : h2;
+                v[0] = w * hv[0] * scale; v[2] = w * hv[2] * scale; v[3] = w * hv[3] * scale;
+                wd = (w > 0.0) ? w * (mu - mean) : 0.0;
+                if (ti == 0 && w > 0.0) atomicAdd(p.csum, w * (mu - mean) * (mu - mean));
+            }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             double x = v[c];
             if (!(x == x) || fabs(x) > 60000.0) x = 0.0;        // NaN statistics (all-missing SNP) contribute nothing
             const __half h = __float2half_rn((float)x);
-            lut_hi[s][c] = h;
-            lut_lo[s][c] = __float2half_rn((float)(x - (double)__half2float(h)));
+            const __half l = __float2half_rn((float)(x - (double)__half2float(h)));
+            if (!fast) {
+                lut_hi[s][c] = h;
+                lut_lo[s][c] = l;
+                lut_p2[s][c] = __float2half_rn(0.0f);
+                lut_u[s][c] = 0.0f;
+            } else {
+                lut_hi[s][c] = __float2half_rn((float)hv[c]);   // exact: |h| <= 2 with 10 fractional bits
+                lut_lo[s][c] = h;
+                lut_p2[s][c] = l;
+                lut_u[s][c] = (float)(wd * hv[c]);
+            }
         }
     }
     __syncthreads();
     // each lane owns SNPs 2*lane, 2*lane+1 of the tile; a warp writes 128 contiguous bytes per row and plane
-    __half2 h01[4], l01[4];
+    __half2 h01[4], l01[4], q01[4];
+    float ua[4], ub[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { h01[c] = __halves2half2(lut_hi[2 * lane][c], lut_hi[2 * lane + 1][c]); l01[c] = __halves2half2(lut_lo[2 * lane][c], lut_lo[2 * lane + 1][c]); }
+    for (int c = 0; c < 4; ++c) {
+        h01[c] = __halves2half2(lut_hi[2 * lane][c], lut_hi[2 * lane + 1][c]);
+        l01[c] = __halves2half2(lut_lo[2 * lane][c], lut_lo[2 * lane + 1][c]);
+        q01[c] = __halves2half2(lut_p2[2 * lane][c], lut_p2[2 * lane + 1][c]);
+        ua[c] = lut_u[2 * lane][c];
+        ub[c] = lut_u[2 * lane + 1][c];
+    }
     const unsigned char* c0 = codes[2 * lane];
     const unsigned char* c1 = codes[2 * lane + 1];
+    auto sel = [](const __half2 (&t)[4], uint32_t ca, uint32_t cb) {
+        const __half2 x = (ca & 2u) ? ((ca & 1u) ? t[3] : t[2]) : ((ca & 1u) ? t[1] : t[0]);
+        const __half2 y = (cb & 2u) ? ((cb & 1u) ? t[3] : t[2]) : ((cb & 1u) ? t[1] : t[0]);
+        return __halves2half2(__low2half(x), __high2half(y));
+    };
     for (int r = warp; r < PT_I; r += 8) {
         const uint32_t ca = ((uint32_t)c0[r >> 2] >> (2 * (r & 3))) & 3u, cb = ((uint32_t)c1[r >> 2] >> (2 * (r & 3))) & 3u;
-        // pick(low half from ca, high half from cb)
-        const __half2 ha = (ca & 2u) ? ((ca & 1u) ? h01[3] : h01[2]) : ((ca & 1u) ? h01[1] : h01[0]);
-        const __half2 hb = (cb & 2u) ? ((cb & 1u) ? h01[3] : h01[2]) : ((cb & 1u) ? h01[1] : h01[0]);
-        const __half2 la = (ca & 2u) ? ((ca & 1u) ? l01[3] : l01[2]) : ((ca & 1u) ? l01[1] : l01[0]);
-        const __half2 lb = (cb & 2u) ? ((cb & 1u) ? l01[3] : l01[2]) : ((cb & 1u) ? l01[1] : l01[0]);
         const long long off = (i0 + r) * p.k_pad + b0 + 2 * lane;
-        *reinterpret_cast<__half2*>(p.hi + off) = __halves2half2(__low2half(ha), __high2half(hb));
-        *reinterpret_cast<__half2*>(p.lo + off) = __halves2half2(__low2half(la), __high2half(lb));
+        *reinterpret_cast<__half2*>(p.hi + off) = sel(h01, ca, cb);
+        *reinterpret_cast<__half2*>(p.lo + off) = sel(l01, ca, cb);
+        if (fast) {
+            *reinterpret_cast<__half2*>(p.p2 + off) = sel(q01, ca, cb);
+            float uv = ((ca & 2u) ? ((ca & 1u) ? ua[3] : ua[2]) : ((ca & 1u) ? ua[1] : ua[0])) +
+                       ((cb & 2u) ? ((cb & 1u) ? ub[3] : ub[2]) : ((cb & 1u) ? ub[1] : ub[0]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) uv += __shfl_xor_sync(0xffffffffu, uv, o);
+            if (lane == 0 && uv != 0.0f && i0 + r < n_out) atomicAdd(p.u + i0 + r, (double)uv);
+        }
     }
 }
 
@@ -436,7 +501,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
-k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const SyrkParams p) {
+k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_p2,
+        const SyrkParams p) {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[STAGES2], bar_empty[STAGES2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -450,7 +516,10 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_hi);
         prefetch_tmap(&map_lo);
+        prefetch_tmap(&map_p2);
     }
+    // exact-dosage chunk (no missing data): A = h (plane 0), B = (w h)_hi, (w h)_lo (planes 1, 2): two MMAs per k-step
+    const bool fast = p.sc != nullptr && p.sc->any_missing == 0u;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 16); }
@@ -477,12 +546,19 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                     mbar_wait(&bar_empty[stage], phase ^ 1u);
                     const uint32_t sb = tiles_base + stage * STAGE2_BYTES;
                     const uint32_t full = smem_u32(&bar_full[stage]) & 0xFEFFFFFFu;   // the leader CTA's barrier
-                    if (leader) mbar_expect_tx(&bar_full[stage], 2u * STAGE2_BYTES);
                     const int kc = kb * BK;
-                    tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
-                    tma_load_2d_2sm(sb + T_BYTES, &map_lo, kc, row_a, full);
-                    tma_load_2d_2sm(sb + 2 * T_BYTES, &map_hi, kc, row_b, full);
-                    tma_load_2d_2sm(sb + 3 * T_BYTES, &map_lo, kc, row_b, full);
+                    if (fast) {
+                        if (leader) mbar_expect_tx(&bar_full[stage], 2u * 3u * T_BYTES);
+                        tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
+                        tma_load_2d_2sm(sb + 2 * T_BYTES, &map_lo, kc, row_b, full);
+                        tma_load_2d_2sm(sb + 3 * T_BYTES, &map_p2, kc, row_b, full);
+                    } else {
+                        if (leader) mbar_expect_tx(&bar_full[stage], 2u * STAGE2_BYTES);
+                        tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
+                        tma_load_2d_2sm(sb + T_BYTES, &map_lo, kc, row_a, full);
+                        tma_load_2d_2sm(sb + 2 * T_BYTES, &map_hi, kc, row_b, full);
+                        tma_load_2d_2sm(sb + 3 * T_BYTES, &map_lo, kc, row_b, full);
+                    }
                     if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -508,9 +584,15 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, kIdesc2, (k == 0) ? first : 1u);
-                            umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, kIdesc2, 1u);
-                            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, kIdesc2, 1u);
+                            if (fast) {
+                                // slots: a_hi = h, b_hi = (w h)_hi, b_lo = (w h)_lo
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, kIdesc2, (k == 0) ? first : 1u);
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, kIdesc2, 1u);
+                            } else {
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, kIdesc2, (k == 0) ? first : 1u);
+                                umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, kIdesc2, 1u);
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, kIdesc2, 1u);
+                            }
                         }
                         tc_commit_mc2(smem_u32(&bar_empty[stage]));
                         if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
@@ -524,7 +606,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         float scale = p.out_scale;
-        if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
+        if (fast) scale *= exp2f(-(float)scale_exponent(p.sc->absmax_w_bits));            // only the right operand is scaled
+        else if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
         const bool vec = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
         uint32_t run = 0;
         for (int t = cluster_id; t < p.ntiles; t += nclusters) {
@@ -602,6 +685,24 @@ void build_tiles2(long long n, std::vector<int2>& out) {
                 for (int J = gj; J < gj + GROUP2 && J <= I; ++J) out.push_back(make_int2(I, J));
 }
 }  // namespace v2
+
+// exact-dosage path: K_ik += u_i + u_k + c on the lower triangle (once per call, before the mirror)
+__global__ void __launch_bounds__(256) k_apply_rank1(float* K, long long n, long long ldk, const double* u, const double* csum) {
+    const long long i = blockIdx.x;
+    const double ui = u[i] + *csum;
+    for (long long k = (long long)blockIdx.y * blockDim.x + threadIdx.x; k <= i; k += (long long)gridDim.y * blockDim.x)
+        K[i * ldk + k] = (float)((double)K[i * ldk + k] + ui + u[k]);
+}
+// the same on compact tile storage [ntiles][256][256]
+__global__ void __launch_bounds__(256) k_apply_rank1_tiles(float* tiles, const int2* coords, long long n, const double* u, const double* csum) {
+    const int2 t = coords[blockIdx.x];
+    float* base = tiles + (long long)blockIdx.x * 65536;
+    const double c = *csum;
+    for (int e = threadIdx.x; e < 65536; e += blockDim.x) {
+        const long long i = (long long)t.x * 256 + (e >> 8), k = (long long)t.y * 256 + (e & 255);
+        if (i < n && k < n) base[e] = (float)((double)base[e] + u[i] + u[k] + c);
+    }
+}
 
 __global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long ldk) {
     __shared__ float tile[32][33];
@@ -754,16 +855,20 @@ int get_tiles(long long n, int version, int rank, int world, cudaStream_t st, co
 long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad, long long k_pad, float* K, long long ldk,
-                int accumulate, const Scalars* sc, float out_scale, cudaStream_t st, int rank = 0, int world = 1, int compact = 0) {
+                int accumulate, const Scalars* sc, float out_scale, cudaStream_t st, int rank = 0, int world = 1, int compact = 0,
+                const __half* p2 = nullptr, const int2** tiles_out = nullptr, int* ntiles_out = nullptr) {
     if (n_pad % ROW_PAD || k_pad % BK || n_pad < n) return fail("planes must be padded to %d rows / %d columns", ROW_PAD, BK);
     if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi, map_lo, map_p2;
     if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
+    if (make_plane_map(&map_p2, p2 ? p2 : lo, n_pad, k_pad)) return 1;
     static const int env_version = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ? 1 : 2;   // 1-CTA 128x256 kept for A/B runs
     const int version = compact ? 2 : env_version;
     const int2* d_tiles = nullptr;
     int ntiles = 0;
     if (get_tiles(n, version, rank, world, st, &d_tiles, &ntiles)) return 1;
+    if (tiles_out) *tiles_out = d_tiles;
+    if (ntiles_out) *ntiles_out = ntiles;
     SyrkParams p{};
     p.tiles = d_tiles;
     p.ntiles = ntiles;
@@ -785,7 +890,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     if (version == 2) {
         int clusters = sm_count_cached() / 2;
         if (clusters > ntiles) clusters = ntiles;
-        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, p);   // __cluster_dims__(2,1,1)
+        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, p);   // __cluster_dims__(2,1,1)
         PSTB_AFTER_LAUNCH("k_syrk2");
         return 0;
     }
@@ -805,7 +910,7 @@ extern "C" int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk) {
     if (n_iid < 0) n_iid = 0;
     if (chunk < BK) chunk = BK;
     const long long n_pad = round_up(n_iid > 0 ? n_iid : 1, ROW_PAD), k_pad = round_up(chunk, BK);
-    return (int64_t)(2 * n_pad * k_pad * 2 + 1024 + sizeof(Scalars));
+    return (int64_t)(3 * n_pad * k_pad * 2 + 1024 + sizeof(Scalars) + (n_pad + 2) * sizeof(double));
 }
 
 extern "C" int pstb_syrk_planes(const void* d_hi, const void* d_lo, int64_t n, int64_t n_pad, int64_t k_pad, float* d_K,
@@ -865,8 +970,19 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(w) + 1023) & ~(uintptr_t)1023);
     __half* hi = reinterpret_cast<__half*>(w);
     __half* lo = hi + n_pad * k_cap;
-    Scalars* sc = reinterpret_cast<Scalars*>(lo + n_pad * k_cap);
+    __half* p2 = lo + n_pad * k_cap;
+    Scalars* sc = reinterpret_cast<Scalars*>(p2 + n_pad * k_cap);
+    double* u = reinterpret_cast<double*>(sc + 1);
+    double* csum = u + n_pad;
     const int dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
+    // the 2-term exact-dosage GEMM needs the dosage counts of this call (to know that a chunk has no missing data) and the
+    // CTA-pair kernel; trained statistics, PSTB_SYRK_V1=1 or PSTB_SYRK_3TERM=1 keep every chunk on the 3-term split
+    static const bool env_slow = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ||
+                                 (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
+    const bool force_slow = use_stats || env_slow;
+    PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
+    const int2* d_tiles = nullptr;
+    int ntiles = 0;
     for (long long c0 = 0; c0 < sid.n; c0 += chunk) {
         const long long ns = (c0 + chunk <= sid.n) ? chunk : sid.n - c0;
         const long long k_pad = round_up(ns, BK);
@@ -874,12 +990,13 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         sub.n = ns;
         if (sid.idx) sub.idx = sid.idx + c0; else sub.start = sid.start + c0 * sid.step;
         double* st_chunk = d_stats + 2 * c0;
+        PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+        if (force_slow) PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));
         if (!use_stats) {
-            int rc = read_impl(d_packed, ld, iid_count, sid_count, iid, sub, count_a1, mode, a, b, 0, st_chunk, nullptr, PSTB_F32,
-                               PSTB_ORDER_F, stream);
+            int rc = read_impl_ex(d_packed, ld, iid_count, sid_count, iid, sub, count_a1, mode, a, b, 0, st_chunk, nullptr, PSTB_F32,
+                                  PSTB_ORDER_F, stream, &sc->any_missing);
             if (rc) return rc;
         }
-        PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
         k_absmax<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(st_chunk, ns, mode, a, b, lnB, sc);
         PSTB_AFTER_LAUNCH("k_absmax");
         PlaneParams pp{};
@@ -898,6 +1015,9 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         pp.sc = sc;
         pp.hi = hi;
         pp.lo = lo;
+        pp.p2 = p2;
+        pp.u = u;
+        pp.csum = csum;
         pp.n_pad = n_pad;
         pp.k_pad = k_pad;
         pp.dense = dense;
@@ -905,13 +1025,24 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         const long long ptiles = (k_pad / PT_S) * (n_pad / PT_I);
         k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
         PSTB_AFTER_LAUNCH("k_planes");
-        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact);
+        int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact, p2,
+                             &d_tiles, &ntiles);
         if (rc) return rc;
+    }
+    if (!force_slow) {
+        if (compact) {
+            if (ntiles > 0) {
+                k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(d_K, d_tiles, n, u, csum);
+                PSTB_AFTER_LAUNCH("k_apply_rank1_tiles");
+            }
+        } else {
+            k_apply_rank1<<<dim3((unsigned)n, (unsigned)((n + 2047) / 2048 > 64 ? 64 : (n + 2047) / 2048)), 256, 0, st>>>(d_K, n, n, u, csum);
+            PSTB_AFTER_LAUNCH("k_apply_rank1");
+        }
     }
     if (mirror && !compact) return pstb_mirror_lower(d_K, n, n, stream);
     return 0;
 }
-
 
 extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                                pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
@@ -971,6 +1102,7 @@ extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_
     const long long si = (order == PSTB_ORDER_C) ? n_sid : 1, sj = (order == PSTB_ORDER_C) ? 1 : n_iid;
     const long long total = n * n_sid;
     PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));       // arbitrary floats: always the 3-term split
     long long g = (total + 255) / 256;
     if (g > (long long)sm_count_cached() * 16) g = (long long)sm_count_cached() * 16;
     if (dtype == PSTB_F32) k_absmax_float<float><<<(unsigned)g, 256, 0, st>>>((const float*)d_val, total, sc);

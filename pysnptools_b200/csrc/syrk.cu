@@ -290,6 +290,7 @@ struct SyrkParams {
     int accumulate;
     const Scalars* sc;      // NULL -> out_scale is used as is
     float out_scale;
+    int run_kb_fast;        // k-blocks per TMEM run on the 2-term path
     int compact;            // K is tile storage [ntiles][256][256] (K-tile sharding: this rank's tiles only), 2-CTA kernel only
 };
 
@@ -504,7 +505,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
 k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_p2,
         const SyrkParams p) {
     extern __shared__ uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t bar_full[STAGES2], bar_empty[STAGES2], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[STAGES2 + 1], bar_empty[STAGES2 + 1], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -520,8 +521,10 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     }
     // exact-dosage chunk (no missing data): A = h (plane 0), B = (w h)_hi, (w h)_lo (planes 1, 2): two MMAs per k-step
     const bool fast = p.sc != nullptr && p.sc->any_missing == 0u;
+    // the 2-term loop spends a third less time per k-block, so it gets a fourth (smaller) stage from the same 192 KiB ring
+    const uint32_t nstages = fast ? STAGES2 + 1 : STAGES2, stage_bytes = fast ? 3u * T_BYTES : STAGE2_BYTES;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES2; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < STAGES2 + 1; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 16); }
         fence_mbar_init();
     }
@@ -533,7 +536,9 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const int num_runs = (p.num_kb + RUN_KB - 1) / RUN_KB;
+    // k-blocks per TMEM run: the same number of truncating accumulates (48) per run in both paths unless overridden
+    const int run_kb = fast ? p.run_kb_fast : RUN_KB;
+    const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
@@ -544,14 +549,14 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                 const int row_a = tile.x * TM + (int)rank * 128, row_b = tile.y * TN + (int)rank * 128;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1u);
-                    const uint32_t sb = tiles_base + stage * STAGE2_BYTES;
+                    const uint32_t sb = tiles_base + stage * stage_bytes;
                     const uint32_t full = smem_u32(&bar_full[stage]) & 0xFEFFFFFFu;   // the leader CTA's barrier
                     const int kc = kb * BK;
                     if (fast) {
                         if (leader) mbar_expect_tx(&bar_full[stage], 2u * 3u * T_BYTES);
                         tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
-                        tma_load_2d_2sm(sb + 2 * T_BYTES, &map_lo, kc, row_b, full);
-                        tma_load_2d_2sm(sb + 3 * T_BYTES, &map_p2, kc, row_b, full);
+                        tma_load_2d_2sm(sb + T_BYTES, &map_lo, kc, row_b, full);
+                        tma_load_2d_2sm(sb + 2 * T_BYTES, &map_p2, kc, row_b, full);
                     } else {
                         if (leader) mbar_expect_tx(&bar_full[stage], 2u * STAGE2_BYTES);
                         tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
@@ -559,7 +564,7 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                         tma_load_2d_2sm(sb + 2 * T_BYTES, &map_hi, kc, row_b, full);
                         tma_load_2d_2sm(sb + 3 * T_BYTES, &map_lo, kc, row_b, full);
                     }
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -573,14 +578,15 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                     mbar_wait(&bar_tempty[acc], ((run >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TN;
-                    const int kb_end = min(p.num_kb, (r + 1) * RUN_KB);
-                    for (int kb = r * RUN_KB; kb < kb_end; ++kb) {
+                    const int kb_end = min(p.num_kb, (r + 1) * run_kb);
+                    for (int kb = r * run_kb; kb < kb_end; ++kb) {
                         mbar_wait(&bar_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t sb = tiles_base + stage * STAGE2_BYTES;
+                        const uint32_t sb = tiles_base + stage * stage_bytes;
+                        // 3-term: [x_hi | x_lo | B x_hi | B x_lo];  2-term: [h | B (w h)_hi | B (w h)_lo]
                         const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + T_BYTES);
-                        const uint64_t b_hi = make_smem_desc(sb + 2 * T_BYTES), b_lo = make_smem_desc(sb + 3 * T_BYTES);
-                        const uint32_t first = (kb == r * RUN_KB) ? 0u : 1u;
+                        const uint64_t b_hi = make_smem_desc(sb + (fast ? 1 : 2) * T_BYTES), b_lo = make_smem_desc(sb + (fast ? 2 : 3) * T_BYTES);
+                        const uint32_t first = (kb == r * run_kb) ? 0u : 1u;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -595,7 +601,7 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                             }
                         }
                         tc_commit_mc2(smem_u32(&bar_empty[stage]));
-                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit_mc2(smem_u32(&bar_tfull[acc]));
                 }
@@ -880,6 +886,8 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.sc = sc;
     p.out_scale = out_scale;
     p.compact = compact;
+    static const int run_kb_fast_env = getenv("PSTB_RUN_KB_FAST") ? atoi(getenv("PSTB_RUN_KB_FAST")) : 0;
+    p.run_kb_fast = (run_kb_fast_env >= 1 && run_kb_fast_env <= 16) ? run_kb_fast_env : 6;
     static thread_local bool attr_set = false;
     if (!attr_set) {
         PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));

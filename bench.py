@@ -463,7 +463,7 @@ def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks)
     need = len(coords) * 256 * 256 * 4
     free, _total = torch.cuda.mem_get_info()
     rec = (n + 3) // 4
-    chunk = 2048
+    chunk = 4096
     budget = need + m * (rec + 16) + int(_lib.lib.pstb_kernel_workspace_bytes(n, chunk)) + (2 << 30)
     if budget > free:
         return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "unavailable": "cfg5 needs {0:.0f} GB per GPU at {1} GPUs ({2:.0f} GB free); run with more GPUs or --cfg5-n".format(budget / 1e9, world, free / 1e9)}

@@ -111,14 +111,15 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe), sampled every 20 ms for the whole run; windows are
+    cut out afterwards by wall-clock time (nvidia-smi needs a few hundred ms to start, the cfg2 timed region lasts ~80 ms)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.thread = [], None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -129,25 +130,41 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
+    def wait_started(self, timeout=3.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.02)
+
+    def window(self, t0, t1):
+        """Median SM clock and the throttle reasons seen between t0 and t1 (the nearest later samples if the window is shorter
+        than the sampling period)."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end and not any(t >= t1 for t, _ in self.rows):
+            time.sleep(0.02)
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.03]
+        if not rows:
+            rows = [r for (t, r) in self.rows if t > t1][:2] or [r for (_, r) in self.rows[-2:]]
+        sm, smax, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows[-3:]]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0]))
                 smax = float(f[1])
+                power.append(float(f[2]))
                 for k, nm in enumerate(names):
                     if f[3 + k].lower().startswith("active"):
                         reasons.add(nm)
             except (ValueError, IndexError):
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "power_w_max": max(power) if power else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 def gen_store_device(dev, torch, n_iid, n_sid, seed, missing_rate=0.0):
@@ -241,10 +258,12 @@ def run_gpu(args):
         _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n_iid, n_sid, full[0], full[1], 0, _lib.STD_UNIT,
                                                float("nan"), float("nan"), 0, stats.data_ptr(), out.data_ptr(), _lib.F32, _lib.ORDER_F, stream))
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.pstb_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0 = time.perf_counter()
@@ -260,7 +279,7 @@ def run_gpu(args):
     launches = lib.pstb_launch_count() - launches0
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = sampler.window(t0, t1) if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * n_iid * n_sid / (ms_per_step * 1e-3)
 
@@ -311,7 +330,9 @@ def run_gpu(args):
     # ---- SnpKernel (cfg3) ----
     kernel = None
     if args.kernel:
-        kernel = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks)
+        kernel = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler)
+    if sampler:
+        sampler.close()
 
     if rank == 0:
         line = {
@@ -401,7 +422,7 @@ def run_api_e2e(torch, store, n_iid, n_sid, rec):
             "api": "Bed(file).read(order='F', dtype=float32, standardizer=Unit()) -> pageable NumPy array (file in the page cache)"}
 
 
-def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks):
+def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler=None):
     """cfg3: SnpKernel(Unit) on 50 000 x 500 000, SNP-sharded over the ranks, one NCCL all-reduce of K."""
     n, m = (args.kernel_n, args.kernel_m)
     m_lo, m_hi = rank * m // world, (rank + 1) * m // world
@@ -431,12 +452,15 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     l0 = _lib.lib.pstb_launch_count()
     steps = max(1, min(args.steps, args.kernel_steps))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tk0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     barrier()
+    tk1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    kclocks = sampler.window(tk0, tk1) if sampler else None
     breakdown = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
                  "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
                  "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks]))}
@@ -453,7 +477,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                        "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "exact fp16 dosage x fp16 hi/lo weights ({0} MMA terms per k-step; 3-term hi/lo split when a chunk has missing data), lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)".format(terms)},
             "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
                          "note": "executed MMA flops per rank ({0} terms x lower-triangular tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained".format(terms)},
-            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown}
+            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
 
 
 def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks):

@@ -16,6 +16,13 @@ SHAPES = {"n300": (300, 1015), "toydata": (500, 10000), "dbx": (100, 100), "snpg
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the shared objects are build artefacts (git-ignored): build them when a fresh checkout has none (nvcc cross-compiles without a GPU)
+    import subprocess
+    lib = os.path.join(ROOT, "pysnptools_b200", "libpst_b200.so")
+    if not os.path.exists(lib):
+        subprocess.call(["bash", os.path.join(ROOT, "pysnptools_b200", "csrc", "build.sh")], stdout=subprocess.DEVNULL)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_build", "libpst_oracle.so")):
+        subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")

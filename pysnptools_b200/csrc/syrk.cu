@@ -888,12 +888,9 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.compact = compact;
     static const int run_kb_fast_env = getenv("PSTB_RUN_KB_FAST") ? atoi(getenv("PSTB_RUN_KB_FAST")) : 0;
     p.run_kb_fast = (run_kb_fast_env >= 1 && run_kb_fast_env <= 16) ? run_kb_fast_env : 6;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
-        PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
-        attr_set = true;
-    }
+    // per launch, not cached: the attribute belongs to the (function, device) pair and a thread may switch devices
+    PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
+    PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
     if (ntiles < 1) return 0;
     if (version == 2) {
         int clusters = sm_count_cached() / 2;
@@ -962,8 +959,15 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
     if (iid.n == 0) return 0;
-    if (!d_K) return fail("d_K is NULL");
     if (sid.n > 0 && !d_stats) return fail("d_stats is NULL");
+    if (compact && pstb_kernel_tile_count(iid.n, rank, world) == 0) {
+        // more ranks than tiles: this rank owns nothing, but its caller still gets the per-SNP statistics
+        if (sid.n > 0 && !use_stats)
+            return read_impl_ex(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, 0, d_stats, nullptr, PSTB_F32, PSTB_ORDER_F,
+                                stream, nullptr);
+        return 0;
+    }
+    if (!d_K) return fail("d_K is NULL");
     if (chunk < BK || chunk % BK) return fail("chunk must be a positive multiple of %d", BK);
     if (work_bytes < pstb_kernel_workspace_bytes(iid.n, chunk) || !d_work) return fail("workspace too small (pstb_kernel_workspace_bytes)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -104,7 +104,7 @@ def test_convert_kernel(dev):
     assert out.dtype == torch.float64 and torch.allclose(out, K.double() * 2.0)
 
 
-@pytest.mark.parametrize("n,m,world", [(700, 300, 1), (1500, 700, 3), (2100, 400, 8)])
+@pytest.mark.parametrize("n,m,world", [(700, 300, 1), (1500, 700, 3), (2100, 400, 8), (200, 130, 3)])   # last: more ranks than tiles
 def test_kernel_tile_sharding(n, m, world, oracle, dev):
     """K-tile sharding (cfg5 path): every rank's tiles together are exactly K; no tile is owned twice."""
     packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + world)

@@ -73,3 +73,7 @@ if "pack" in which:
         vc = v.contiguous()
         ms = timeit(lambda: dev.pack(vc))
         print("pack %s C n=%d m=%d: %.3f ms  %.0f GB/s" % (str(dt), n, m, ms, n * m * (es + 0.25) / ms / 1e6), flush=True)
+if "nsweep" in which:
+    for n in (300, 1000, 2000, 4000, 8000, 16000, 24000, 32000):
+        m = int(4e9 // (4 * n)) // 8 * 8
+        run("decode+Unit f32 F N=%d" % n, n, m, np.float32, "F", ("unit",))

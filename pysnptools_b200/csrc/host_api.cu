@@ -4,6 +4,7 @@
 // H2D of packed records (2 bits / genotype), the fused decode(+standardize) kernel, and D2H of the float
 // output overlap, so the call runs at the speed of the device->host link.  Pinned caller buffers
 // (pstb_host_alloc) are copied directly; pageable ones go through internal pinned staging.
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -42,20 +43,22 @@ struct Buf {
     }
 };
 
+constexpr int kSlots = 4;     // pipeline depth of the host-buffer read: H2D, repack, kernel and D2H of different chunks overlap
+
 struct HostCtx {
     int device = -1;
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    Buf d_packed[2], d_out[2], d_stats, d_idx, d_work, h_in[2], h_out[2];
+    cudaStream_t s[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
+    Buf d_packed[kSlots], d_tight[kSlots], d_out[kSlots], d_stats, d_idx, d_work, h_in[kSlots], h_out[kSlots];
     HostCtx() {
-        for (int k = 0; k < 2; ++k) { h_in[k].host = true; h_out[k].host = true; }
+        for (int k = 0; k < kSlots; ++k) { h_in[k].host = true; h_out[k].host = true; }
     }
     int init() {
         int dev = 0;
         PSTB_CUDA(cudaGetDevice(&dev));
         if (dev == device) return 0;
-        for (int k = 0; k < 2; ++k) {
-            d_packed[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release();
+        for (int k = 0; k < kSlots; ++k) {
+            d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release();
             if (s[k]) cudaStreamDestroy(s[k]);
             if (done[k]) cudaEventDestroy(done[k]);
             PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
@@ -174,7 +177,8 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
     const int64_t rec = (iid_count + 3) / 4;
     const int64_t ld = pstb_packed_ld(iid_count);
     const size_t col_bytes = (size_t)n_iid * es;
-    const size_t target = (size_t)64 << 20;
+    static const size_t target_mb = [] { const char* e = getenv("PSTB_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)((v >= 1 && v <= 4096) ? v : 64); }();
+    const size_t target = target_mb << 20;             // output bytes per pipeline chunk (tuning knob: PSTB_HOST_CHUNK_MB)
     int64_t chunk = (int64_t)(target / (col_bytes > (size_t)ld ? col_bytes : (size_t)ld));
     if (chunk < 1) chunk = 1;
     if (order == PSTB_ORDER_C && chunk < 64) chunk = 64;   // keep the strided D2H rows at >= 256 bytes
@@ -186,12 +190,12 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
         if (use_stats) PSTB_CUDA(cudaMemcpy(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice));
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kSlots; ++k) {
         if (c.d_packed[k].ensure((size_t)chunk * ld) || c.d_out[k].ensure((size_t)chunk * col_bytes)) return 1;
         if (!out_pinned && c.h_out[k].ensure((size_t)chunk * col_bytes)) return 1;
     }
 
-    struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[2];
+    struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kSlots];
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return 0;
         PSTB_CUDA(cudaEventSynchronize(c.done[slot]));
@@ -214,7 +218,7 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
     int rc = 0;
     int64_t nchunks = (n_sid + chunk - 1) / chunk;
     for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
-        const int slot = (int)(ch & 1);
+        const int slot = (int)(ch % kSlots);
         const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
         if ((rc = finish(slot))) break;
         cudaStream_t st = c.s[slot];
@@ -223,8 +227,15 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
         for (int64_t k = 1; h_sid_idx && k < ns && contiguous; ++k) contiguous = h_sid_idx[b0 + k] == j0 + k;
         if (contiguous && packed_pinned) {
-            PSTB_CUDA(cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, h_packed + (size_t)j0 * rec, (size_t)rec, (size_t)rec,
-                                        (size_t)ns, cudaMemcpyHostToDevice, st));
+            // one contiguous DMA over PCIe (rows of ceil(N/4) bytes make a slow 2-D copy), then re-pitch to ld on the device
+            if (ld == rec) {
+                PSTB_CUDA(cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
+            } else {
+                if (c.d_tight[slot].ensure((size_t)chunk * rec)) return 1;
+                PSTB_CUDA(cudaMemcpyAsync(c.d_tight[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
+                PSTB_CUDA(cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns,
+                                            cudaMemcpyDeviceToDevice, st));
+            }
         } else {
             if (c.h_in[slot].ensure((size_t)chunk * ld)) return 1;
             char* stage = (char*)c.h_in[slot].p;
@@ -257,7 +268,7 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         pend[slot].ns = ns;
         pend[slot].active = true;
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kSlots; ++k) {
         int r2 = finish(k);
         if (!rc) rc = r2;
     }

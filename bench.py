@@ -385,7 +385,7 @@ def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank
     h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_float)), shape=(m, n_iid))
     e2e_ok = bool(np.array_equal(h_stats[:256], stats[lo:lo + 256].cpu().numpy())) and bool(np.isfinite(h_out[-1]).all())
     res = {"value": n_iid * n_sid / dt_e, "unit": "genotypes/s", "h2d_bytes_per_step": n_sid * rec, "d2h_bytes_per_step": n_iid * n_sid * 4 + 16 * n_sid,
-           "ms_per_step": dt_e * 1e3, "steps": e2e_steps, "api": "pstb_read_host (host-buffer C ABI), pinned host buffers, 64 MiB chunks on 2 streams",
+           "ms_per_step": dt_e * 1e3, "steps": e2e_steps, "api": "pstb_read_host (host-buffer C ABI), pinned host buffers, 64 MiB chunks on 4 streams",
            "work": "one cfg2 workload in total" + ("" if world == 1 else ", SNP ranges split over the {0} ranks; bytes are totals over ranks".format(world)),
            "stats_match_device_run": e2e_ok}
     del h_out, h_packed

@@ -19,6 +19,21 @@ def get_num_threads(num_threads=None):
     return os.cpu_count() or 1
 
 
+def pinned_empty(shape, dtype=np.float64, order="F"):
+    """An uninitialised NumPy array in page-locked host memory (``pstb_host_alloc``): as ``out=`` of ``Bed.read`` it is filled
+    by direct DMA at PCIe speed.  The memory is released when the array (and every view of it) is garbage collected."""
+    import ctypes
+    import weakref
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    ptr = _lib.lib.pstb_host_alloc(max(1, count * dtype.itemsize))
+    if not ptr:
+        raise MemoryError(_lib.last_error())
+    raw = (ctypes.c_uint8 * max(1, count * dtype.itemsize)).from_address(ptr)
+    weakref.finalize(raw, _lib.lib.pstb_host_free, ptr)          # the ctypes buffer is the base object of every view below
+    return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape, order="F" if order in ("F", "A") else "C")
+
+
 def sub_matrix(val, row_index_list, col_index_list, order="A", dtype=np.float64, num_threads=None):
     """``val[row_index_list][:, col_index_list]`` for 2-D or 3-D arrays, in the given order / dtype, gathered on the GPU."""
     val = np.asarray(val)

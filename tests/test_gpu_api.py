@@ -283,3 +283,25 @@ def test_intersect_apply_with_kernel(golden):
     assert rel_fro(kern.read().val, ref) < 1e-5
     late, _ = intersect_apply([SnpKernel(bed, Unit()), (vals, ids)], intersect_before_standardize=False)
     assert rel_fro(late.read().val, golden["n300_unit_K_every2"]) < 1e-5
+
+
+def test_read_into_out_and_pinned_buffers(golden):
+    """read(out=...) fills a caller-owned array (pinned memory from util.pinned_empty goes by direct DMA)."""
+    from pysnptools_b200 import Unit
+    from pysnptools_b200.util import pinned_empty
+    bed = _bed("n300")
+    want = i8_to_float(golden["n300_decode_i8"], np.float32)
+    for order in ("F", "C"):
+        buf = pinned_empty((300, 1015), dtype=np.float32, order=order)
+        assert buf.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"] and buf.flags["WRITEABLE"]
+        d = bed.read(order=order, dtype=np.float32, out=buf)
+        assert d.val is buf and np.array_equal(buf, want, equal_nan=True)
+        d2 = bed.read(order=order, dtype=np.float32, standardizer=Unit(), out=buf)
+        np.testing.assert_allclose(buf[:, :160], golden["n300_unit_val"], rtol=1e-5, atol=1e-6)
+    sub = np.empty((150, 10), dtype=np.float64, order="F")
+    assert bed[::2, :10].read(out=sub).val is sub and np.array_equal(sub, want[::2, :10].astype(np.float64), equal_nan=True)
+    with pytest.raises(ValueError):
+        bed.read(out=np.empty((3, 3)))
+    del buf, d, d2
+    import gc
+    gc.collect()

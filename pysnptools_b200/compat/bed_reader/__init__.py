@@ -199,16 +199,30 @@ def to_bed(filepath, val, properties={}, count_A1=True, fam_filepath=None, bim_f
         f.write(bytes([0x6C, 0x1B, 0x01]))
         f.write(packed.tobytes())
 
-    def col(name, count, default):
+    def text(x, missing, integral):
+        # NaN -> the column's missing value ('0'); integral floats without a decimal point (PLINK writes '1', not '1.0')
+        if isinstance(x, (float, np.floating)):
+            if x != x:
+                return missing
+            if integral or float(x).is_integer():
+                return str(int(x))
+            return repr(float(x))
+        return str(x)
+
+    def col(name, count, default, missing="0", integral=False):
         v = properties.get(name)
-        return [default(k) for k in range(count)] if v is None else list(v)
+        if v is None:
+            return [default(k) for k in range(count)]
+        if len(v) != count:
+            raise ValueError("property '{0}' has {1} entries, expected {2}".format(name, len(v), count))
+        return [text(x, missing, integral) for x in list(v)]
     fam = [col("fid", n, lambda k: "0"), col("iid", n, lambda k: "iid{0}".format(k + 1)), col("father", n, lambda k: "0"),
            col("mother", n, lambda k: "0"), col("sex", n, lambda k: 0), col("pheno", n, lambda k: "0")]
     with open(fam_filepath or base + ".fam", "w") as f:
         for k in range(n):
             f.write(" ".join(str(c[k]) for c in fam) + "\n")
     bim = [col("chromosome", m, lambda k: "0"), col("sid", m, lambda k: "sid{0}".format(k + 1)), col("cm_position", m, lambda k: 0.0),
-           col("bp_position", m, lambda k: 0), col("allele_1", m, lambda k: "A1"), col("allele_2", m, lambda k: "A2")]
+           col("bp_position", m, lambda k: 0, integral=True), col("allele_1", m, lambda k: "A1"), col("allele_2", m, lambda k: "A2")]
     with open(bim_filepath or base + ".bim", "w") as f:
         for k in range(m):
             f.write("\t".join(str(c[k]) for c in bim) + "\n")

@@ -9,7 +9,75 @@ from .snpreader import _compose, _resolve_indexer
 from .standardizer import DiagKtoN, Identity, _is_tensor
 
 
-class KernelData(object):
+class KernelReader(object):
+    """Accessor surface shared by KernelData and SnpKernel (kernelreader/kernelreader.py:60-243); subclasses give row / col."""
+
+    @property
+    def iid0(self):
+        return self.row
+
+    @property
+    def iid1(self):
+        return self.col
+
+    @property
+    def iid(self):
+        assert self.row is self.col or np.array_equal(self.row, self.col), "When 'iid' is used, iid0 must be the same as iid1"
+        return self.row
+
+    @property
+    def iid_count(self):
+        return len(self.iid)
+
+    @property
+    def iid0_count(self):
+        return len(self.row)
+
+    @property
+    def iid1_count(self):
+        return len(self.col)
+
+    row_count = iid0_count
+    col_count = iid1_count
+
+    @property
+    def shape(self):
+        return (self.iid0_count, self.iid1_count)
+
+    @property
+    def row_property(self):
+        return np.empty((self.iid0_count, 0))
+
+    @property
+    def col_property(self):
+        return np.empty((self.iid1_count, 0))
+
+    @property
+    def val_shape(self):
+        return None
+
+    @staticmethod
+    def _to_index(labels, wanted):
+        lookup = {tuple(x): i for i, x in enumerate(labels)}
+        return np.array([lookup[tuple(x)] for x in wanted], dtype=np.int64)
+
+    def iid0_to_index(self, list):
+        return self._to_index(self.row, list)
+
+    def iid1_to_index(self, list):
+        return self._to_index(self.col, list)
+
+    def iid_to_index(self, list):
+        return self._to_index(self.iid, list)
+
+    row_to_index = iid0_to_index
+    col_to_index = iid1_to_index
+
+    def copyinputs(self, copier):
+        pass
+
+
+class KernelData(KernelReader):
     """In-memory kernel: ``val`` [iid0_count, iid1_count] + iids."""
     _is_kernel = True
 
@@ -39,14 +107,6 @@ class KernelData(object):
         self._val = new_value
 
     @property
-    def iid0(self):
-        return self._row
-
-    @property
-    def iid1(self):
-        return self._col
-
-    @property
     def row(self):
         return self._row
 
@@ -54,28 +114,14 @@ class KernelData(object):
     def col(self):
         return self._col
 
-    @property
-    def iid(self):
-        assert self._row is self._col or np.array_equal(self._row, self._col), "When 'iid' is used, iid0 must be the same as iid1"
-        return self._row
+    def allclose(self, value, equal_nan=True):
+        """Same iids and close values (kerneldata.py:113-134)."""
+        def arr(v):
+            return v.cpu().numpy() if _is_tensor(v) else np.asarray(v)
+        return (np.array_equal(self.iid0, value.iid0) and np.array_equal(self.iid1, value.iid1)
+                and bool(np.allclose(arr(self.val), arr(value.val), equal_nan=equal_nan)))
 
-    @property
-    def iid_count(self):
-        return len(self.iid)
-
-    @property
-    def iid0_count(self):
-        return len(self._row)
-
-    @property
-    def iid1_count(self):
-        return len(self._col)
-
-    @property
-    def shape(self):
-        return (self.iid0_count, self.iid1_count)
-
-    def read(self, order="A", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
+    def read(self, order="F", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
         val = self._val
         if _is_tensor(val):
             val = val.cpu().numpy()
@@ -85,7 +131,8 @@ class KernelData(object):
             val = np.array(val, dtype=dtype, order=order)
         return KernelData(iid0=self._row, iid1=self._col, val=val, name=str(self))
 
-    def __getitem__(self, indexer):
+    def __getitem__(self, iid_indexer_and_snp_indexer):
+        indexer = iid_indexer_and_snp_indexer
         r, c = indexer if isinstance(indexer, tuple) else (indexer, indexer)
         ri, ci = _resolve_indexer(r, self.iid0_count), _resolve_indexer(c, self.iid1_count)
         val = self._val
@@ -101,12 +148,11 @@ class KernelData(object):
         return standardizer.standardize(self, return_trained=return_trained, force_python_only=force_python_only, num_threads=num_threads)
 
 
-class SnpKernel(object):
+class SnpKernel(KernelReader):
     """Lazy ``K = X X^T`` of a standardized :class:`SnpReader` (kernelreader/snpkernel.py)."""
 
-    def __init__(self, snpreader, standardizer=None, test=None, block_size=None):
+    def __init__(self, snpreader, standardizer=None, block_size=None):
         assert standardizer is not None, "'standardizer' must be provided"
-        assert test is None, "test= (train x test kernels) is not on the GPU path yet"
         self.snpreader = snpreader
         self.standardizer = standardizer
         self.block_size = block_size
@@ -124,19 +170,32 @@ class SnpKernel(object):
         return iid if self._index is None else iid[self._index]
 
     col = row
-    iid = row
-    iid0 = row
-    iid1 = row
+
+    # the SNP side of the underlying reader (snpkernel.py:134-150)
+    @property
+    def sid(self):
+        return self.snpreader.sid
 
     @property
-    def iid_count(self):
-        return len(self.row)
+    def sid_count(self):
+        return self.snpreader.sid_count
 
     @property
-    def shape(self):
-        return (self.iid_count, self.iid_count)
+    def pos(self):
+        return self.snpreader.pos
 
-    def __getitem__(self, indexer):
+    def copyinputs(self, copier):
+        copier.input(self.snpreader)
+        copier.input(self.standardizer)
+
+    def read_snps(self, order="F", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
+        """The standardized SNP values behind the kernel as a SnpData (snpkernel.py:152-187): one fused GPU pass."""
+        data = self.snpreader.read(order=order, dtype=dtype, force_python_only=force_python_only, view_ok=view_ok,
+                                   num_threads=num_threads, standardizer=self.standardizer)
+        return data if self._index is None else data[self._index, :].read(order=order, dtype=dtype, view_ok=True)
+
+    def __getitem__(self, iid_indexer_and_snp_indexer):
+        indexer = iid_indexer_and_snp_indexer
         r, c = indexer if isinstance(indexer, tuple) else (indexer, indexer)
         ri, ci = _resolve_indexer(r, self.iid_count), _resolve_indexer(c, self.iid_count)
         same = (ri is None and ci is None) or (ri is not None and ci is not None and np.array_equal(ri, ci))
@@ -159,7 +218,7 @@ class SnpKernel(object):
             val = np.array(val[self._index][:, self._index], order="F" if order == "F" else "C")
         return (val, trained) if return_trained else val
 
-    def read(self, order="A", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
+    def read(self, order="F", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
         val = self._read(order, np.dtype(dtype), force_python_only, view_ok, num_threads)
         return KernelData(iid=self.row, val=val, name=str(self))
 

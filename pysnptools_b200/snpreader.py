@@ -51,6 +51,13 @@ def _compose(outer, inner):
     return outer[inner]
 
 
+def _symmetric_to_host(K, order):
+    """Device kernel -> NumPy in the requested order.  K is exactly symmetric (the upper triangle is a copy of the lower
+    one), so its transpose view IS the F-ordered matrix: no 8*N^2-byte re-layout on the host (snpdata.py:207-209)."""
+    host = K.cpu().numpy()
+    return host.T if order == "F" else host
+
+
 def _order_code(order):
     if order in ("F", "A"):
         return _lib.ORDER_F
@@ -95,13 +102,30 @@ class SnpReader(object):
     def shape(self):
         return (self.iid_count, self.sid_count)
 
+    @property
+    def row_property(self):
+        """SnpReaders carry no per-iid properties: an empty [iid_count, 0] array (snpreader.py:393-397)."""
+        return np.empty((self.iid_count, 0))
+
+    @property
+    def val_shape(self):
+        return None
+
     def iid_to_index(self, list):
+        """Indices of the given iids; KeyError for an unknown one (pstreader.py:339-352)."""
         lookup = {tuple(x): i for i, x in enumerate(self.iid)}
         return np.array([lookup[tuple(x)] for x in list], dtype=np.int64)
 
     def sid_to_index(self, list):
         lookup = {x: i for i, x in enumerate(self.sid)}
         return np.array([lookup[x] for x in list], dtype=np.int64)
+
+    row_to_index = iid_to_index
+    col_to_index = sid_to_index
+
+    def copyinputs(self, copier):
+        """Cluster runners' file-staging hook (snpreader.py:563-565): readers with files override it."""
+        pass
 
     # --- subsetting ---
     def __getitem__(self, iid_indexer_and_snp_indexer):
@@ -175,7 +199,7 @@ class SnpReader(object):
         K32, d_stats = device.snp_kernel(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats,
                                          chunk=_kernel_chunk(block_size, self.iid_count, self.sid_count))
         out = device.convert_kernel(K32, dtype)
-        val = out if to_device else np.asarray(out.cpu().numpy(), order="F" if order == "F" else "C")
+        val = out if to_device else _symmetric_to_host(out, order)
         if return_trained:
             st = d_stats.cpu().numpy().astype(dtype if dtype in (np.float32, np.float64) else np.float64)
             return val, standardizer._make_trained(sid_labels, st)
@@ -410,11 +434,22 @@ class Bed(SnpReader):
                                                val.ctypes.data, _DT_CODE[dtype], _order_code(order)))
         return val if spec is None else (val, stats)
 
+    def copyinputs(self, copier):
+        """bed.py:196-201: the three files this reader needs."""
+        copier.input(self.filename)
+        copier.input(self.fam_filename)
+        copier.input(self.bim_filename)
+
     # --- write (bed.py:229-316 -> to_bed) ---
     @staticmethod
-    def write(filename, snpdata, count_A1=False, force_python_only=False, _require_float32_64=True, num_threads=None):
-        """Pack ``snpdata.val`` ({0,1,2,NaN} or int8 with -127) on the GPU and write ``.bed/.fam/.bim``; returns a Bed."""
+    def write(filename, snpdata, count_A1=False, force_python_only=False, _require_float32_64=True, num_threads=None,
+              reverse_chrom_map={}):
+        """Pack ``snpdata.val`` ({0,1,2,NaN} or int8 with -127) on the GPU and write ``.bed/.fam/.bim``; returns a Bed.
+        ``reverse_chrom_map`` (e.g. ``{23: 'X'}``) maps chromosome numbers back to names in the ``.bim`` (bed.py:293-298)."""
         _no_python_path(force_python_only)
+        if isinstance(filename, SnpReader) and isinstance(snpdata, str):        # historical argument order (bed.py:275-282)
+            warnings.warn("write statement should have filename before data to write", DeprecationWarning)
+            filename, snpdata = snpdata, filename
         import torch
         from . import device
         filename = str(filename)
@@ -439,7 +474,8 @@ class Bed(SnpReader):
         with open(filename[:-4] + ".bim", "w") as f:
             for k, sid in enumerate(snpdata.sid):
                 c, cm, bp = (0 if np.isnan(x) else x for x in pos[k])
-                f.write("{0}\t{1}\t{2}\t{3}\tA\tC\n".format(int(c), sid, cm, int(bp)))
+                c = reverse_chrom_map.get(c, int(c) if float(c).is_integer() else c)
+                f.write("{0}\t{1}\t{2}\t{3}\tA\tC\n".format(c, sid, cm, int(bp)))
         return Bed(filename, count_A1=count_A1)
 
 
@@ -517,6 +553,20 @@ class SnpData(SnpReader):
     def _root_and_indices(self):
         raise NotImplementedError("SnpData has no packed store")
 
+    def allclose(self, value, equal_nan=True):
+        """Same labels and close values (snpdata.py:108-124 -> pstdata.py allclose)."""
+        def arr(v):
+            return v.cpu().numpy() if _is_tensor(v) else np.asarray(v)
+        return (np.array_equal(self.iid, value.iid) and np.array_equal(self.sid, value.sid)
+                and np.allclose(self.pos, value.pos, equal_nan=True)
+                and self.val.shape == value.val.shape and bool(np.allclose(arr(self.val), arr(value.val), equal_nan=equal_nan)))
+
+    def train_standardizer(self, apply_in_place, standardizer=Unit(), force_python_only=False, num_threads=None):
+        """Deprecated spelling (snpdata.py:126-135): ``standardize(..., return_trained=True)``."""
+        warnings.warn("train_standardizer is deprecated. standardize(...,return_trained=True,...) instead", DeprecationWarning)
+        assert apply_in_place, "code assumes apply_in_place"
+        return self.standardize(standardizer, return_trained=True, force_python_only=force_python_only, num_threads=num_threads)[1]
+
     def standardize(self, standardizer=Unit(), block_size=None, return_trained=False, force_python_only=False, num_threads=None):
         """In-place standardize; returns self (and the trained standardizer) -- snpdata.py:138-188."""
         self._std_string_list.append(str(standardizer))
@@ -538,5 +588,5 @@ class SnpData(SnpReader):
         v = data.val if _is_tensor(data.val) else torch.from_numpy(np.ascontiguousarray(data.val)).cuda()
         K32 = device.float_kernel(v)
         out = device.convert_kernel(K32, dtype)
-        val = out if to_device else np.asarray(out.cpu().numpy(), order="F" if order == "F" else "C")
+        val = out if to_device else _symmetric_to_host(out, order)
         return (val, trained) if return_trained else val

@@ -1,0 +1,155 @@
+"""GPU: the UNMODIFIED reference package running on this library through the ``bed_reader`` shim.
+
+``baseline/_ref`` holds a plain ``pip install --no-deps --target baseline/_ref /root/reference`` of the reference's
+pure-Python layer (git-ignored, made in the build container -- DESIGN.md section 5; it travels to the GPU box with the
+snapshot).  Its native half, the Rust wheel ``bed-reader``, is absent; ``pysnptools_b200/compat/bed_reader`` stands in
+for it, so every decode / standardize / gather below is the reference's own Python code (``snpreader/bed.py``,
+``standardizer/standardizer.py``, ``snpreader/snpreader.py:623-668``, ``util/__init__.py:271-393``) calling
+``libpst_b200.so``.  Results are compared with the goldens the reference itself produced (tests/golden/make_golden.py).
+
+Only two NumPy-2 compatibility aliases are applied to the reference (it predates NumPy 2): ``np.NAN`` and
+``PstReader._process_ndarray`` (``dtype=np.integer``), exactly as in tests/golden/make_golden.py.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import DATA_DIR, ROOT, i8_to_float
+
+pytestmark = pytest.mark.gpu
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.isdir(os.path.join(REF_DIR, "pysnptools")):
+        pytest.skip("baseline/_ref (pip --target install of the reference's Python layer) is not present")
+    warnings.simplefilter("ignore")
+    np.NAN = np.NaN = np.nan
+    added = [os.path.join(ROOT, "pysnptools_b200", "compat"), REF_DIR]
+    for p in added:
+        sys.path.insert(0, p)
+    import types
+    import bed_reader
+    assert "pysnptools_b200" in bed_reader.__file__, "the CUDA shim must be the bed_reader the reference imports"
+    import pysnptools.pstreader.pstreader as pr
+
+    def _process_ndarray(indexer):
+        if len(indexer) == 0:
+            return np.zeros((0), dtype=np.int64)
+        if indexer.dtype == bool:
+            return np.arange(len(indexer), dtype=np.int64)[indexer]
+        return indexer
+    pr.PstReader._process_ndarray = staticmethod(_process_ndarray)
+    ns = types.SimpleNamespace()
+    from pysnptools.snpreader import Bed, SnpData
+    from pysnptools.standardizer import Unit, Beta, DiagKtoN
+    from pysnptools.kernelreader import SnpKernel
+    import pysnptools.util as pstutil
+    ns.Bed, ns.SnpData, ns.Unit, ns.Beta, ns.DiagKtoN, ns.SnpKernel, ns.util = Bed, SnpData, Unit, Beta, DiagKtoN, SnpKernel, pstutil
+    assert "baseline" in sys.modules["pysnptools"].__file__
+    yield ns
+    for p in added:
+        sys.path.remove(p)
+
+
+def rel_fro(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", ["n300", "dbx", "snpgen", "gen1", "gen4"])
+def test_reference_bed_read(ref, golden, name):
+    """Bed._read (bed.py:318-345) -> open_bed.read on the GPU: bit-exact values, dtype and order flags (test.py:960-992)."""
+    want = golden[name + "_decode_i8"]
+    bed = ref.Bed(os.path.join(DATA_DIR, name + ".bed"), count_A1=False)
+    for order in ("F", "C"):
+        for dtype in (np.float64, np.float32):
+            d = bed.read(order=order, dtype=dtype)
+            assert d.val.dtype == dtype and d.val.flags["C_CONTIGUOUS" if order == "C" else "F_CONTIGUOUS"]
+            assert np.array_equal(d.val, i8_to_float(want, dtype), equal_nan=True)
+    a1 = ref.Bed(os.path.join(DATA_DIR, name + ".bed"), count_A1=True).read().val
+    if name + "_decode_A1_i8" in golden.files:
+        assert np.array_equal(a1, i8_to_float(golden[name + "_decode_A1_i8"]), equal_nan=True)
+    obs = want != -127
+    assert np.array_equal(a1[obs], 2.0 - want[obs]) and np.isnan(a1[~obs]).all()              # test.py:226-232
+
+
+def test_reference_subset_and_labels(ref, golden):
+    bed = ref.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    assert bed.iid_count == 300 and bed.sid_count == 1015 and bed.pos.shape == (1015, 3)
+    sub = bed[::-2, [5, 3, 3, -1]][1:40:3, :].read(order="C", dtype=np.float32)
+    assert np.array_equal(sub.val, golden["n300_subset_rev_f32"], equal_nan=True)
+    assert list(sub.sid) == list(bed.sid[[5, 3, 3, 1014]])
+    full = i8_to_float(golden["n300_decode_i8"])
+    mask = np.arange(300) % 7 == 0
+    assert np.array_equal(bed[mask, 2:5].read().val, full[mask][:, 2:5])
+    # in-memory subsetting goes through util.sub_matrix -> subset_f64_f64 (pstreader.py:695-710, util/__init__.py:341-375)
+    data = bed.read()
+    rows, cols = [7, 1, 1, 299], [1014, 0, 3]
+    assert np.array_equal(data[rows, cols].read().val, full[rows][:, cols])
+    out = ref.util.sub_matrix(data.val.astype(np.float32), rows, cols, order="C", dtype=np.float64)
+    assert out.dtype == np.float64 and np.array_equal(out, full[rows][:, cols])
+
+
+@pytest.mark.parametrize("name", ["n300", "dbx", "snpgen"])
+def test_reference_standardize(ref, golden, name):
+    """Standardizer._standardize_unit_and_beta (standardizer.py:89-133) -> standardize_f64/f32 on the GPU."""
+    bed = ref.Bed(os.path.join(DATA_DIR, name + ".bed"), count_A1=False)
+    for key, std in (("unit", ref.Unit()), ("beta_1_25", ref.Beta(1, 25)), ("beta_2_10", ref.Beta(2, 10))):
+        want, wstats = golden["{0}_{1}_val".format(name, key)], golden["{0}_{1}_stats".format(name, key)]
+        for order in ("F", "C"):
+            d = bed.read(order=order, dtype=np.float64)
+            d, trained = d.standardize(std, return_trained=True)
+            got = d.val[:, : want.shape[1]]
+            assert np.max(np.abs(got - want)) <= 1e-6 * max(1.0, np.max(np.abs(want)))
+            fin = np.isfinite(wstats)
+            assert np.allclose(trained.stats[fin], wstats[fin], rtol=1e-9)
+        d32 = bed.read(dtype=np.float32).standardize(std)
+        assert d32.val.dtype == np.float32 and np.max(np.abs(d32.val[:, : want.shape[1]] - want)) <= 2e-6 * max(1.0, np.max(np.abs(want)))
+
+
+def test_reference_trained_on_other_iids(ref, golden):
+    """UnitTrained / BetaTrained (unittrained.py:47-70, betatrained.py:47-63): use_stats=True through the shim."""
+    bed = ref.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    for std, key in ((ref.Unit(), "unit"), (ref.Beta(1, 25), "beta")):
+        _, trained = bed[10:, :].read().standardize(std, return_trained=True)
+        assert np.allclose(trained.stats, golden["n300_trained_{0}_stats".format(key)], rtol=1e-9)
+        test = bed[:10, :].read().standardize(trained)
+        want = golden["n300_trained_{0}_test_val".format(key)]
+        assert np.max(np.abs(test.val - want)) <= 1e-6 * max(1.0, np.max(np.abs(want)))
+
+
+def test_reference_read_kernel(ref, golden):
+    """SnpReader._read_kernel block loop (snpreader.py:623-668) and SnpKernel.read on the GPU-backed reader."""
+    bed = ref.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    K = bed.read_kernel(ref.Unit(), block_size=100).val
+    assert rel_fro(K, golden["n300_unit_K"]) < 1e-9
+    Kb = ref.SnpKernel(bed, ref.Beta(1, 25), block_size=333).read().val
+    assert rel_fro(Kb, golden["n300_beta_1_25_K"]) < 1e-9
+    toy = ref.Bed(os.path.join(DATA_DIR, "toydata.bed"), count_A1=False)
+    Kt = ref.SnpKernel(toy, ref.Unit(), block_size=2500).read().val
+    assert rel_fro(Kt, golden["toydata_unit_K_shipped"]) < 1e-9
+    kd = ref.SnpKernel(toy, ref.Unit()).read().standardize(ref.DiagKtoN())
+    assert abs(kd.val[0, 0] - float(golden["toydata_unit_K_diagKtoN_00"])) < 1e-6 and abs(np.trace(kd.val) - 500) < 1e-6
+
+
+def test_reference_write_roundtrip_and_pickle(ref, golden, tmp_path):
+    """Bed.write -> to_bed (bed.py:229-316) then read back; the open handle survives pickling (test.py:993-1003)."""
+    import pickle
+    bed = ref.Bed(os.path.join(DATA_DIR, "dbx.bed"), count_A1=False)
+    data = bed.read()
+    out = str(tmp_path / "copy.bed")
+    ref.Bed.write(out, data, count_A1=False)
+    back = ref.Bed(out, count_A1=False)
+    assert np.array_equal(back.read().val, data.val, equal_nan=True)
+    assert list(back.sid) == list(data.sid) and np.array_equal(back.iid, data.iid)
+    with open(out, "rb") as f1, open(os.path.join(DATA_DIR, "dbx.bed"), "rb") as f0:
+        assert f1.read() == f0.read()
+    again = pickle.loads(pickle.dumps(back))
+    assert np.array_equal(again[::3, 1:7].read().val, data.val[::3, 1:7], equal_nan=True)
+    bad = ref.SnpData(iid=data.iid, sid=data.sid, val=np.full(data.val.shape, 7.0))
+    with pytest.raises(Exception):
+        ref.Bed.write(str(tmp_path / "bad.bed"), bad, count_A1=False)

@@ -223,3 +223,37 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "genotypes/s decoded+standardized" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_pstreader_accessor_surface():
+    """Accessors the reference's PstReader / KernelReader expose on every reader (pstreader.py:300-400, kernelreader.py:60-243)."""
+    import inspect
+    from pysnptools_b200 import Bed, KernelData, SnpData, SnpKernel, Unit
+    bed = Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    assert bed.row_count == 300 and bed.col_count == 1015 and bed.row_property.shape == (300, 0) and bed.val_shape is None
+    assert np.array_equal(bed.row_to_index([bed.iid[7], bed.iid[2]]), [7, 2]) and np.array_equal(bed.col_to_index(bed.sid[[9, 0]]), [9, 0])
+    with pytest.raises(KeyError):
+        bed.sid_to_index(["no such snp"])
+
+    class Copier(object):
+        def __init__(self):
+            self.seen = []
+
+        def input(self, x):
+            self.seen.append(x) if isinstance(x, str) else (x.copyinputs(self) if hasattr(x, "copyinputs") else None)
+    c = Copier()
+    kernel = SnpKernel(bed, Unit(), 500)                                     # positional block_size, as in the reference
+    assert kernel.block_size == 500 and list(inspect.signature(SnpKernel.__init__).parameters) == ["self", "snpreader", "standardizer", "block_size"]
+    kernel.copyinputs(c)
+    assert c.seen == [bed.filename, bed.fam_filename, bed.bim_filename]
+    assert kernel.sid_count == 1015 and kernel.pos.shape == (1015, 3) and kernel.iid0_count == kernel.iid1_count == kernel.row_count == 300
+    assert np.array_equal(kernel.iid1_to_index([bed.iid[5]]), [5]) and kernel[::2].iid_count == 150
+    assert repr(kernel) == "SnpKernel(Bed('{0}',count_A1=False),standardizer=Unit(),block_size=500)".format(bed.filename)
+    a = SnpData(iid=[["f", "a"], ["f", "b"]], sid=["s1", "s2"], val=np.array([[0.0, 1.0], [2.0, np.nan]]))
+    b = SnpData(iid=[["f", "a"], ["f", "b"]], sid=["s1", "s2"], val=np.array([[0.0, 1.0], [2.0, np.nan]]))
+    assert a.allclose(b) and not a.allclose(b, equal_nan=False)                # snpdata.py:115-121
+    kd = KernelData(iid0=[["f", "a"], ["f", "b"]], iid1=[["f", "c"]], val=np.array([[1.0], [2.0]]))
+    assert kd.shape == (2, 1) and kd.col_count == 1 and np.array_equal(kd.iid0_to_index([["f", "b"]]), [1]) and kd.allclose(kd)
+    assert kd.read().val.flags["F_CONTIGUOUS"] and kd[[1, 0], :].val[0, 0] == 2.0
+    with pytest.raises(AssertionError):
+        kd.iid

@@ -124,6 +124,20 @@ int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count
                           int mode, double a, double b, int use_stats, double* d_stats,
                           float* d_tiles, int rank, int world, int accumulate,
                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* Train x test kernel (what FaST-LMM builds from SnpKernel + the *Trained standardizers: unittrained.py:47-70,
+ * betatrained.py:47-63 applied to a second iid set, then train.val.dot(test.val.T)):
+ *   d_out [n_r, n_c] float32, C order (ld = n_c):  out[i, k] (+)= sum_j x_ij y_kj
+ * x = the `_r` (row / train) selection, y = the `_c` (column / test) selection, possibly of two different stores; both sides
+ * select the same number of SNPs (position j of sid_r pairs with position j of sid_c).  Both are standardized with ONE set of
+ * per-SNP statistics: use_stats == 0 computes them from the ROW side and writes d_stats [n_sid][2]; use_stats != 0 reads them.
+ * Missing genotypes contribute 0 (mean imputation).  Same fp16 hi/lo tensor-core path as pstb_snp_kernel (3 MMA terms). */
+int64_t pstb_cross_kernel_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t chunk);
+int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, int64_t iid_count_r, int64_t sid_count_r,
+                          pstb_axis iid_r, pstb_axis sid_r, int count_a1_r,
+                          const uint8_t* d_packed_c, int64_t ld_c, int64_t iid_count_c, int64_t sid_count_c,
+                          pstb_axis iid_c, pstb_axis sid_c, int count_a1_c,
+                          int mode, double a, double b, int use_stats, double* d_stats,
+                          float* d_out, int accumulate, void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
 /* K = V V^T for a float matrix V [n_iid, n_sid] already in HBM (float32 / float64, C or F order): replaces the
  * val.dot(val.T) of SnpData._read_kernel (snpdata.py:203-206).  Same fp16 hi/lo tensor-core path and workspace. */
 int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,

@@ -165,6 +165,23 @@ def read_kernel(packed, iid_count, is_beta=False, a=np.nan, b=np.nan, count_A1=F
     return K, (np.concatenate(stats) if stats else np.zeros((0, 2)))
 
 
+def read_cross_kernel(packed_r, iid_count_r, packed_c, iid_count_c, is_beta=False, a=np.nan, b=np.nan, count_A1_r=False,
+                      count_A1_c=False, iid_index_r=None, iid_index_c=None, sid_index_r=None, sid_index_c=None, stats=None):
+    """Train x test kernel in float64: standardize the row (train) side (``standardizer.py:135-211``; or apply ``stats``),
+    apply ITS statistics to the column (test) side (``unittrained.py:47-70`` / ``betatrained.py:47-63``: use_stats=True),
+    then ``train.val.dot(test.val.T)`` (the product of ``snpdata.py:203-206`` with two operands)."""
+    xr = decode(packed_r, iid_count_r, _resolve_index(iid_index_r, iid_count_r), _resolve_index(sid_index_r, packed_r.shape[0]),
+                count_A1_r, np.float64, "F")
+    xc = decode(packed_c, iid_count_c, _resolve_index(iid_index_c, iid_count_c), _resolve_index(sid_index_c, packed_c.shape[0]),
+                count_A1_c, np.float64, "F")
+    if stats is None:
+        xr, st = standardize(xr, is_beta, a, b)
+    else:
+        xr, st = standardize(xr, is_beta, a, b, use_stats=True, stats=stats)
+    xc, _ = standardize(xc, is_beta, a, b, use_stats=True, stats=st)
+    return xr.dot(xc.T), st
+
+
 def sub_matrix(val, row_index, col_index, dtype=None, order="C"):
     """``out[i,j,...] = val[row[i], col[j], ...]`` (util/__init__.py:271-393)."""
     out = np.asarray(val)[np.asarray(row_index, dtype=np.int64)][:, np.asarray(col_index, dtype=np.int64)]

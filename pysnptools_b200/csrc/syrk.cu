@@ -292,6 +292,10 @@ struct SyrkParams {
     float out_scale;
     int run_kb_fast;        // k-blocks per TMEM run on the 2-term path
     int compact;            // K is tile storage [ntiles][256][256] (K-tile sharding: this rank's tiles only), 2-CTA kernel only
+    // rectangular (train x test) product on stacked planes, 2-CTA kernel only: plane rows [0, row0) hold the column operand,
+    // rows [row0, row0 + n) the row operand; tiles are (I, J) with 256 I >= row0 > 256 J; output row = plane row - row0,
+    // n_cols columns.  Symmetric product: row0 = 0, n_cols = n.
+    long long row0, n_cols;
 };
 
 __global__ void __launch_bounds__(SYRK_THREADS, 1)
@@ -638,9 +642,9 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(smem_u32(&bar_tempty[acc]), 0u);
             }
-            const long long row = (long long)tile.x * TM + rank * 128 + quad * 32 + lane;
+            const long long row = (long long)tile.x * TM + rank * 128 + quad * 32 + lane - p.row0;
             const long long col0 = (long long)tile.y * TN + half * 128;
-            const long long row_hi = (long long)tile.x * TM + rank * 128 + quad * 32 + 31;
+            const long long row_hi = (long long)tile.x * TM + rank * 128 + quad * 32 + 31;       // plane row: never above a stacked column
             // compact: tile t of this rank's list is stored whole (256 x 256, ld 256), diagonal tiles included in full
             float* kbase = p.compact ? p.K + (long long)t * (TM * TN) + (long long)(rank * 128 + quad * 32 + lane) * TN + half * 128
                                      : p.K + row * p.ldk + col0;
@@ -648,10 +652,10 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const long long cc = col0 + c * 32;
-                if ((!p.compact && cc > row_hi) || cc >= p.n) continue;
+                if ((!p.compact && cc > row_hi) || cc >= p.n_cols) continue;
                 if (row < p.n) {
                     float* dst = kbase + c * 32;
-                    if (vec_t && cc + 32 <= p.n) {
+                    if (vec_t && cc + 32 <= p.n_cols) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 o = make_float4(sum[c * 32 + 4 * q] * scale, sum[c * 32 + 4 * q + 1] * scale,
@@ -663,7 +667,7 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                     } else {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) {
-                            if (cc + q < p.n) {
+                            if (cc + q < p.n_cols) {
                                 float o = sum[c * 32 + q] * scale;
                                 if (p.accumulate) o += dst[q];
                                 dst[q] = o;
@@ -881,6 +885,8 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.num_kb = (int)(k_pad / BK);
     p.K = K;
     p.n = n;
+    p.n_cols = n;
+    p.row0 = 0;
     p.ldk = ldk;
     p.accumulate = accumulate;
     p.sc = sc;
@@ -903,6 +909,76 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     if (grid > ntiles) grid = ntiles;
     k_syrk<<<grid, SYRK_THREADS, SYRK_SMEM, st>>>(map_hi, map_lo, p);
     PSTB_AFTER_LAUNCH("k_syrk");
+    return 0;
+}
+
+// ---- rectangular product (train x test) on stacked planes ----------------------------------------------------------------
+struct CrossTileCache {
+    long long rb = -1, cb = -1;
+    int device = -1;
+    int2* d_tiles = nullptr;
+    int ntiles = 0;
+};
+
+// tiles (I, J): I over the row operand's 256-row blocks (stacked after the cb column blocks), J over the column blocks;
+// rasterised in GROUP2 x GROUP2 super-blocks like the triangular list
+int get_cross_tiles(long long row_blocks, long long col_blocks, cudaStream_t st, const int2** d_tiles, int* ntiles) {
+    static thread_local CrossTileCache c;
+    int dev = 0;
+    PSTB_CUDA(cudaGetDevice(&dev));
+    if (c.rb != row_blocks || c.cb != col_blocks || c.device != dev) {
+        std::vector<int2> tiles;
+        for (long long gi = 0; gi < row_blocks; gi += v2::GROUP2)
+            for (long long gj = 0; gj < col_blocks; gj += v2::GROUP2)
+                for (long long I = gi; I < gi + v2::GROUP2 && I < row_blocks; ++I)
+                    for (long long J = gj; J < gj + v2::GROUP2 && J < col_blocks; ++J)
+                        tiles.push_back(make_int2((int)(col_blocks + I), (int)J));
+        PSTB_CUDA(cudaStreamSynchronize(st));
+        if (c.d_tiles) cudaFree(c.d_tiles);
+        c.d_tiles = nullptr;
+        c.rb = -1;
+        PSTB_CUDA(cudaMalloc(&c.d_tiles, (tiles.size() + 1) * sizeof(int2)));
+        PSTB_CUDA(cudaMemcpy(c.d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        c.ntiles = (int)tiles.size();
+        c.rb = row_blocks;
+        c.cb = col_blocks;
+        c.device = dev;
+    }
+    *d_tiles = c.d_tiles;
+    *ntiles = c.ntiles;
+    return 0;
+}
+
+// out[n_rows, n_cols] (+)= X_rows X_cols^T: planes hold the column operand in rows [0, cols_pad) and the row operand in rows
+// [cols_pad, cols_pad + rows_pad); always the 3-term hi/lo split (sc->any_missing is set by the caller)
+int launch_cross(const __half* hi, const __half* lo, long long n_rows, long long rows_pad, long long n_cols, long long cols_pad,
+                 long long k_pad, float* out, long long ldo, int accumulate, const Scalars* sc, cudaStream_t st) {
+    const long long n_pad = rows_pad + cols_pad;
+    CUtensorMap map_hi, map_lo;
+    if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
+    const int2* d_tiles = nullptr;
+    int ntiles = 0;
+    if (get_cross_tiles(rows_pad / v2::TM, cols_pad / v2::TN, st, &d_tiles, &ntiles)) return 1;
+    SyrkParams p{};
+    p.tiles = d_tiles;
+    p.ntiles = ntiles;
+    p.num_kb = (int)(k_pad / BK);
+    p.K = out;
+    p.n = n_rows;
+    p.n_cols = n_cols;
+    p.row0 = cols_pad;
+    p.ldk = ldo;
+    p.accumulate = accumulate;
+    p.sc = sc;
+    p.out_scale = 1.0f;
+    p.compact = 0;
+    p.run_kb_fast = 6;
+    PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
+    if (ntiles < 1) return 0;
+    int clusters = sm_count_cached() / 2;
+    if (clusters > ntiles) clusters = ntiles;
+    v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_lo, p);
+    PSTB_AFTER_LAUNCH("k_syrk2");
     return 0;
 }
 
@@ -1131,5 +1207,94 @@ extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_
         if (rc) return rc;
     }
     if (mirror) return pstb_mirror_lower(d_K, n, n, stream);
+    return 0;
+}
+
+// ---- train x test kernel: out[i, k] = sum_j x_ij y_kj, both sides standardized with the statistics of the ROW (train) side ----
+extern "C" int64_t pstb_cross_kernel_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t chunk) {
+    if (n_rows < 0) n_rows = 0;
+    if (n_cols < 0) n_cols = 0;
+    return pstb_kernel_workspace_bytes(round_up(n_rows > 0 ? n_rows : 1, ROW_PAD) + round_up(n_cols > 0 ? n_cols : 1, ROW_PAD), chunk);
+}
+
+extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, int64_t iid_count_r, int64_t sid_count_r, pstb_axis iid_r,
+                                     pstb_axis sid_r, int count_a1_r, const uint8_t* d_packed_c, int64_t ld_c, int64_t iid_count_c,
+                                     int64_t sid_count_c, pstb_axis iid_c, pstb_axis sid_c, int count_a1_c, int mode, double a, double b,
+                                     int use_stats, double* d_stats, float* d_out, int accumulate, void* d_work, int64_t work_bytes,
+                                     int64_t chunk, void* stream) {
+    if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
+    if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
+    if (iid_r.n < 0 || iid_c.n < 0 || sid_r.n < 0 || sid_c.n < 0) return fail("negative selection length");
+    if (sid_r.n != sid_c.n) return fail("both sides must select the same number of SNPs (%lld vs %lld)", (long long)sid_r.n, (long long)sid_c.n);
+    if (iid_r.n == 0 || iid_c.n == 0) return 0;
+    if (!d_out) return fail("d_out is NULL");
+    if (sid_r.n > 0 && !d_stats) return fail("d_stats is NULL");
+    if (chunk < BK || chunk % BK) return fail("chunk must be a positive multiple of %d", BK);
+    if (work_bytes < pstb_cross_kernel_workspace_bytes(iid_r.n, iid_c.n, chunk) || !d_work)
+        return fail("workspace too small (pstb_cross_kernel_workspace_bytes)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long nr = iid_r.n, nc = iid_c.n, rows_pad = round_up(nr, ROW_PAD), cols_pad = round_up(nc, ROW_PAD), n_pad = rows_pad + cols_pad;
+    if (sid_r.n == 0) {
+        if (!accumulate) PSTB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nr * nc * sizeof(float), st));
+        return 0;
+    }
+    const double lnB = (mode == PSTB_STD_BETA) ? lgamma(a) + lgamma(b) - lgamma(a + b) : 0.0;
+    const long long k_cap = round_up(chunk, BK);
+    char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_work) + 1023) & ~(uintptr_t)1023);
+    __half* hi = reinterpret_cast<__half*>(w);
+    __half* lo = hi + n_pad * k_cap;
+    __half* p2 = lo + n_pad * k_cap;
+    Scalars* sc = reinterpret_cast<Scalars*>(p2 + n_pad * k_cap);
+    double* u = reinterpret_cast<double*>(sc + 1);
+    for (long long c0 = 0; c0 < sid_r.n; c0 += chunk) {
+        const long long ns = (c0 + chunk <= sid_r.n) ? chunk : sid_r.n - c0;
+        const long long k_pad = round_up(ns, BK);
+        pstb_axis sub_r = sid_r, sub_c = sid_c;
+        sub_r.n = sub_c.n = ns;
+        if (sid_r.idx) sub_r.idx = sid_r.idx + c0; else sub_r.start = sid_r.start + c0 * sid_r.step;
+        if (sid_c.idx) sub_c.idx = sid_c.idx + c0; else sub_c.start = sid_c.start + c0 * sid_c.step;
+        double* st_chunk = d_stats + 2 * c0;
+        PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+        PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));      // always the 3-term split
+        if (!use_stats) {                                                                 // statistics of the row (train) side
+            int rc = read_impl_ex(d_packed_r, ld_r, iid_count_r, sid_count_r, iid_r, sub_r, count_a1_r, mode, a, b, 0, st_chunk, nullptr,
+                                  PSTB_F32, PSTB_ORDER_F, stream, nullptr);
+            if (rc) return rc;
+        }
+        k_absmax<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(st_chunk, ns, mode, a, b, lnB, sc);
+        PSTB_AFTER_LAUNCH("k_absmax");
+        for (int side = 0; side < 2; ++side) {                                            // 0: column operand (rows 0..), 1: row operand
+            const pstb_axis& iid = side ? iid_r : iid_c;
+            PlaneParams pp{};
+            pp.packed = side ? d_packed_r : d_packed_c;
+            pp.ld = side ? ld_r : ld_c;
+            pp.iid_count = side ? iid_count_r : iid_count_c;
+            pp.sid_count = side ? sid_count_r : sid_count_c;
+            pp.iid = to_axis(iid);
+            pp.sid = to_axis(side ? sub_r : sub_c);
+            pp.count_a1 = (side ? count_a1_r : count_a1_c) ? 1 : 0;
+            pp.mode = mode;
+            pp.a = a;
+            pp.b = b;
+            pp.lnB = lnB;
+            pp.stats = st_chunk;
+            pp.sc = sc;
+            const long long off = side ? cols_pad * k_pad : 0;
+            pp.hi = hi + off;
+            pp.lo = lo + off;
+            pp.p2 = p2;
+            pp.u = u;
+            pp.csum = u;
+            pp.n_pad = side ? rows_pad : cols_pad;
+            pp.k_pad = k_pad;
+            pp.dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
+            pp.byte_off = pp.dense ? iid.start / 4 : 0;
+            const long long ptiles = (k_pad / PT_S) * (pp.n_pad / PT_I);
+            k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
+            PSTB_AFTER_LAUNCH("k_planes");
+        }
+        int rc = launch_cross(hi, lo, nr, rows_pad, nc, cols_pad, k_pad, d_out, nc, (accumulate || c0 > 0) ? 1 : 0, sc, st);
+        if (rc) return rc;
+    }
     return 0;
 }

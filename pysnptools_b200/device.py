@@ -241,6 +241,47 @@ def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=(
     return K, d_stats
 
 
+def snp_cross_kernel(store_r, store_c, iid_r=None, iid_c=None, sid_r=None, sid_c=None, count_A1_r=False, count_A1_c=False,
+                     standardizer=("unit",), stats=None, chunk=None, out=None, accumulate=False):
+    """Train x test kernel ``out[i, k] = sum_j x_ij y_kj`` (float32 CUDA tensor [n_r, n_c]) on the tensor cores.
+
+    ``store_r`` / ``store_c`` are the row (train) and column (test) packed stores (may be the same store with different iid
+    selections); both sides are standardized with the statistics of the row side (or with ``stats`` when given).
+    Returns ``(out, stats)``.
+    """
+    _lib.require_gpu()
+    dev = store_r.device
+    assert store_c.device == dev, "both stores must live on the same GPU"
+    ir = iid_r if isinstance(iid_r, Selection) else Selection(iid_r, store_r.iid_count, dev)
+    ic = iid_c if isinstance(iid_c, Selection) else Selection(iid_c, store_c.iid_count, dev)
+    sr = sid_r if isinstance(sid_r, Selection) else Selection(sid_r, store_r.sid_count, dev)
+    sc = sid_c if isinstance(sid_c, Selection) else Selection(sid_c, store_c.sid_count, dev)
+    if sr.n != sc.n:
+        raise ValueError("both sides must select the same number of SNPs ({0} vs {1})".format(sr.n, sc.n))
+    mode, a, b = _mode_args(standardizer)
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.zeros((ir.n, ic.n), dtype=torch.float32, device=dev)
+            accumulate = False
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (ir.n, ic.n)
+        use_stats = 0
+        if stats is not None:
+            d_stats = torch.as_tensor(stats, dtype=torch.float64, device=dev).contiguous()
+            assert tuple(d_stats.shape) == (sr.n, 2), "stats must be [n_sid, 2]"
+            use_stats = 1
+        else:
+            d_stats = torch.empty((sr.n, 2), dtype=torch.float64, device=dev)
+        if chunk is None:
+            chunk = default_kernel_chunk(ir.n + ic.n, sr.n)
+        wbytes = int(lib.pstb_cross_kernel_workspace_bytes(ir.n, ic.n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(lib.pstb_snp_cross_kernel(store_r.tensor.data_ptr(), store_r.ld, store_r.iid_count, store_r.sid_count, ir.axis(), sr.axis(),
+                                        int(bool(count_A1_r)), store_c.tensor.data_ptr(), store_c.ld, store_c.iid_count, store_c.sid_count,
+                                        ic.axis(), sc.axis(), int(bool(count_A1_c)), mode, a, b, use_stats, d_stats.data_ptr(),
+                                        out.data_ptr(), int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _stream()))
+    return out, d_stats
+
+
 def kernel_tile_coords(n_iid, rank=0, world=1):
     """(I, J) block coordinates of the 256 x 256 lower-triangular tiles owned by ``rank`` of ``world`` (int32 [count, 2])."""
     count = int(lib.pstb_kernel_tile_count(n_iid, rank, world))

@@ -151,17 +151,24 @@ class KernelData(KernelReader):
 class SnpKernel(KernelReader):
     """Lazy ``K = X X^T`` of a standardized :class:`SnpReader` (kernelreader/snpkernel.py)."""
 
-    def __init__(self, snpreader, standardizer=None, block_size=None):
+    def __init__(self, snpreader, standardizer=None, block_size=None, test=None):
+        """``test=`` (keyword, an extension over snpkernel.py:43-50): a second SnpReader over the same SNPs; the kernel is then
+        the train x test matrix FaST-LMM predicts with -- ``iid0`` = ``snpreader.iid``, ``iid1`` = ``test.iid``,
+        ``val = X_train X_test^T`` with BOTH sides standardized by the statistics learned on ``snpreader`` (the *Trained
+        standardizers, unittrained.py:47-70 / betatrained.py:47-63)."""
         assert standardizer is not None, "'standardizer' must be provided"
         self.snpreader = snpreader
         self.standardizer = standardizer
         self.block_size = block_size
+        self.test = test
         self._index = None          # subset of the kernel's iids applied AFTER the kernel is computed
 
     def __repr__(self):
         s = "SnpKernel({0},standardizer={1}".format(self.snpreader, self.standardizer)
         if self.block_size is not None:
             s += ",block_size={0}".format(self.block_size)
+        if self.test is not None:
+            s += ",test={0}".format(self.test)
         return s + ")"
 
     @property
@@ -169,7 +176,9 @@ class SnpKernel(KernelReader):
         iid = self.snpreader.iid
         return iid if self._index is None else iid[self._index]
 
-    col = row
+    @property
+    def col(self):
+        return self.row if self.test is None else self.test.iid
 
     # the SNP side of the underlying reader (snpkernel.py:134-150)
     @property
@@ -197,6 +206,13 @@ class SnpKernel(KernelReader):
     def __getitem__(self, iid_indexer_and_snp_indexer):
         indexer = iid_indexer_and_snp_indexer
         r, c = indexer if isinstance(indexer, tuple) else (indexer, indexer)
+        if self.test is not None:
+            # rectangular: the column subset is a plain subset of the test reader; a row subset changes the training set only
+            # for a non-constant standardizer, so it is applied after the read
+            ri, ci = _resolve_indexer(r, self.iid0_count), _resolve_indexer(c, self.iid1_count)
+            out = SnpKernel(self.snpreader, self.standardizer, block_size=self.block_size, test=self.test if ci is None else self.test[ci, :])
+            out._index = _compose(self._index, ri) if ri is not None else self._index
+            return out
         ri, ci = _resolve_indexer(r, self.iid_count), _resolve_indexer(c, self.iid_count)
         same = (ri is None and ci is None) or (ri is not None and ci is not None and np.array_equal(ri, ci))
         assert same, "SnpKernel supports the same indexer on both axes"
@@ -209,7 +225,37 @@ class SnpKernel(KernelReader):
         out._index = _compose(self._index, ri)
         return out
 
+    def _read_cross(self, order, dtype, force_python_only, return_trained):
+        """Train x test on the GPU: pstb_snp_cross_kernel over the two packed stores."""
+        from . import device
+        from .standardizer import Standardizer, _no_python_path
+        from .snpreader import _kernel_chunk
+        _no_python_path(force_python_only)
+        std = self.standardizer
+        if not isinstance(std, Standardizer) or std._device_spec() is None:
+            raise NotImplementedError("train x test kernels on the GPU support Unit, Beta and their trained forms")
+        train, test = self.snpreader, self.test
+        if not np.array_equal(train.sid, test.sid):
+            test = test[:, test.sid_to_index(train.sid)]                        # pair the SNPs by name (a KeyError names a missing one)
+        root_r, ii_r, si_r = train._root_and_indices()
+        root_c, ii_c, si_c = test._root_and_indices()
+        store_r, sel_r = root_r._store_for(si_r)
+        store_c, sel_c = root_c._store_for(si_c)
+        stats = std._trained_stats_for(train.sid)
+        out, d_stats = device.snp_cross_kernel(store_r, store_c, ii_r, ii_c, sel_r, sel_c, count_A1_r=root_r.count_A1,
+                                               count_A1_c=root_c.count_A1, standardizer=std._device_spec(), stats=stats,
+                                               chunk=_kernel_chunk(self.block_size, train.iid_count + test.iid_count, train.sid_count))
+        val = out.cpu().numpy().astype(dtype, copy=False)
+        if self._index is not None:
+            val = val[self._index]
+        val = np.asarray(val, order="F" if order == "F" else "C")
+        if return_trained:
+            return val, std._make_trained(train.sid, d_stats.cpu().numpy().astype(dtype if dtype in (np.float32, np.float64) else np.float64))
+        return val
+
     def _read(self, order, dtype, force_python_only, view_ok, num_threads, return_trained=False):
+        if self.test is not None:
+            return self._read_cross(order, np.dtype(dtype), force_python_only, return_trained)
         res = self.snpreader._read_kernel(self.standardizer, self.block_size, order, dtype, force_python_only, view_ok,
                                           return_trained=return_trained, num_threads=num_threads)
         val, trained = res if return_trained else (res, None)
@@ -220,12 +266,19 @@ class SnpKernel(KernelReader):
 
     def read(self, order="F", dtype=np.float64, force_python_only=False, view_ok=False, num_threads=None):
         val = self._read(order, np.dtype(dtype), force_python_only, view_ok, num_threads)
+        if self.test is not None:
+            return KernelData(iid0=self.row, iid1=self.col, val=val, name=str(self))
         return KernelData(iid=self.row, val=val, name=str(self))
 
     def _read_with_standardizing(self, to_kerneldata, kernel_standardizer=DiagKtoN(), return_trained=False, num_threads=None):
         """FaST-LMM's entry (snpkernel.py:104-132): kernel + trained SNP standardizer + trained kernel standardizer."""
         assert to_kerneldata, "only the KernelData form is on the GPU path"
         val, snp_trained = self._read("A", np.dtype(np.float64), False, False, num_threads, return_trained=True)
-        kernel = KernelData(iid=self.row, val=val, name=str(self))
+        if self.test is not None:
+            # a train x test kernel has no diagonal to learn from: it takes the factor learned on the train kernel
+            assert kernel_standardizer.is_constant, "a train x test kernel needs a trained kernel standardizer (DiagKtoNTrained) or Identity"
+            kernel = KernelData(iid0=self.row, iid1=self.col, val=val, name=str(self))
+        else:
+            kernel = KernelData(iid=self.row, val=val, name=str(self))
         kernel, kernel_trained = kernel.standardize(kernel_standardizer, return_trained=True, num_threads=num_threads)
         return (kernel, snp_trained, kernel_trained) if return_trained else kernel

@@ -152,6 +152,34 @@ def test_snp_kernel(golden):
     assert rel_fro(ktr2.val, want @ want.T) < 1e-5 and ktr.val.shape == (10, 10)
 
 
+def test_train_test_kernel(golden, oracle):
+    """SnpKernel(train, standardizer, test=test): X_train X_test^T with the statistics learned on the train iids -- the product
+    FaST-LMM predicts with; values pinned by the reference's trained-standardizer goldens (unittrained.py / betatrained.py)."""
+    from pysnptools_b200 import Beta, SnpKernel, Unit
+    bed = _bed("n300")
+    packed, n, m = fixture_packed("n300")
+    for std, key, args in ((Unit(), "unit", {}), (Beta(1, 25), "beta", dict(is_beta=True, a=1, b=25))):
+        train, test = bed[10:, :], bed[:10, :]
+        xr, st = oracle.standardize(oracle.decode(packed, n, np.arange(10, n)), **args)
+        want = xr @ golden["n300_trained_{0}_test_val".format(key)].T                # test values standardized BY THE REFERENCE
+        k = SnpKernel(train, std, test=test)
+        assert k.iid0_count == n - 10 and k.iid1_count == 10 and k.shape == (n - 10, 10)
+        kd = k.read()
+        assert kd.val.shape == (n - 10, 10) and kd.val.dtype == np.float64 and kd.val.flags["F_CONTIGUOUS"]
+        assert np.array_equal(kd.iid0, train.iid) and np.array_equal(kd.iid1, test.iid)
+        assert rel_fro(kd.val, want) < 1e-5, rel_fro(kd.val, want)
+        # a trained standardizer gives the same matrix; float32 / C order / block_size / column subset respected
+        _, trained = train.read().standardize(std, return_trained=True)
+        k32 = SnpKernel(train, trained, block_size=200, test=test).read(order="C", dtype=np.float32)
+        assert k32.val.dtype == np.float32 and k32.val.flags["C_CONTIGUOUS"] and rel_fro(k32.val.astype(np.float64), want) < 1e-5
+        sub = k[::3, [7, 2]].read()
+        assert sub.val.shape == (len(range(0, n - 10, 3)), 2) and rel_fro(sub.val, want[::3][:, [7, 2]]) < 1e-5
+        # SNPs are paired by name: a test reader with its SNPs in another order gives the same kernel
+        perm = np.random.default_rng(0).permutation(m)
+        assert rel_fro(SnpKernel(train, std, test=test[:, perm]).read().val, want) < 1e-5
+    assert "test=" in repr(SnpKernel(bed[10:, :], Unit(), test=bed[:10, :]))
+
+
 def test_bed_write_round_trips(tmp_path, oracle):
     """test_write_bed_f64cpp_* / test_write_x_x_cpp (test.py:671-765): 0/1/2/5 iids, NaN, both count_A1, illegal values."""
     from pysnptools_b200 import Bed, SnpData

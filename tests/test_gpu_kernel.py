@@ -128,3 +128,47 @@ def test_kernel_tile_sharding(n, m, world, oracle, dev):
     assert len(seen) == T * (T + 1) // 2 and not np.isnan(K).any()
     assert np.linalg.norm(K - ref) / np.linalg.norm(ref) < K_TOL
     assert np.allclose(K, K.T, rtol=0, atol=1e-3 * np.abs(ref).max())      # diagonal tiles are stored whole (both triangles)
+
+
+@pytest.mark.parametrize("n_r,n_c,m,chunk", [(300, 100, 200, 64), (1500, 700, 1000, 512), (257, 1030, 333, None), (5, 2100, 64, None)])
+def test_cross_kernel_vs_oracle(n_r, n_c, m, chunk, oracle, dev):
+    """Train x test kernel (pstb_snp_cross_kernel): both sides standardized with the train statistics, missing -> 0."""
+    rng = np.random.default_rng(n_r + n_c)
+    pr = oracle.synth_packed(n_r, 0, m, missing_rate=0.04, seed=n_r)
+    pc = oracle.synth_packed(n_c, 0, m, missing_rate=0.04, seed=n_c + 1)
+    sr, sc = dev.PackedStore.from_host(pr, n_r), dev.PackedStore.from_host(pc, n_c)
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        ref, rst = oracle.read_cross_kernel(pr, n_r, pc, n_c, **args)
+        out, st = dev.snp_cross_kernel(sr, sc, standardizer=std, chunk=chunk)
+        assert tuple(out.shape) == (n_r, n_c)
+        assert rel_fro(out.double().cpu().numpy(), ref) < K_TOL, rel_fro(out.double().cpu().numpy(), ref)
+        np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12)
+        out2, _ = dev.snp_cross_kernel(sr, sc, standardizer=std, stats=st, chunk=chunk)       # given (trained) statistics
+        assert rel_fro(out2.double().cpu().numpy(), ref) < K_TOL
+    # gathered iids on both sides, differently ordered SNP selections pairing the same SNPs, count_A1 on the test side only
+    ii_r, ii_c = rng.permutation(n_r)[: max(1, n_r // 2)], rng.permutation(n_c)[: max(1, n_c // 3)]
+    si = rng.permutation(m)[: m // 2]
+    ref, _ = oracle.read_cross_kernel(pr, n_r, pc, n_c, iid_index_r=ii_r, iid_index_c=ii_c, sid_index_r=si, sid_index_c=si)
+    out, st = dev.snp_cross_kernel(sr, sc, ii_r, ii_c, si, si, chunk=chunk)
+    assert rel_fro(out.double().cpu().numpy(), ref) < K_TOL
+    # SNP-sharded accumulation (what the multi-GPU path sums) == one pass
+    half = len(si) // 2
+    acc, st_a = dev.snp_cross_kernel(sr, sc, ii_r, ii_c, si[:half], si[:half], chunk=chunk)
+    acc, st_b = dev.snp_cross_kernel(sr, sc, ii_r, ii_c, si[half:], si[half:], chunk=chunk, out=acc, accumulate=True)
+    assert rel_fro(acc.double().cpu().numpy(), ref) < K_TOL
+    # train x train through the rectangular path == the symmetric kernel
+    Ks, _ = dev.snp_kernel(sr, chunk=chunk)
+    Kx, _ = dev.snp_cross_kernel(sr, sr, chunk=chunk)
+    assert rel_fro(Kx.double().cpu().numpy(), Ks.double().cpu().numpy()) < 2e-6
+
+
+def test_cross_kernel_edges(oracle, dev):
+    import torch
+    pr = oracle.synth_packed(40, 0, 70, seed=3)
+    s = dev.PackedStore.from_host(pr, 40)
+    out, st = dev.snp_cross_kernel(s, s, [1, 2, 3], [], None, None)
+    assert tuple(out.shape) == (3, 0)
+    out, st = dev.snp_cross_kernel(s, s, [1, 2, 3], [4, 5], [], [])
+    assert tuple(out.shape) == (3, 2) and float(out.abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        dev.snp_cross_kernel(s, s, None, None, [1, 2], [1])

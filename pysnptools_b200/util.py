@@ -34,6 +34,12 @@ def pinned_empty(shape, dtype=np.float64, order="F"):
     return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape, order="F" if order in ("F", "A") else "C")
 
 
+def release_gpu_buffers():
+    """Return the buffers the host-buffer entry points keep cached for this thread (chunk ring, SYRK workspace, the device copy
+    of the last kernel) to the CUDA driver (``pstb_host_release``)."""
+    _lib.check(_lib.lib.pstb_host_release())
+
+
 def sub_matrix(val, row_index_list, col_index_list, order="A", dtype=np.float64, num_threads=None):
     """``val[row_index_list][:, col_index_list]`` for 2-D or 3-D arrays, in the given order / dtype, gathered on the GPU."""
     val = np.asarray(val)

@@ -172,3 +172,56 @@ def test_cross_kernel_edges(oracle, dev):
     assert tuple(out.shape) == (3, 2) and float(out.abs().sum()) == 0.0
     with pytest.raises(ValueError):
         dev.snp_cross_kernel(s, s, None, None, [1, 2], [1])
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_snp_kernel_host_entry(pinned, oracle, dev, monkeypatch):
+    """pstb_snp_kernel_host: packed host bytes -> K on the host (float32 / float64), several H2D slices, gathered axes, trained stats."""
+    import ctypes
+    from pysnptools_b200._lib import lib, check, F32, F64, STD_UNIT, STD_BETA
+    n, m = 700, 1500
+    rec = (n + 3) // 4
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=11)
+    monkeypatch.setenv("PSTB_KERNEL_SLICE_SNPS", "256")                       # 6 slices of 256 SNPs (4 chunks of 64 each)
+    if pinned:
+        p_in, p_out = lib.pstb_host_alloc(m * rec), lib.pstb_host_alloc(n * n * 8)
+        h_packed = np.ctypeslib.as_array(ctypes.cast(p_in, ctypes.POINTER(ctypes.c_uint8)), shape=(m, rec))
+        h_packed[...] = packed
+    else:
+        h_packed = packed
+    rng = np.random.default_rng(5)
+    ii = rng.permutation(n)[:300].astype(np.int64)
+    si = rng.permutation(m)[:800].astype(np.int64)
+    for dtype, code in ((np.float64, F64), (np.float32, F32)):
+        for (mode, args, ab) in ((STD_UNIT, {}, (float("nan"), float("nan"))), (STD_BETA, dict(is_beta=True, a=1, b=25), (1.0, 25.0))):
+            for iid_idx, sid_idx in ((None, None), (ii, si)):
+                ni, ns = (n if iid_idx is None else len(iid_idx)), (m if sid_idx is None else len(sid_idx))
+                ref, rst = oracle.read_kernel(packed, n, iid_index=iid_idx, sid_index=sid_idx, **args)
+                if pinned:
+                    K = np.ctypeslib.as_array(ctypes.cast(p_out, ctypes.POINTER(ctypes.c_double if dtype == np.float64 else ctypes.c_float)), shape=(ni, ni))
+                else:
+                    K = np.empty((ni, ni), dtype=dtype)
+                K[...] = -1
+                stats = np.empty((ns, 2))
+                check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None if iid_idx is None else iid_idx.ctypes.data, ni,
+                                               None if sid_idx is None else sid_idx.ctypes.data, ns, 0, mode, ab[0], ab[1], 0,
+                                               stats.ctypes.data, K.ctypes.data, code, 64))
+                assert rel_fro(K.astype(np.float64), ref) < K_TOL and np.array_equal(K, K.T)
+                np.testing.assert_allclose(stats, rst, rtol=1e-12)
+                K2 = np.empty((ni, ni), dtype=dtype)
+                check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None if iid_idx is None else iid_idx.ctypes.data, ni,
+                                               None if sid_idx is None else sid_idx.ctypes.data, ns, 0, mode, ab[0], ab[1], 1,
+                                               stats.ctypes.data, K2.ctypes.data, code, 128))
+                assert rel_fro(K2.astype(np.float64), ref) < K_TOL
+    # no SNPs -> zeros; bad index -> error
+    Kz = np.full((n, n), 3.0, dtype=np.float32)
+    st0 = np.empty((0, 2))
+    empty = np.zeros(0, dtype=np.int64)
+    check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, empty.ctypes.data, 0, 0, STD_UNIT, 0.0, 0.0, 0, st0.ctypes.data, Kz.ctypes.data, F32, 64))
+    assert not Kz.any()
+    bad = np.array([m], dtype=np.int64)
+    assert lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, bad.ctypes.data, 1, 0, STD_UNIT, 0.0, 0.0, 0, np.empty((1, 2)).ctypes.data, Kz.ctypes.data, F32, 64) != 0
+    if pinned:
+        del h_packed, K
+        lib.pstb_host_free(p_in)
+        lib.pstb_host_free(p_out)

@@ -64,6 +64,9 @@ def main():
             shutil.copyfile(os.path.join(REF, stem + ext), dst)
             os.chmod(dst, 0o644)
 
+    shutil.copyfile(os.path.join(REF, "pysnptools/examples/toydata.phe"), os.path.join(data, "toydata.phe"))   # kernelreader/test.py:125
+    os.chmod(os.path.join(data, "toydata.phe"), 0o644)
+
     # DistributedBed fixture (snpreader/distributedbed.py:296-311): pieces written with count_A1=True == distributed_bed_test1_X
     dst_dir = os.path.join(data, "distributed_bed_test1")
     if os.path.isdir(dst_dir):

@@ -153,3 +153,49 @@ def test_reference_write_roundtrip_and_pickle(ref, golden, tmp_path):
     bad = ref.SnpData(iid=data.iid, sid=data.sid, val=np.full(data.val.shape, 7.0))
     with pytest.raises(Exception):
         ref.Bed.write(str(tmp_path / "bad.bed"), bad, count_A1=False)
+
+
+# ---- the reference's OWN unit tests, unmodified, on the GPU library ---------------------------------------------------------
+# kernelreader/test.py: TestKernelReader (SnpKernel / read_kernel / trained standardizers / intersect_apply / KernelData);
+# pstreader/test.py: test_every_read (util.sub_matrix through PstData subsetting);  util/test.py: test_sub_matrix.
+REF_UNIT_TESTS = [
+    ("pysnptools.kernelreader.test", "TestKernelReader", name) for name in (
+        "test_merge_std", "test_cpp_std", "test_intersection", "test_respect_inputs", "test_fail", "test_kernel2", "test_snp_kernel2",
+        "test_npz", "test_subset", "test_identity", "test_identity_sub", "test_underscore_read1", "test_underscore_read2")
+    # test_respect_read_inputs needs h5py (KernelHdf5), which this image does not have
+] + [("pysnptools.pstreader.test", "TestPstReader", "test_every_read"), ("pysnptools.util.test", "TestUtilTools", "test_sub_matrix")]
+
+
+@pytest.fixture(scope="module")
+def ref_examples(ref, golden):
+    """`pysnptools/examples/` of the installed reference, filled from the fixtures this repo carries (the pip install has no data)."""
+    import shutil
+    ex = os.path.join(REF_DIR, "pysnptools", "examples")
+    os.makedirs(ex, exist_ok=True)
+    for ext in ("bed", "bim", "fam"):
+        shutil.copyfile(os.path.join(DATA_DIR, "toydata." + ext), os.path.join(ex, "toydata.5chrom." + ext))
+    shutil.copyfile(os.path.join(DATA_DIR, "toydata.phe"), os.path.join(ex, "toydata.phe"))
+    from pysnptools.kernelreader import KernelData, KernelNpz
+    iid = ref.Bed(os.path.join(ex, "toydata.5chrom.bed"), count_A1=False).iid
+    KernelNpz.write(os.path.join(ex, "toydata.kernel.npz"), KernelData(iid=iid, val=np.array(golden["toydata_unit_K_shipped"])))
+    return ex
+
+
+@pytest.mark.parametrize("module,cls,name", REF_UNIT_TESTS, ids=[t[2] for t in REF_UNIT_TESTS])
+def test_reference_unit_test(ref, ref_examples, module, cls, name):
+    import importlib
+    import unittest
+    mod = importlib.import_module(module)
+    case_cls = getattr(mod, cls)
+    if name not in unittest.defaultTestLoader.getTestCaseNames(case_cls):
+        pytest.skip("{0}.{1} has no {2} in this reference version".format(module, cls, name))
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(mod.__file__))                       # the reference's tests use paths relative to their own folder
+    try:
+        result = unittest.TestResult()
+        unittest.TestSuite([case_cls(name)]).run(result)
+    finally:
+        os.chdir(cwd)
+    problems = result.failures + result.errors
+    assert not problems, problems[0][1]
+    assert result.testsRun == 1

@@ -14,6 +14,19 @@ def shard_range(count, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def assign_pieces(sizes, world):
+    """DistributedBed pieces -> ranks: longest piece first onto the least loaded rank (SNP counts as weights).  Every piece goes
+    to exactly one rank; returns ``world`` ascending lists of piece numbers.  Pieces are SNP ranges, i.e. the per-GPU shard unit
+    of the kinship path, so a rank reads only its own piece files."""
+    loads = [0] * int(world)
+    owned = [[] for _ in range(int(world))]
+    for k in sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i)):
+        r = min(range(int(world)), key=lambda q: (loads[q], q))
+        owned[r].append(k)
+        loads[r] += int(sizes[k])
+    return [sorted(o) for o in owned]
+
+
 def allreduce_sum_(tensor, group=None):
     """In-place sum over the process group (NCCL on GPUs, gloo in the CPU tests). No-op without a group."""
     import torch.distributed as dist
@@ -47,13 +60,48 @@ def snp_kernel_sharded(store_shard, partial_kernel_fn, n_iid, group=None, mirror
     return K, stats
 
 
+def distributed_bed_partial_kernel(dbed, rank, world, standardizer_spec=("unit",), chunk=None):
+    """This rank's share of ``K`` for a :class:`DistributedBed`: the lower triangle accumulated over the pieces
+    ``assign_pieces`` gives it (each piece file is read by one rank only).  Returns ``(K_r, stats_r, sid_positions_r)``:
+    float32 CUDA tensor [n, n] (not mirrored), float64 CUDA tensor [m_r, 2], and the positions of those SNPs in ``dbed.sid``."""
+    import torch
+    from . import device
+    dbed._run_once()
+    sizes = [p.sid_count for p in dbed._pieces]
+    mine = assign_pieces(sizes, world)[rank]
+    n = dbed.iid_count
+    K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+    stats, where = [], []
+    for k in mine:
+        piece = dbed._pieces[k]
+        store = device.PackedStore.from_host(np.asarray(piece._packed_host()), n)
+        K, st = device.snp_kernel(store, count_A1=piece.count_A1, standardizer=standardizer_spec, chunk=chunk, K=K, accumulate=True, mirror=False)
+        stats.append(st)
+        where.append(np.arange(dbed._starts[k], dbed._starts[k + 1], dtype=np.int64))
+    stats = torch.cat(stats) if stats else torch.zeros((0, 2), dtype=torch.float64, device="cuda")
+    return K, stats, (np.concatenate(where) if where else np.zeros(0, dtype=np.int64))
+
+
 def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=None):
-    """SnpKernel over a Bed file with the SNPs sharded over the ranks of ``group`` (every rank returns the full K)."""
+    """SnpKernel over a Bed file (SNP ranges) or a DistributedBed (whole pieces) sharded over the ranks of ``group``; one
+    all-reduce of the partial kernels; every rank returns the full K and the statistics in SNP order."""
     import torch
     import torch.distributed as dist
     from . import _lib, device
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if hasattr(bed, "_read_kernel_pieces"):                                  # DistributedBed
+        K, stats, where = distributed_bed_partial_kernel(bed, rank, world, standardizer_spec, chunk)
+        if world > 1:
+            allreduce_sum_(K, group)
+            owned = assign_pieces([p.sid_count for p in bed._pieces], world)
+            counts = [int(sum(bed._pieces[k].sid_count for k in o)) for o in owned]
+            stats = allgather_rows(stats, counts, group)
+            where = np.concatenate([np.arange(bed._starts[k], bed._starts[k + 1], dtype=np.int64) for o in owned for k in o])
+        _lib.check(_lib.lib.pstb_mirror_lower(K.data_ptr(), K.shape[0], K.shape[0], torch.cuda.current_stream().cuda_stream))
+        ordered = torch.empty_like(stats)
+        ordered[torch.as_tensor(where, device=stats.device)] = stats         # rank-major -> SNP order
+        return K, ordered
     lo, hi = shard_range(bed.sid_count, rank, world)
     packed = np.asarray(bed._packed_host()[lo:hi])
     store = device.PackedStore.from_host(packed, bed.iid_count)

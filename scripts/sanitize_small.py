@@ -22,6 +22,14 @@ for n, m in ((5, 3), (203, 31), (1003, 17), (4099, 5), (30001, 3)):
     dev.standardize(x, ("unit",)); dev.standardize(x.t().contiguous().t(), ("unit",))
     dev.float_kernel(x.float())
     dev.pack(torch.randint(0, 3, (n, m), device="cuda").to(torch.int8))
+    if n <= 4099:
+        other = dev.PackedStore.from_host(o.synth_packed(77, 0, m, 0.1, seed=n + 1), 77)
+        dev.snp_cross_kernel(store, other, ii, None, None, None, chunk=64)                       # train x test, gathered rows
+        from pysnptools_b200 import _lib
+        Kh = np.empty((n, n), dtype=np.float64)
+        sth = np.empty((m, 2))
+        _lib.check(_lib.lib.pstb_snp_kernel_host(packed.ctypes.data, n, m, None, n, None, m, 0, _lib.STD_UNIT, 0.0, 0.0, 0,
+                                                 sth.ctypes.data, Kh.ctypes.data, _lib.F64, 64))
 tight = torch.from_numpy(o.synth_packed(203, 0, 9, 0.1, seed=1)).cuda()
 dev.read(dev.PackedStore(tight, 203, 9), dtype=np.float32, standardizer=("unit",))
 nomiss = o.synth_packed(300, 0, 128, 0.0, seed=2)

@@ -298,6 +298,34 @@ def test_distributed_bed(golden, tmp_path):
     assert np.array_equal(back.sid, d.sid)
 
 
+def test_distributed_bed_pieces_as_rank_shards(golden):
+    """Multi-GPU DistributedBed path with the ranks run one after the other on this GPU: every piece goes to exactly one rank,
+    the partial kernels sum to the golden K, the gathered statistics come back in SNP order; world 1 == read_kernel_multi_gpu."""
+    import torch
+    from pysnptools_b200 import DistributedBed
+    from pysnptools_b200.parallel import assign_pieces, distributed_bed_partial_kernel, read_kernel_multi_gpu
+    d = DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1"))
+    for world in (1, 2, 3):
+        K = torch.zeros((100, 100), dtype=torch.float32, device="cuda")
+        stats = np.full((100, 2), np.nan)
+        seen = []
+        for rank in range(world):
+            K_r, st_r, where = distributed_bed_partial_kernel(d, rank, world, chunk=64)
+            K += K_r
+            stats[where] = st_r.cpu().numpy()
+            seen += list(where)
+        assert sorted(seen) == list(range(100))
+        Kl = np.tril(K.double().cpu().numpy())
+        full = Kl + np.tril(Kl, -1).T
+        assert rel_fro(full, golden["dbx_unit_K"]) < 1e-5
+        np.testing.assert_allclose(stats, golden["dbx_unit_stats"], rtol=1e-12)
+    K1, st1 = read_kernel_multi_gpu(d)                                                  # no process group: world 1
+    assert rel_fro(K1.double().cpu().numpy(), golden["dbx_unit_K"]) < 1e-5
+    np.testing.assert_allclose(st1.cpu().numpy(), golden["dbx_unit_stats"], rtol=1e-12)
+    d._run_once()
+    assert sum(len(o) for o in assign_pieces([p.sid_count for p in d._pieces], 3)) == len(d._pieces)
+
+
 def test_intersect_apply_with_kernel(golden):
     from pysnptools_b200 import SnpKernel, Unit
     from pysnptools_b200.util import intersect_apply

@@ -218,11 +218,12 @@ def test_bench_reference_arm_prints_contract_line():
     import json
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-sample-sid", "300"], capture_output=True, text=True, timeout=300)
+                          "--ref-sample-sid", "300", "--kernel-n", "1500", "--ref-kernel-sid", "128"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "genotypes/s decoded+standardized" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    assert line["kernel"]["unit"] == "TFLOP/s" and line["kernel"]["value"] > 0 and line["kernel"]["cpu_baseline"]["float64_value"] > 0
 
 
 def test_pstreader_accessor_surface():
@@ -257,3 +258,17 @@ def test_pstreader_accessor_surface():
     assert kd.read().val.flags["F_CONTIGUOUS"] and kd[[1, 0], :].val[0, 0] == 2.0
     with pytest.raises(AssertionError):
         kd.iid
+
+
+def test_assign_pieces_balances_and_partitions():
+    from pysnptools_b200.parallel import assign_pieces
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for count in (0, 1, 5, 22, 100):
+            sizes = rng.integers(1, 5000, size=count)
+            owned = assign_pieces(sizes, world)
+            assert len(owned) == world and sorted(k for o in owned for k in o) == list(range(count))
+            assert all(o == sorted(o) for o in owned)
+            loads = [int(sum(sizes[k] for k in o)) for o in owned]
+            if count >= world:
+                assert max(loads) - min(loads) <= int(sizes.max())           # greedy longest-first bound

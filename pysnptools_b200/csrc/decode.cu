@@ -894,6 +894,148 @@ __global__ void __launch_bounds__(256) k_emit_c(const ReadParams p, long long ti
     }
 }
 
+// ---- C order, wide rows: 32 bytes (one 256-bit store) per lane, 1 KiB of one output row per warp store ------------------
+// The tile is (32 * V) SNPs x 512 individuals with V = 32 / sizeof(T) adjacent SNPs per lane (float32: 256 SNPs, float64: 128).
+// DRAM sees 1 KiB contiguous row pieces instead of 256 B ones.  The packed bytes are transposed on the way into shared
+// memory -- codes_t[row quad][SNP] -- so a lane fetches the codes of its V SNPs for four rows with ONE 64- / 32-bit
+// shared load, conflict-free (consecutive lanes read consecutive bytes).  Lane <-> record during the fill: the 32 lanes of a
+// warp walk the 128-byte fragments of 32 records word by word (each fragment is one L1 line, touched 32 times) and drop
+// the four bytes of a word into four smem rows, 32 consecutive bytes per warp store.
+template <typename T>
+struct WideRow;
+template <>
+struct WideRow<float> {
+    static constexpr int V = 8;
+    static __device__ __forceinline__ void st(float* o, const float (&v)[8]) { st256_f32(o, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]); }
+};
+template <>
+struct WideRow<double> {
+    static constexpr int V = 4;
+    static __device__ __forceinline__ void st(double* o, const double (&v)[4]) { st256_f64(o, v[0], v[1], v[2], v[3]); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_emit_c_wide(const ReadParams p, long long tiles_i) {
+    constexpr int V = WideRow<T>::V;
+    constexpr int TS = kTileS * V;                  // SNPs per tile
+    constexpr int Q = kTileI / 4;                   // row quads per tile
+    constexpr int kPitch = TS + 8;                  // bytes per row quad (8-byte aligned rows for the 64-bit loads)
+    __shared__ __align__(16) unsigned char codes_t[Q][kPitch];
+    __shared__ T lut_s[TS][4];
+    const long long tile = blockIdx.x;
+    const long long ts = tile / tiles_i, ti = tile % tiles_i;
+    const long long b0 = ts * TS, i0 = ti * kTileI;
+    const long long n_out = p.iid.n;
+    const int rows = (int)min((long long)kTileI, n_out - i0);
+    const int nsnp = (int)min((long long)TS, p.sid.n - b0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nbytes = (rows + 3) >> 2;             // row quads in use
+    const bool word_ok = p.dense && (p.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.packed) & 3u) == 0) && (p.byte_off % 4 == 0);
+
+    for (int s0 = warp * 32; s0 < TS; s0 += nwarps * 32) {
+        const int s = s0 + lane;
+        const bool live = s < nsnp;
+        const long long j = live ? clampll(p.sid.at(b0 + s), p.sid_count) : 0;
+        const uint8_t* src = p.packed + j * p.ld;
+        if (word_ok) {
+            const uint32_t* frag = reinterpret_cast<const uint32_t*>(src + p.byte_off + (i0 >> 2));
+            const int nwords = (nbytes + 3) >> 2;   // may run up to 3 bytes into the record's ld padding; those codes are never emitted
+#pragma unroll 4
+            for (int w = 0; w < nwords; ++w) {
+                const uint32_t word = live ? __ldg(frag + w) : 0x55555555u;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (4 * w + t < Q) codes_t[4 * w + t][s] = (unsigned char)(word >> (8 * t));
+            }
+        } else {
+            for (int q = 0; q < nbytes; ++q) {
+                uint32_t byte = 0x55u;
+                if (live) {
+                    if (p.dense) {
+                        byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+                    } else {
+                        byte = 0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const long long a = i0 + 4 * q + t;
+                            if (a < n_out) {
+                                const long long i = clampll(p.iid.at(a), p.iid_count);
+                                byte |= ((uint32_t)(__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u) << (2 * t);
+                            }
+                        }
+                    }
+                }
+                codes_t[q][s] = (unsigned char)byte;
+            }
+        }
+    }
+    for (int s = threadIdx.x; s < nsnp; s += blockDim.x) {
+        double mean = 0.0, sd = 1.0;
+        if (p.mode != PSTB_STD_NONE) {
+            mean = p.stats[2 * (b0 + s)];
+            sd = p.stats[2 * (b0 + s) + 1];
+        }
+        Lut4<T> l = make_code_lut<T>(p.mode, p.count_a1, p.a, p.b, p.lnB, mean, sd);
+        lut_s[s][0] = l.c0; lut_s[s][1] = l.c1; lut_s[s][2] = l.c2; lut_s[s][3] = l.c3;
+    }
+    __syncthreads();
+    if (V * lane >= nsnp) return;
+    Lut4<T> lut[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int s = min(V * lane + k, nsnp - 1);
+        lut[k].c0 = lut_s[s][0]; lut[k].c1 = lut_s[s][1]; lut[k].c2 = lut_s[s][2]; lut[k].c3 = lut_s[s][3];
+    }
+    const bool full = V * lane + V <= nsnp;
+    T* dst = reinterpret_cast<T*>(p.out) + (i0 + 4LL * warp) * p.out_ld + b0 + V * lane;
+    const long long dstep = 4LL * nwarps * p.out_ld;
+    for (int q = warp; q < nbytes; q += nwarps, dst += dstep) {
+        uint32_t lo, hi = 0;
+        if (V == 8) {
+            const uint2 two = *reinterpret_cast<const uint2*>(&codes_t[q][V * lane]);
+            lo = two.x;
+            hi = two.y;
+        } else {
+            lo = *reinterpret_cast<const uint32_t*>(&codes_t[q][V * lane]);
+        }
+        const int nr = min(4, rows - 4 * q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < nr) {
+                T v[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const uint32_t byte = ((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu;
+                    v[k] = lut[k].pick((byte >> (2 * t)) & 3u);
+                }
+                T* d = dst + (long long)t * p.out_ld;
+                if (full) WideRow<T>::st(d, v);
+                else
+                    for (int k = 0; k < V; ++k)
+                        if (V * lane + k < nsnp) d[k] = v[k];
+            }
+        }
+    }
+}
+
+// returns -1 when the wide kernel does not apply (int8, rows not 32-byte aligned, fewer SNPs than one tile): narrow tiles then
+template <typename T>
+static int launch_emit_c_wide(const ReadParams& p, cudaStream_t st) {
+    if constexpr (sizeof(T) == 1) {
+        return -1;
+    } else {
+        constexpr int V = WideRow<T>::V, TS = kTileS * V;
+        static const bool narrow_env = getenv("PSTB_EMIT_C_NARROW") && atoi(getenv("PSTB_EMIT_C_NARROW")) != 0;     // A/B runs
+        if (narrow_env || p.sid.n < TS || p.sid.n % V != 0 || (reinterpret_cast<uintptr_t>(p.out) & 31u)) return -1;
+        const long long tiles_i = (p.iid.n + kTileI - 1) / kTileI, tiles_s = (p.sid.n + TS - 1) / TS;
+        const long long tiles = tiles_i * tiles_s;
+        if (tiles > 0x7fffffffLL) return fail("C-order read too large for one launch (%lld tiles)", tiles);
+        k_emit_c_wide<T><<<(unsigned)tiles, 256, 0, st>>>(p, tiles_i);
+        PSTB_AFTER_LAUNCH("k_emit_c_wide");
+        return 0;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 static int check_axis(const pstb_axis& ax, int64_t count, const char* name) {
     if (ax.n < 0) return fail("%s.n is negative", name);
@@ -921,6 +1063,10 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         }
         if (!p.out) return 0;
         p.out_ld = p.sid.n;
+        {
+            const int rc = launch_emit_c_wide<T>(p, st);
+            if (rc >= 0) return rc;
+        }
         // V adjacent SNPs per lane when the rows allow vector stores (row stride and base aligned to V elements)
         constexpr int kV = sizeof(T) == 4 ? 2 : (sizeof(T) == 1 ? 4 : 1);
         const bool vec = kV > 1 && (p.sid.n % kV == 0) && (reinterpret_cast<uintptr_t>(p.out) % (kV * sizeof(T)) == 0);

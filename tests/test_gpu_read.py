@@ -347,3 +347,29 @@ def test_all_missing_and_constant_snps(oracle, dev):
     x, _ = oracle.standardize(oracle.decode(packed[[0, 1, 3, 5]], n))
     ref = x @ x.T
     assert np.linalg.norm(_np(K).astype(np.float64) - ref) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.parametrize("n,m", [(515, 264), (1030, 520), (37, 1032), (2049, 256), (600, 776)])
+def test_c_order_wide_tiles(n, m, oracle, dev):
+    """C order with 32-byte row pieces per lane (k_emit_c_wide: float32 / float64, n_sid a multiple of 8 / 4 and >= one tile):
+    partial SNP tiles, partial row quads, gathered / strided axes, count_A1, fused standardize, and the narrow fallback."""
+    rng = np.random.default_rng(n + m)
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.1, seed=n * m)
+    store = dev.PackedStore.from_host(packed, n)
+    sels = [(None, None), (rng.permutation(n)[: max(1, n // 2)], None), (slice(None, None, -1), slice(0, m - m % 8 - 8)),
+            (None, rng.permutation(m)[: 264]), (slice(16, None), slice(3, 3 + 256))]
+    for isel, ssel in sels:
+        ii = None if isel is None else np.arange(n)[isel]
+        si = None if ssel is None else np.arange(m)[ssel]
+        for dtype in (np.float32, np.float64):
+            for a1 in (False, True):
+                val, _ = dev.read(store, isel, ssel, count_A1=a1, dtype=dtype, order="C")
+                assert val.is_contiguous()
+                assert np.array_equal(_np(val), oracle.decode(packed, n, ii, si, a1, dtype, "C"), equal_nan=True), (n, m, dtype, a1)
+            for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+                val, st = dev.read(store, isel, ssel, dtype=dtype, order="C", standardizer=std)
+                ref, rst = oracle.standardize(oracle.decode(packed, n, ii, si), **args)
+                np.testing.assert_allclose(_np(val), ref, rtol=1e-6 if dtype == np.float32 else 1e-12, atol=1e-6 if dtype == np.float32 else 1e-12)
+                np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12)
+                valf, _ = dev.read(store, isel, ssel, dtype=dtype, order="F", standardizer=std)
+                assert np.array_equal(_np(val), _np(valf))                       # C and F order carry identical values

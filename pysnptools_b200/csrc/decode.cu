@@ -373,6 +373,68 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
     }
 }
 
+// ---- statistics only (no output), contiguous individuals --------------------------------------------------
+// The first pass of a C-order standardizing read and of every K3 chunk is a pure read: k_read_f's one-record-ahead TMA
+// staging is latency-bound there (2.6 TB/s on cfg2-sized records, 1.3 TB/s at 12.5 KB).  Here every warp streams whole
+// records straight into registers with 128-bit loads, four loads per lane in flight, and counts with popc.
+__global__ void __launch_bounds__(256) k_stats_dense(const ReadParams p, int R) {
+    // a warp takes R consecutive records at a time (R a power of two <= 32); lane r keeps the counts of record r, so the fp64
+    // mean / sd arithmetic runs once per R records with R lanes busy and the statistics leave as one coalesced store
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_out = p.iid.n;
+    const long long full16 = n_out >> 6;                       // 128-bit words holding 64 selected genotypes each
+    const long long tail0 = full16 << 6;                       // first genotype of the tail
+    const long long tail_words = (n_out - tail0 + 15) >> 4;    // 32-bit words of the tail (last one masked)
+    for (long long b0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; b0 < p.sid.n; b0 += nwarps * R) {
+        unsigned int k1 = 0, k2 = 0, k3 = 0;
+        const int nrec = (int)min((long long)R, p.sid.n - b0);
+        for (int r = 0; r < nrec; ++r) {
+            const long long j = clampll(p.sid.at(b0 + r), p.sid_count);
+            const uint8_t* src = p.packed + j * p.ld + p.byte_off;
+            const uint4* src16 = reinterpret_cast<const uint4*>(src);
+            unsigned int c1 = 0, c2 = 0, c3 = 0;
+            auto add = [&](uint32_t word) {
+                const uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
+                c1 += __popc(lo & ~hi);
+                c2 += __popc(hi & ~lo);
+                c3 += __popc(hi & lo);
+            };
+            long long w = lane;
+            for (; w + 96 < full16; w += 128) {
+                const uint4 v0 = __ldg(src16 + w), v1 = __ldg(src16 + w + 32), v2 = __ldg(src16 + w + 64), v3 = __ldg(src16 + w + 96);
+                add(v0.x); add(v0.y); add(v0.z); add(v0.w);
+                add(v1.x); add(v1.y); add(v1.z); add(v1.w);
+                add(v2.x); add(v2.y); add(v2.z); add(v2.w);
+                add(v3.x); add(v3.y); add(v3.z); add(v3.w);
+            }
+            for (; w < full16; w += 32) {
+                const uint4 v = __ldg(src16 + w);
+                add(v.x); add(v.y); add(v.z); add(v.w);
+            }
+            const uint32_t* tail = reinterpret_cast<const uint32_t*>(src + (tail0 >> 2));
+            for (long long t = lane; t < tail_words; t += 32) {
+                // the last word may reach into the record's ld padding: masked to the selected genotypes
+                uint32_t word = __ldg(tail + t);
+                const long long left = n_out - tail0 - 16 * t;
+                if (left < 16) word &= (1u << (2 * (unsigned)left)) - 1u;
+                add(word);
+            }
+            c1 = __reduce_add_sync(0xffffffffu, c1);
+            c2 = __reduce_add_sync(0xffffffffu, c2);
+            c3 = __reduce_add_sync(0xffffffffu, c3);
+            if (lane == r) { k1 = c1; k2 = c2; k3 = c3; }
+        }
+        if (lane < nrec) {
+            const long long c0 = n_out - (long long)k1 - (long long)k2 - (long long)k3;
+            double mean, sd;
+            stats_from_counts(p.count_a1 ? (long long)k3 : c0, (long long)k2, p.count_a1 ? c0 : (long long)k3, mean, sd);
+            if (k1 && p.miss_flag) *p.miss_flag = 1u;
+            reinterpret_cast<double2*>(p.stats)[b0 + lane] = make_double2(mean, sd);
+        }
+    }
+}
+
 // ---- K1/K2, F order, gathered individuals: S records per batch share one pass over the index vector ---------
 // The iid index vector costs 4 bytes per output genotype -- as much as the float32 output itself -- so it is read
 // once per batch of S staged records (TMA bulk copies on one mbarrier), every thread turning its 4 indices into
@@ -1087,6 +1149,21 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         p.vec_ok = ((base & 31u) == 0 && col % 32 == 0) ? 2 : (((base & 15u) == 0 && col % 16 == 0) ? 1 : 0);
     }
     const unsigned rec16 = (p.rec_bytes + 15u) & ~15u;
+    if (!p.out && p.stats && (reinterpret_cast<uintptr_t>(p.stats) & 15u) == 0 && p.mode != PSTB_STD_NONE && !p.use_stats && p.dense &&
+        n_out >= 1024 && p.ld % 16 == 0 &&
+        ((reinterpret_cast<uintptr_t>(p.packed) + (uintptr_t)p.byte_off) & 15u) == 0 &&
+        ((n_out + 15) / 16 * 4 + p.byte_off <= p.ld || p.sid_count == 0) && !getenv("PSTB_STATS_V1")) {
+        // statistics only: 128-bit register streaming (the tail's last 32-bit word stays inside the record's ld bytes)
+        long long grid = (long long)sms * 8;
+        int R = 1;                                               // records per warp block: ~2 blocks per resident warp, at most 32
+        while (R < 32 && p.sid.n >= grid * 8 * 2 * (2 * R)) R *= 2;
+        const long long want = (p.sid.n + 8LL * R - 1) / (8LL * R);
+        if (grid > want) grid = want;
+        if (grid < 1) grid = 1;
+        k_stats_dense<<<(unsigned)grid, 256, 0, st>>>(p, R);
+        PSTB_AFTER_LAUNCH("k_stats_dense");
+        return 0;
+    }
     p.bulk_ok = ((reinterpret_cast<uintptr_t>(p.packed) & 15u) == 0) && (p.ld % 16 == 0) && (rec16 <= p.ld || p.sid_count == 0);
     p.copy_bytes = rec16;
     p.raw_stride = rec16;
@@ -1182,7 +1259,9 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         // fewer concurrent column streams write DRAM more efficiently (measured on cfg2: 1 CTA/SM 84.4 %, 2: 83.9 %, 4: 82.6 % of
         // the HBM peak); two CTAs keep enough warps to hide the per-record statistics chain.  Short records keep full occupancy.
-        if (p.rec_bytes >= 1024 && ctas_per_sm > 2) ctas_per_sm = 2;
+        // A statistics-only pass (no output: the first pass of a C-order read, every K3 chunk) is a pure latency-bound read and
+        // wants every resident warp it can get (2 CTAs/SM read 2.5 TB/s on cfg2-sized records).
+        if (p.out && p.rec_bytes >= 1024 && ctas_per_sm > 2) ctas_per_sm = 2;
         if (const char* e = getenv("PSTB_READ_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctas_per_sm = v; }   // tuning experiments
         long long want = (p.sid.n + warps - 1) / warps;
         long long grid = (long long)sms * ctas_per_sm;

@@ -64,6 +64,17 @@ if "variants" in which:
     run("decode+Unit f32 F N=50k (cta)", 50000, 200000, np.float32, "F", ("unit",))
     run("decode+Unit f32 F N=500k (cta)", 500000, 20000, np.float32, "F", ("unit",))
     run("decode+Unit f32 F N=300", 300, 4000000, np.float32, "F", ("unit",))
+if "stats" in which:
+    # statistics only (no output): the first pass of a C-order read and of every K3 chunk
+    for n, m in ((10000, 500000), (50000, 100000)):
+        store = rand_store(n, m)
+        stats = torch.empty((m, 2), dtype=torch.float64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        fn = lambda: _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n, m, _lib.Axis(None, 0, 1, n), _lib.Axis(None, 0, 1, m), 0,
+                                                            _lib.STD_UNIT, float("nan"), float("nan"), 0, stats.data_ptr(), None, _lib.F32, _lib.ORDER_F, st))
+        ms = timeit(fn)
+        print("statistics only n=%d m=%d: %.3f ms  %.0f GB/s of packed reads" % (n, m, ms, m * ((n + 3) // 4) / ms / 1e6), flush=True)
+        del store
 if "pack" in which:
     for dt, es in ((torch.int8, 1), (torch.float32, 4)):
         n, m = 10000, 200000

@@ -28,9 +28,23 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return t;
 }
 
+// value = (x - mean) * scale with ONE reciprocal per SNP instead of an fp64 division per value (the transform was bound by the
+// fp64 pipe, not by HBM): scale = 1/sd (Unit; sd = inf -> 0) or the Beta weight (0 for an SNC SNP).  The subtraction stays in
+// fp64; float32 outputs multiply in float32 like the reference's float32 path does.
+__device__ __forceinline__ double std_scale(int mode, double sd, double f) {
+    if (mode == PSTB_STD_UNIT) return 1.0 / sd;
+    return isinf(sd) ? 0.0 : f;
+}
+template <typename T>
+__device__ __forceinline__ T std_apply(double x, double mean, double scale);
+template <>
+__device__ __forceinline__ double std_apply<double>(double x, double mean, double scale) { return (x - mean) * scale; }
+template <>
+__device__ __forceinline__ float std_apply<float>(double x, double mean, double scale) { return (float)(x - mean) * (float)scale; }
+
 // ---- F order: one CTA per SNP column --------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) k_std_f(T* val, long long n_iid, long long n_sid, int mode, double a, double b,
+__global__ void __launch_bounds__(1024) k_std_f(T* val, long long n_iid, long long n_sid, int mode, double a, double b,
                                                double lnB, int apply, int use_stats, double* stats) {
     __shared__ double scratch[32];
     for (long long j = blockIdx.x; j < n_sid; j += gridDim.x) {
@@ -59,17 +73,116 @@ __global__ void __launch_bounds__(256) k_std_f(T* val, long long n_iid, long lon
             if (threadIdx.x == 0) { stats[2 * j] = mean; stats[2 * j + 1] = sd; }
         }
         if (apply) {
-            const double f = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
+            const double scale = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
             for (long long i = threadIdx.x; i < n_iid; i += blockDim.x) {
                 double x = (double)col[i];
-                col[i] = (x != x) ? (T)0 : from_double<T>(std_value(mode, x, mean, sd, f));
+                col[i] = (x != x) ? (T)0 : std_apply<T>(x, mean, scale);
             }
         }
     }
 }
 
+// ---- F order, column staged in shared memory: every value crosses HBM once in each direction ----------------------------
+// k_std_f above sweeps a column three times (sum, squared deviations, apply) and relies on L2 for the re-reads.  Here a CTA
+// brings the column into shared memory with ONE TMA bulk copy (the next column's copy is in flight meanwhile when two fit),
+// runs the two statistics passes and the transform on the shared copy, and writes it back with ONE bulk store
+// (cp.async.bulk.global.shared::cta): no load / store instructions touch global memory at all.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, long long n_sid, int mode, double a, double b,
+                                                      double lnB, int apply, int use_stats, double* stats, unsigned col_bytes,
+                                                      int nbuf) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ double scratch[64];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn);
+    unsigned char* buf0 = smem_dyn + 128;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](long long jj, int buf) {
+        mbar_expect_tx(&bars[buf], col_bytes);
+        bulk_g2s(buf0 + (size_t)buf * col_bytes, val + jj * n_iid, col_bytes, &bars[buf]);
+    };
+    long long j = blockIdx.x;
+    if (tid == 0 && j < n_sid) issue(j, 0);
+    for (uint32_t it = 0; j < n_sid; j += gridDim.x, ++it) {
+        const int cur = (nbuf == 2) ? (int)(it & 1u) : 0;
+        const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1u) : (it & 1u);
+        T* col = reinterpret_cast<T*>(buf0 + (size_t)cur * col_bytes);
+        const long long nj = j + gridDim.x;
+        if (nbuf == 2 && tid == 0 && nj < n_sid) {
+            bulk_store_wait_read();                       // the store of the column that lived in the other buffer has read it
+            issue(nj, cur ^ 1);
+        }
+        mbar_wait(&bars[cur], parity);
+        double mean, sd;
+        if (use_stats) {
+            mean = stats[2 * j];
+            sd = stats[2 * j + 1];
+        } else {
+            double s = 0.0;
+            unsigned int cnt = 0;
+            for (long long i = tid; i < n_iid; i += blockDim.x) {
+                const T x = col[i];
+                const bool ok = x == x;
+                s += ok ? (double)x : 0.0;
+                cnt += ok ? 1u : 0u;
+            }
+            // sum and count share one reduction: the count rides in the second half of the scratch array
+            s = warp_sum(s);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            const int w = tid >> 5, nw = (blockDim.x + 31) >> 5;
+            __syncthreads();
+            if ((tid & 31) == 0) { scratch[w] = s; scratch[32 + w] = (double)cnt; }
+            __syncthreads();
+            s = 0.0;
+            double c = 0.0;
+            for (int k = 0; k < nw; ++k) { s += scratch[k]; c += scratch[32 + k]; }
+            mean = s / c;
+            double ss = 0.0;
+            for (long long i = tid; i < n_iid; i += blockDim.x) {
+                const T x = col[i];
+                const double d = (x == x) ? (double)x - mean : 0.0;
+                ss = fma(d, d, ss);
+            }
+            ss = block_sum(ss, scratch);
+            sd = sqrt(ss / c);
+            if (sd == 0.0) sd = INFINITY;
+            if (tid == 0) { stats[2 * j] = mean; stats[2 * j + 1] = sd; }
+        }
+        if (apply) {
+            const double scale = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
+            for (long long i = tid; i < n_iid; i += blockDim.x) {
+                const T x = col[i];
+                col[i] = (x != x) ? (T)0 : std_apply<T>((double)x, mean, scale);
+            }
+            fence_async_smem();                           // generic-proxy writes -> visible to the bulk store
+            __syncthreads();
+            if (tid == 0) bulk_s2g(val + j * n_iid, col, col_bytes);
+        } else {
+            __syncthreads();                              // every thread is done with the column before its buffer is refilled
+        }
+        if (nbuf == 1 && tid == 0 && nj < n_sid) {
+            bulk_store_wait_read();
+            issue(nj, 0);
+        }
+    }
+    if (tid == 0) bulk_store_wait_read();                 // shared memory must outlive the last store's reads
+}
+
 // ---- C order: column sums with lanes along SNPs ---------------------------------------------------------
-// work layout (doubles): [0,m) sum  [m,2m) count  [2m,3m) sum of squared deviations  [3m,4m) mean  [4m,5m) sd  [5m,6m) factor
+// work layout (doubles): [0,m) sum  [m,2m) count  [2m,3m) sum of squared deviations  [3m,4m) mean  [4m,5m) scale  [5m,6m) unused
 //                        [6m, 6m + 2*kMaxSplits*m) per-row-split partials (summed in a fixed order: deterministic results)
 constexpr int kMaxSplits = 16;
 
@@ -135,8 +248,7 @@ __global__ void k_finalize_c(long long n_sid, int mode, double a, double b, doub
         stats[2 * j + 1] = sd;
     }
     work[3 * n_sid + j] = mean;
-    work[4 * n_sid + j] = sd;
-    work[5 * n_sid + j] = (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0;
+    work[4 * n_sid + j] = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
 }
 
 template <typename T>
@@ -145,7 +257,7 @@ __global__ void __launch_bounds__(256) k_apply_c(T* val, long long n_iid, long l
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long j = e % n_sid;
         double x = (double)val[e];
-        val[e] = (x != x) ? (T)0 : from_double<T>(std_value(mode, x, work[3 * n_sid + j], work[4 * n_sid + j], work[5 * n_sid + j]));
+        val[e] = (x != x) ? (T)0 : std_apply<T>(x, work[3 * n_sid + j], work[4 * n_sid + j]);
     }
 }
 
@@ -154,8 +266,37 @@ static int standardize_impl(T* d_val, int order, int64_t n_iid, int64_t n_sid, i
                             int apply, int use_stats, double* d_stats, double* d_work, cudaStream_t st) {
     const int sms = sm_count_cached();
     if (order == PSTB_ORDER_F) {
-        long long grid = n_sid < (long long)sms * 8 ? n_sid : (long long)sms * 8;
-        k_std_f<T><<<(unsigned)grid, 256, 0, st>>>(d_val, n_iid, n_sid, mode, a, b, lnB, apply, use_stats, d_stats);
+        const unsigned long long col_bytes = (unsigned long long)n_iid * sizeof(T);
+        const unsigned max_smem = 220u * 1024u;
+        static const bool v1 = getenv("PSTB_STD_F_V1") && atoi(getenv("PSTB_STD_F_V1")) != 0;            // A/B runs
+        if (!v1 && col_bytes >= 4096 && col_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(d_val) & 15u) == 0 && 128 + col_bytes <= max_smem) {
+            // measured on B200 (scripts/sweep_k2f.sh): ONE buffer per CTA and as many CTAs as shared memory holds beat double
+            // buffering inside fewer CTAs (float32 N = 10 000: 4.9 vs 3.8 TB/s) -- neighbouring CTAs overlap each other's load /
+            // compute / store phases; threads so that the resident CTAs fill the SM's 2048 thread slots
+            int nbuf = 1;
+            const int fit = (int)(max_smem / (128 + col_bytes));
+            int threads = fit >= 4 ? 256 : (fit >= 2 ? 512 : 1024);
+            if (const char* e = getenv("PSTB_STD_NBUF")) { int v = atoi(e); if (v == 1 || (v == 2 && 128 + 2 * col_bytes <= max_smem)) nbuf = v; }   // tuning
+            if (const char* e = getenv("PSTB_STD_THREADS")) { int v = atoi(e); if (v >= 64 && v <= 1024 && v % 32 == 0) threads = v; }
+            const unsigned smem = 128u + (unsigned)nbuf * (unsigned)col_bytes;
+            PSTB_CUDA(cudaFuncSetAttribute(k_std_f_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int ctas_per_sm = 1;
+            PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_std_f_staged<T>, threads, smem));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            long long grid = (long long)sms * ctas_per_sm;
+            if (grid > n_sid) grid = n_sid;
+            k_std_f_staged<T><<<(unsigned)grid, threads, smem, st>>>(d_val, n_iid, n_sid, mode, a, b, lnB, apply, use_stats, d_stats,
+                                                                     (unsigned)col_bytes, nbuf);
+            PSTB_AFTER_LAUNCH("k_std_f_staged");
+            return 0;
+        }
+        // columns that do not fit shared memory: three sweeps, the second and third out of L2 -- so only as many columns in
+        // flight as L2 holds (64 MB budget of the 126 MB)
+        long long per_sm = (long long)((64ull << 20) / ((unsigned long long)sms * (col_bytes ? col_bytes : 1)));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+        const int threads = per_sm <= 2 ? 1024 : 256;
+        long long grid = n_sid < (long long)sms * per_sm ? n_sid : (long long)sms * per_sm;
+        k_std_f<T><<<(unsigned)grid, threads, 0, st>>>(d_val, n_iid, n_sid, mode, a, b, lnB, apply, use_stats, d_stats);
         PSTB_AFTER_LAUNCH("k_std_f");
         return 0;
     }

@@ -75,6 +75,32 @@ if "stats" in which:
         ms = timeit(fn)
         print("statistics only n=%d m=%d: %.3f ms  %.0f GB/s of packed reads" % (n, m, ms, m * ((n + 3) // 4) / ms / 1e6), flush=True)
         del store
+if "k2f" in which:
+    # K2f: standardize an existing float matrix in place (read + write = 2 * esize bytes per value)
+    for dt, es in ((torch.float32, 4), (torch.float64, 8)):
+        for n, m in ((10000, 400000 if es == 4 else 200000), (50000, 80000 if es == 4 else 40000)):
+            base = torch.randint(0, 3, (m, n), device="cuda").to(dt)
+            base[::97, ::89] = float("nan")
+            for order, v in (("F", base.t()), ("C", base.t().contiguous())):
+                src = v.clone() if order == "C" else None
+                def fn():
+                    dev.standardize(v, ("unit",))
+                ms = timeit(fn, reps=3, warm=1)
+                print("K2f Unit %s %s n=%d m=%d: %.3f ms  %.0f GB/s (read + write)" % (str(dt), order, n, m, ms, 2 * es * n * m / ms / 1e6), flush=True)
+            del base, v
+    # sub_matrix gather: half the rows x half the columns, random
+    for dt, es in ((torch.float32, 4), (torch.float64, 8)):
+        n, m = 20000, 100000 if es == 4 else 50000
+        src = torch.randn((n, m), device="cuda", dtype=dt)
+        rng = np.random.default_rng(0)
+        rows = dev.Selection(rng.permutation(n)[: n // 2], n, "cuda"); cols = dev.Selection(rng.permutation(m)[: m // 2], m, "cuda")
+        out = torch.empty((rows.n, cols.n), device="cuda", dtype=dt)
+        code = _lib.F32 if es == 4 else _lib.F64
+        st = torch.cuda.current_stream().cuda_stream
+        fn = lambda: _lib.check(lib.pstb_subset(src.data_ptr(), code, _lib.ORDER_C, n, m, 1, rows.axis(), cols.axis(), out.data_ptr(), code, _lib.ORDER_C, st))
+        ms = timeit(fn)
+        print("subset %s C->C %dx%d of %dx%d: %.3f ms  %.0f GB/s (out bytes x 2)" % (str(dt), rows.n, cols.n, n, m, ms, 2 * es * rows.n * cols.n / ms / 1e6), flush=True)
+        del src, out
 if "pack" in which:
     for dt, es in ((torch.int8, 1), (torch.float32, 4)):
         n, m = 10000, 200000

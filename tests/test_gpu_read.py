@@ -373,3 +373,36 @@ def test_c_order_wide_tiles(n, m, oracle, dev):
                 np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12)
                 valf, _ = dev.read(store, isel, ssel, dtype=dtype, order="F", standardizer=std)
                 assert np.array_equal(_np(val), _np(valf))                       # C and F order carry identical values
+
+
+@pytest.mark.parametrize("n,m", [(1024, 40), (4100, 333), (30000, 20), (52000, 7), (2051, 9)])
+def test_standardize_float_matrix_staged_columns(n, m, oracle, dev):
+    """K2f, F order with the column staged in shared memory (TMA bulk load + bulk store; one or two buffers; (2051, 9): float32
+    columns that are not 16-byte multiples fall back to the sweeping kernel): values, statistics, trained reuse, stats only."""
+    import torch
+    from pysnptools_b200 import _lib
+    rng = np.random.default_rng(n)
+    y = rng.integers(0, 3, size=(n, m)).astype(np.float64)
+    y[:, 1] = 1.0                                                       # SNC column
+    y[rng.random(y.shape) < 0.07] = np.nan
+    if m > 5:
+        y[:, 5] = rng.normal(50.0, 0.01, size=n)                        # |mean| >> sd: the two-pass formula matters
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        src = y if std[0] == "unit" else np.where(np.abs(y) > 2, np.nan, y)
+        # column 5 (mean 50, sd 0.01) amplifies a 4-ulp difference in the mean (summation order) by mean / sd = 5000
+        for dtype, rtol, atol in ((np.float64, 1e-10, 1e-10), (np.float32, 2e-4, 2e-5)):
+            ref, rst = oracle.standardize(np.array(src, dtype=dtype).astype(np.float64), **args)     # the values the GPU is given
+            t = torch.from_numpy(np.array(src, dtype=dtype, order="F")).cuda()
+            assert t.t().is_contiguous()
+            st = dev.standardize(t, std)
+            got, gst = _np(t), _np(st)
+            fin = np.isfinite(rst).all(axis=1)
+            np.testing.assert_allclose(gst[fin], rst[fin], rtol=1e-12 if dtype == np.float64 else 1e-6)
+            assert np.array_equal(np.isinf(gst[:, 1]), np.isinf(rst[:, 1]))
+            np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+            t2 = torch.from_numpy(np.array(src, dtype=dtype, order="F")).cuda()
+            dev.standardize(t2, std, stats=st)
+            np.testing.assert_allclose(_np(t2), got, rtol=1e-12, atol=1e-14)
+            t3 = torch.from_numpy(np.array(src, dtype=dtype, order="F")).cuda()
+            st3 = dev.standardize(t3, std, apply_in_place=False)        # statistics only: the matrix is left alone
+            assert np.array_equal(_np(t3), np.array(src, dtype=dtype), equal_nan=True) and np.array_equal(_np(st3), gst, equal_nan=True)

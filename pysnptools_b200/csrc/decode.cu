@@ -999,7 +999,22 @@ __global__ void __launch_bounds__(256) k_emit_c_wide(const ReadParams p, long lo
         const bool live = s < nsnp;
         const long long j = live ? clampll(p.sid.at(b0 + s), p.sid_count) : 0;
         const uint8_t* src = p.packed + j * p.ld;
-        if (word_ok) {
+        if (word_ok && nbytes == Q && p.ld % 16 == 0 && ((reinterpret_cast<uintptr_t>(p.packed) + (uintptr_t)p.byte_off) & 15u) == 0) {
+            // full tile: the whole 128-byte fragment with eight independent 128-bit loads (all in flight at once: the fill was
+            // the exposed latency of this kernel, stall long_scoreboard 15 per issue in profiles/r1_late_kernels_full.txt)
+            const uint4* frag = reinterpret_cast<const uint4*>(src + p.byte_off + (i0 >> 2));
+            uint4 v[Q / 16];
+#pragma unroll
+            for (int k = 0; k < Q / 16; ++k) v[k] = live ? __ldg(frag + k) : make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
+#pragma unroll
+            for (int k = 0; k < Q / 16; ++k) {
+                const uint32_t wd[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) codes_t[16 * k + 4 * u + t][s] = (unsigned char)(wd[u] >> (8 * t));
+            }
+        } else if (word_ok) {
             const uint32_t* frag = reinterpret_cast<const uint32_t*>(src + p.byte_off + (i0 >> 2));
             const int nwords = (nbytes + 3) >> 2;   // may run up to 3 bytes into the record's ld padding; those codes are never emitted
 #pragma unroll 4

@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
             issue(nj, cur ^ 1);
         }
         mbar_wait(&bars[cur], parity);
+        // 128-bit shared-memory accesses: 4 float32 / 2 float64 values per instruction (the scalar version was issue-bound at
+        // 39 instructions per value, profiles/r1_late_kernels_full.txt); the column starts 16-byte aligned in shared memory
+        constexpr int VW = 16 / sizeof(T);
+        struct alignas(16) Vec { T v[VW]; };
+        Vec* colv = reinterpret_cast<Vec*>(col);
+        const long long nvec = n_iid / VW;
         double mean, sd;
         if (use_stats) {
             mean = stats[2 * j];
@@ -133,7 +139,16 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
         } else {
             double s = 0.0;
             unsigned int cnt = 0;
-            for (long long i = tid; i < n_iid; i += blockDim.x) {
+            for (long long i = tid; i < nvec; i += blockDim.x) {
+                const Vec x = colv[i];
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    const bool ok = x.v[k] == x.v[k];
+                    s += ok ? (double)x.v[k] : 0.0;
+                    cnt += ok ? 1u : 0u;
+                }
+            }
+            for (long long i = nvec * VW + tid; i < n_iid; i += blockDim.x) {
                 const T x = col[i];
                 const bool ok = x == x;
                 s += ok ? (double)x : 0.0;
@@ -151,7 +166,15 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
             for (int k = 0; k < nw; ++k) { s += scratch[k]; c += scratch[32 + k]; }
             mean = s / c;
             double ss = 0.0;
-            for (long long i = tid; i < n_iid; i += blockDim.x) {
+            for (long long i = tid; i < nvec; i += blockDim.x) {
+                const Vec x = colv[i];
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    const double d = (x.v[k] == x.v[k]) ? (double)x.v[k] - mean : 0.0;
+                    ss = fma(d, d, ss);
+                }
+            }
+            for (long long i = nvec * VW + tid; i < n_iid; i += blockDim.x) {
                 const T x = col[i];
                 const double d = (x == x) ? (double)x - mean : 0.0;
                 ss = fma(d, d, ss);
@@ -163,7 +186,13 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
         }
         if (apply) {
             const double scale = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
-            for (long long i = tid; i < n_iid; i += blockDim.x) {
+            for (long long i = tid; i < nvec; i += blockDim.x) {
+                Vec x = colv[i];
+#pragma unroll
+                for (int k = 0; k < VW; ++k) x.v[k] = (x.v[k] != x.v[k]) ? (T)0 : std_apply<T>((double)x.v[k], mean, scale);
+                colv[i] = x;
+            }
+            for (long long i = nvec * VW + tid; i < n_iid; i += blockDim.x) {
                 const T x = col[i];
                 col[i] = (x != x) ? (T)0 : std_apply<T>((double)x, mean, scale);
             }

@@ -110,6 +110,11 @@ if "pack" in which:
         vc = v.contiguous()
         ms = timeit(lambda: dev.pack(vc))
         print("pack %s C n=%d m=%d: %.3f ms  %.0f GB/s" % (str(dt), n, m, ms, n * m * (es + 0.25) / ms / 1e6), flush=True)
+if "nfine" in which:
+    # does the F-order write efficiency depend on the column stride (DRAM channel camping)?
+    for n in (8192, 9984, 10000, 10016, 10240, 10496, 11264, 12288, 16384):
+        m = int(8e9 // (4 * n)) // 8 * 8
+        run("decode+Unit f32 F N=%d" % n, n, m, np.float32, "F", ("unit",))
 if "nsweep" in which:
     for n in (300, 1000, 2000, 4000, 8000, 16000, 24000, 32000):
         m = int(4e9 // (4 * n)) // 8 * 8

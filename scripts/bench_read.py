@@ -18,6 +18,9 @@ def timeit(fn, reps=5, warm=2):
 
 def rand_store(n, m, missing=False):
     ld = int(lib.pstb_packed_ld(n))
+    if os.environ.get("PSTB_BENCH_LD_ALIGN"):
+        al = int(os.environ["PSTB_BENCH_LD_ALIGN"])
+        ld = ((n + 3) // 4 + al - 1) // al * al
     t = torch.randint(0, 256, (m, ld), dtype=torch.uint8, device="cuda")
     if not missing:
         lo = t & 0x55; hi = (t >> 1) & 0x55

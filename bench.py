@@ -93,8 +93,18 @@ def cpu_snp_kernel(lib, n_iid, sample_sid, threads, dtype, seed=0):
 
 
 def cpu_kernel_baseline(lib, n_iid, sample_sid, threads):
-    t32, f32 = cpu_snp_kernel(lib, n_iid, sample_sid, threads, np.float32)
-    t64, f64 = cpu_snp_kernel(lib, n_iid, max(64, sample_sid // 2), threads, np.float64)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU baseline gets every host core, as the reference would use them
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=threads)
+    except Exception:
+        limiter = None
+    try:
+        t32, f32 = cpu_snp_kernel(lib, n_iid, sample_sid, threads, np.float32)
+        t64, f64 = cpu_snp_kernel(lib, n_iid, max(64, sample_sid // 2), threads, np.float64)
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
     return {"value": f32, "unit": "TFLOP/s", "cores": threads, "kind": "port",
             "sample": "one block of {0} SNPs x {1} iids of the cfg3 workload: oracle/c decode + Unit standardize, then NumPy val.dot(val.T) (BLAS, all cores) "
                       "into a float32 K; seconds = {2:.2f}".format(sample_sid, n_iid, t32),

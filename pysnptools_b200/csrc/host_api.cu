@@ -300,32 +300,86 @@ extern "C" int pstb_standardize_host(void* h_val, int dtype, int order, int64_t 
     if (dtype != PSTB_F32 && dtype != PSTB_F64) return fail("standardize needs float32 or float64");
     if (n_sid == 0) return 0;
     if (!h_stats) return fail("h_stats is NULL");
+    if (n_iid > 0 && !h_val) return fail("h_val is NULL");
     HostCtx& c = ctx();
     if (c.init()) return 1;
     const size_t es = esize_of(dtype);
-    cudaStream_t st = c.s[0];
     if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
     if (c.d_work.ensure((size_t)pstb_standardize_work_bytes(n_sid))) return 1;
-    if (use_stats) PSTB_CUDA(cudaMemcpyAsync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    // F order streams column blocks; C order needs the whole matrix resident
+    if (use_stats) PSTB_CUDA(cudaMemcpy(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice));
     const size_t col_bytes = (size_t)n_iid * es;
-    int64_t chunk = n_sid;
-    if (order == PSTB_ORDER_F && col_bytes > 0) {
-        chunk = (int64_t)(((size_t)256 << 20) / col_bytes);
+    if (order == PSTB_ORDER_C || col_bytes == 0) {
+        // C order: statistics need whole columns, i.e. the whole matrix resident
+        cudaStream_t st = c.s[0];
+        const size_t bytes = (size_t)n_sid * col_bytes;
+        if (c.d_out[0].ensure(bytes + 16)) return 1;
+        if (bytes) PSTB_CUDA(cudaMemcpyAsync(c.d_out[0].p, h_val, bytes, cudaMemcpyHostToDevice, st));
+        if (pstb_standardize(c.d_out[0].p, dtype, order, n_iid, n_sid, mode, a, b, apply_in_place, use_stats, (double*)c.d_stats.p,
+                             c.d_work.p, st))
+            return 1;
+        if (apply_in_place && bytes) PSTB_CUDA(cudaMemcpyAsync(h_val, c.d_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+        PSTB_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // F order: column blocks through a kSlots-deep ring -- the H2D copy of one block, the kernel of the next and the D2H copy
+        // of a third overlap (PCIe is full duplex); pageable arrays are staged through pinned buffers by host threads
+        size_t target = (size_t)64 << 20;
+        if (const char* e = getenv("PSTB_STD_HOST_CHUNK_KB")) { const long v = atol(e); if (v >= 1) target = (size_t)v << 10; }   // tests: many chunks
+        int64_t chunk = (int64_t)(target / col_bytes);
         if (chunk < 1) chunk = 1;
         if (chunk > n_sid) chunk = n_sid;
-    }
-    if (c.d_out[0].ensure((size_t)chunk * col_bytes + 16)) return 1;
-    for (int64_t b0 = 0; b0 < n_sid; b0 += chunk) {
-        const int64_t ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
-        char* hp = (char*)h_val + (order == PSTB_ORDER_F ? (size_t)b0 * col_bytes : 0);
-        const size_t bytes = (size_t)ns * col_bytes;
-        if (bytes) PSTB_CUDA(cudaMemcpyAsync(c.d_out[0].p, hp, bytes, cudaMemcpyHostToDevice, st));
-        if (pstb_standardize(c.d_out[0].p, dtype, order, n_iid, ns, mode, a, b, apply_in_place, use_stats,
-                             (double*)c.d_stats.p + 2 * b0, c.d_work.p, st))
-            return 1;
-        if (apply_in_place && bytes) PSTB_CUDA(cudaMemcpyAsync(hp, c.d_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
-        PSTB_CUDA(cudaStreamSynchronize(st));
+        const bool pinned = is_pinned(h_val);
+        for (int k = 0; k < kSlots; ++k) {
+            if (c.d_out[k].ensure((size_t)chunk * col_bytes + 16)) return 1;
+            if (!pinned && c.h_out[k].ensure((size_t)chunk * col_bytes)) return 1;
+        }
+        struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kSlots];
+        auto finish = [&](int slot) -> int {
+            if (!pend[slot].active) return 0;
+            PSTB_CUDA(cudaEventSynchronize(c.done[slot]));
+            pend[slot].active = false;
+            if (pinned || !apply_in_place) return 0;
+            char* dst = (char*)h_val + (size_t)pend[slot].b0 * col_bytes;
+            const char* src = (const char*)c.h_out[slot].p;
+            parallel_ranges((size_t)pend[slot].ns * col_bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+            return 0;
+        };
+        int rc = 0;
+        const int64_t nchunks = (n_sid + chunk - 1) / chunk;
+        for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
+            const int slot = (int)(ch % kSlots);
+            const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
+            if ((rc = finish(slot))) break;
+            cudaStream_t st = c.s[slot];
+            char* hp = (char*)h_val + (size_t)b0 * col_bytes;
+            const size_t bytes = (size_t)ns * col_bytes;
+            const void* from = hp;
+            if (!pinned) {
+                char* stage = (char*)c.h_out[slot].p;
+                parallel_ranges(bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(stage + lo, hp + lo, hi - lo); });
+                from = stage;
+            }
+            if (cudaMemcpyAsync(c.d_out[slot].p, from, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail("H2D copy failed"); break; }
+            rc = pstb_standardize(c.d_out[slot].p, dtype, order, n_iid, ns, mode, a, b, apply_in_place, use_stats,
+                                  (double*)c.d_stats.p + 2 * b0, c.d_work.p, st);
+            if (rc) break;
+            if (apply_in_place &&
+                cudaMemcpyAsync(pinned ? (void*)hp : c.h_out[slot].p, c.d_out[slot].p, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+                rc = fail("D2H copy failed");
+                break;
+            }
+            if (cudaEventRecord(c.done[slot], st) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
+            pend[slot].b0 = b0;
+            pend[slot].ns = ns;
+            pend[slot].active = true;
+        }
+        for (int k = 0; k < kSlots; ++k) {
+            int r2 = finish(k);
+            if (!rc) rc = r2;
+        }
+        if (rc) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
     }
     if (!use_stats) PSTB_CUDA(cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;

@@ -406,3 +406,32 @@ def test_standardize_float_matrix_staged_columns(n, m, oracle, dev):
             t3 = torch.from_numpy(np.array(src, dtype=dtype, order="F")).cuda()
             st3 = dev.standardize(t3, std, apply_in_place=False)        # statistics only: the matrix is left alone
             assert np.array_equal(_np(t3), np.array(src, dtype=dtype), equal_nan=True) and np.array_equal(_np(st3), gst, equal_nan=True)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_abi_standardize_pipelined_chunks(pinned, oracle, monkeypatch):
+    """pstb_standardize_host, F order: many column blocks through the 4-slot H2D / kernel / D2H ring (pageable arrays are staged
+    by host threads, pinned ones copied directly); statistics only (apply_in_place = 0) leaves the array alone; trained reuse."""
+    from pysnptools_b200 import _lib
+    from pysnptools_b200.util import pinned_empty
+    lib = _lib.lib
+    p = ctypes.c_void_p
+    monkeypatch.setenv("PSTB_STD_HOST_CHUNK_KB", "96")
+    rng = np.random.default_rng(3)
+    n, m = 1500, 173
+    y = rng.integers(0, 3, size=(n, m)).astype(np.float64)
+    y[rng.random(y.shape) < 0.05] = np.nan
+    for dtype, code, rtol, atol in ((np.float64, 1, 1e-12, 1e-13), (np.float32, 0, 1e-4, 1e-6)):
+        for mode, args, ab in ((1, {}, (float("nan"), float("nan"))), (2, dict(is_beta=True, a=1, b=25), (1.0, 25.0))):
+            ref, rst = oracle.standardize(y, **args)
+            val = pinned_empty((n, m), dtype=dtype, order="F") if pinned else np.empty((n, m), dtype=dtype, order="F")
+            val[...] = y
+            st = np.zeros((m, 2))
+            assert lib.pstb_standardize_host(p(val.ctypes.data), code, 0, n, m, mode, ab[0], ab[1], 0, 0, p(st.ctypes.data)) == 0, _lib.last_error()
+            assert np.array_equal(val, y.astype(dtype), equal_nan=True)                       # statistics only
+            np.testing.assert_allclose(st, rst, rtol=1e-12 if dtype == np.float64 else 1e-6)
+            assert lib.pstb_standardize_host(p(val.ctypes.data), code, 0, n, m, mode, ab[0], ab[1], 1, 0, p(st.ctypes.data)) == 0, _lib.last_error()
+            np.testing.assert_allclose(val, ref, rtol=rtol, atol=atol)
+            again = np.array(y, dtype=dtype, order="F")
+            assert lib.pstb_standardize_host(p(again.ctypes.data), code, 0, n, m, mode, ab[0], ab[1], 1, 1, p(st.ctypes.data)) == 0, _lib.last_error()
+            np.testing.assert_allclose(again, val, rtol=1e-12 if dtype == np.float64 else 1e-6, atol=1e-7)

@@ -12,6 +12,7 @@ from .kernelreader import KernelData, SnpKernel
 from .snpreader import Bed, SnpData, SnpReader
 from .distributedbed import DistributedBed
 from .standardizer import Beta, BetaTrained, DiagKtoN, Identity, Standardizer, Unit, UnitTrained
+from . import kernelreader, kernelstandardizer, snpreader, standardizer, util  # noqa: F401  (the reference's sub-package names)
 
 __all__ = ["Bed", "DistributedBed", "SnpData", "SnpReader", "Unit", "Beta", "UnitTrained", "BetaTrained", "Identity", "DiagKtoN", "Standardizer",
            "SnpKernel", "KernelData"]

@@ -618,3 +618,11 @@ class SnpData(SnpReader):
         out = device.convert_kernel(K32, dtype)
         val = out if to_device else _symmetric_to_host(out, order)
         return (val, trained) if return_trained else val
+
+
+def __getattr__(name):
+    """``pysnptools_b200.snpreader.DistributedBed`` as in the reference's package layout (imported lazily: it builds on this module)."""
+    if name == "DistributedBed":
+        from .distributedbed import DistributedBed
+        return DistributedBed
+    raise AttributeError("module {0!r} has no attribute {1!r}".format(__name__, name))

@@ -47,6 +47,9 @@ def test_bed_metadata_subsets_and_pickle():
     assert bed[3, np.int64(4)].shape == (1, 1)
     clone = pickle.loads(pickle.dumps(bed))
     assert repr(clone) == repr(bed) and clone.sid_count == 1015
+    import cloudpickle                                                        # what the reference's cluster runners use (test.py:993-1003)
+    clone = cloudpickle.loads(cloudpickle.dumps(bed[::2, 5:9]))
+    assert clone.shape == (150, 4) and np.array_equal(clone.sid, bed.sid[5:9])
     assert np.array_equal(bed.sid_to_index(["1_34", "1_12"]), [1, 0])
     given = Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=True, iid=bed.iid, sid=bed.sid, pos=bed.pos, skip_format_check=True)
     assert given.sid_count == 1015 and given.count_A1 is True

@@ -210,58 +210,61 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
     if (tid == 0) bulk_store_wait_read();                 // shared memory must outlive the last store's reads
 }
 
-// ---- C order: column sums with lanes along SNPs ---------------------------------------------------------
-// work layout (doubles): [0,m) sum  [m,2m) count  [2m,3m) sum of squared deviations  [3m,4m) mean  [4m,5m) scale  [5m,6m) unused
-//                        [6m, 6m + 2*kMaxSplits*m) per-row-split partials (summed in a fixed order: deterministic results)
-constexpr int kMaxSplits = 16;
+// ---- C order: one sweep for the statistics, one for the transform ---------------------------------------------------------
+// Thread <-> SNP column, so a CTA reads whole 1-2 KiB row pieces; the rows are cut into up to kMaxSplits blocks.  Every
+// (block, column) pair yields (n, mean, M2) from ONE pass with sums shifted by the block's first valid value
+// (s1 = sum(x - k), s2 = sum((x - k)^2): no cancellation as long as k is a sample of the column), and the blocks are merged
+// in a fixed order with the pairwise update of Chan et al. -- deterministic, and equal to the two-pass nanmean / nanstd of
+// the reference's python twin to ~1e-15.  (The first version swept DRAM three times and spent a 64-bit modulo per value.)
+// work layout (doubles): [0,m) mean  [m,2m) scale  then per block b: [2m + 3mb, +m) n  [.. + m, +m) mean  [.. + 2m, +m) M2
+constexpr int kMaxSplits = 12;
 
-template <typename T, int kPass>
-__global__ void __launch_bounds__(256) k_colacc_c(const T* val, long long n_iid, long long n_sid, long long rows_per_block,
-                                                  double* work) {
-    __shared__ double sh[2][8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long long j = (long long)blockIdx.x * 32 + tx;
+template <typename T>
+__global__ void __launch_bounds__(256) k_colstats_c(const T* val, long long n_iid, long long n_sid, long long rows_per_block,
+                                                    double* work) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sid) return;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(n_iid, r0 + rows_per_block);
-    double acc0 = 0.0, acc1 = 0.0;
-    if (j < n_sid) {
-        double mean = 0.0;
-        if (kPass == 1) mean = work[j] / work[n_sid + j];
-        for (long long i = r0 + ty; i < r1; i += 8) {
-            double x = (double)val[i * n_sid + j];
+    const T* p = val + r0 * n_sid + j;
+    double k = 0.0, s1 = 0.0, s2 = 0.0;
+    unsigned int cnt = 0;
+    bool have_k = false;
+    long long i = r0;
+    for (; i + 4 <= r1; i += 4, p += 4 * n_sid) {
+        const T x0 = p[0], x1 = p[n_sid], x2 = p[2 * n_sid], x3 = p[3 * n_sid];        // four independent loads in flight
+        const T xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double x = (double)xs[u];
             if (x == x) {
-                if (kPass == 0) { acc0 += x; acc1 += 1.0; }
-                else acc0 += (x - mean) * (x - mean);
+                if (!have_k) { k = x; have_k = true; }
+                const double d = x - k;
+                s1 += d;
+                s2 = fma(d, d, s2);
+                ++cnt;
             }
         }
     }
-    sh[0][ty][tx] = acc0;
-    sh[1][ty][tx] = acc1;
-    __syncthreads();
-    if (ty == 0 && j < n_sid) {
-        double t0 = 0.0, t1 = 0.0;
-        for (int k = 0; k < 8; ++k) { t0 += sh[0][k][tx]; t1 += sh[1][k][tx]; }
-        double* part = work + 6 * n_sid + (long long)blockIdx.y * 2 * n_sid;
-        part[j] = t0;
-        part[n_sid + j] = t1;
+    for (; i < r1; ++i, p += n_sid) {
+        const double x = (double)p[0];
+        if (x == x) {
+            if (!have_k) { k = x; have_k = true; }
+            const double d = x - k;
+            s1 += d;
+            s2 = fma(d, d, s2);
+            ++cnt;
+        }
     }
+    double* part = work + 2 * n_sid + (long long)blockIdx.y * 3 * n_sid;
+    const double n = (double)cnt;
+    part[j] = n;
+    part[n_sid + j] = cnt ? k + s1 / n : 0.0;
+    part[2 * n_sid + j] = cnt ? s2 - s1 * s1 / n : 0.0;
 }
 
-template <int kPass>
-__global__ void k_colsum_partials(long long n_sid, int splits, double* work) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_sid) return;
-    double t0 = 0.0, t1 = 0.0;
-    for (int s = 0; s < splits; ++s) {
-        const double* part = work + 6 * n_sid + (long long)s * 2 * n_sid;
-        t0 += part[j];
-        t1 += part[n_sid + j];
-    }
-    if (kPass == 0) { work[j] = t0; work[n_sid + j] = t1; }
-    else work[2 * n_sid + j] = t0;
-}
-
-__global__ void k_finalize_c(long long n_sid, int mode, double a, double b, double lnB, int use_stats, double* stats, double* work) {
+__global__ void k_finalize_c(long long n_sid, int splits, int mode, double a, double b, double lnB, int use_stats, double* stats,
+                             double* work) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_sid) return;
     double mean, sd;
@@ -269,24 +272,47 @@ __global__ void k_finalize_c(long long n_sid, int mode, double a, double b, doub
         mean = stats[2 * j];
         sd = stats[2 * j + 1];
     } else {
-        const double c = work[n_sid + j];
-        mean = work[j] / c;
-        sd = sqrt(work[2 * n_sid + j] / c);
+        double n = 0.0, m2 = 0.0;
+        mean = 0.0;
+        for (int s = 0; s < splits; ++s) {                       // fixed order: deterministic
+            const double* part = work + 2 * n_sid + (long long)s * 3 * n_sid;
+            const double nb = part[j], mb = part[n_sid + j], m2b = part[2 * n_sid + j];
+            if (nb > 0.0) {
+                const double nt = n + nb, delta = mb - mean;
+                mean += delta * (nb / nt);
+                m2 += m2b + delta * delta * (n * nb / nt);
+                n = nt;
+            }
+        }
+        if (n == 0.0) mean = NAN;                                // all-missing SNP: NaN statistics, as the python twin
+        sd = sqrt(m2 / n);
         if (sd == 0.0) sd = INFINITY;
         stats[2 * j] = mean;
         stats[2 * j + 1] = sd;
     }
-    work[3 * n_sid + j] = mean;
-    work[4 * n_sid + j] = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
+    work[j] = mean;
+    work[n_sid + j] = std_scale(mode, sd, (mode == PSTB_STD_BETA) ? beta_factor(mean, a, b, lnB) : 0.0);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_apply_c(T* val, long long n_iid, long long n_sid, int mode, const double* work) {
-    const long long total = n_iid * n_sid;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long j = e % n_sid;
-        double x = (double)val[e];
-        val[e] = (x != x) ? (T)0 : std_apply<T>(x, work[3 * n_sid + j], work[4 * n_sid + j]);
+__global__ void __launch_bounds__(256) k_apply_c(T* val, long long n_iid, long long n_sid, long long rows_per_block, const double* work) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sid) return;
+    const double mean = work[j], scale = work[n_sid + j];
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(n_iid, r0 + rows_per_block);
+    T* p = val + r0 * n_sid + j;
+    long long i = r0;
+    for (; i + 4 <= r1; i += 4, p += 4 * n_sid) {
+        const T x0 = p[0], x1 = p[n_sid], x2 = p[2 * n_sid], x3 = p[3 * n_sid];
+        p[0] = (x0 != x0) ? (T)0 : std_apply<T>((double)x0, mean, scale);
+        p[n_sid] = (x1 != x1) ? (T)0 : std_apply<T>((double)x1, mean, scale);
+        p[2 * n_sid] = (x2 != x2) ? (T)0 : std_apply<T>((double)x2, mean, scale);
+        p[3 * n_sid] = (x3 != x3) ? (T)0 : std_apply<T>((double)x3, mean, scale);
+    }
+    for (; i < r1; ++i, p += n_sid) {
+        const T x = p[0];
+        p[0] = (x != x) ? (T)0 : std_apply<T>((double)x, mean, scale);
     }
 }
 
@@ -330,32 +356,26 @@ static int standardize_impl(T* d_val, int order, int64_t n_iid, int64_t n_sid, i
         return 0;
     }
     if (!d_work) return fail("C-order standardize needs d_work (pstb_standardize_work_bytes)");
-    const unsigned gx = (unsigned)((n_sid + 31) / 32);
+    const unsigned gx = (unsigned)((n_sid + 255) / 256);
+    long long splits = ((long long)sms * 8 + gx - 1) / gx;
+    if (splits < 1) splits = 1;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    long long rows_per_block = (n_iid + splits - 1) / splits;
+    if (rows_per_block < 4) rows_per_block = 4;
+    unsigned gy = (unsigned)((n_iid + rows_per_block - 1) / rows_per_block);
+    if (gy < 1) gy = 1;
     if (!use_stats) {
-        long long splits = ((long long)sms * 8 + gx - 1) / gx;
-        if (splits < 1) splits = 1;
-        if (splits > kMaxSplits) splits = kMaxSplits;
-        long long rows_per_block = (n_iid + splits - 1) / splits;
-        if (rows_per_block < 8) rows_per_block = 8;
-        unsigned gy = (unsigned)((n_iid + rows_per_block - 1) / rows_per_block);
-        if (gy < 1) gy = 1;
-        const unsigned gs = (unsigned)((n_sid + 255) / 256);
-        k_colacc_c<T, 0><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
-        PSTB_AFTER_LAUNCH("k_colacc_c<0>");
-        k_colsum_partials<0><<<gs, 256, 0, st>>>(n_sid, (int)gy, d_work);
-        PSTB_AFTER_LAUNCH("k_colsum_partials<0>");
-        k_colacc_c<T, 1><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
-        PSTB_AFTER_LAUNCH("k_colacc_c<1>");
-        k_colsum_partials<1><<<gs, 256, 0, st>>>(n_sid, (int)gy, d_work);
-        PSTB_AFTER_LAUNCH("k_colsum_partials<1>");
+        k_colstats_c<T><<<dim3(gx, gy), 256, 0, st>>>(d_val, n_iid, n_sid, rows_per_block, d_work);
+        PSTB_AFTER_LAUNCH("k_colstats_c");
     }
-    k_finalize_c<<<(unsigned)((n_sid + 255) / 256), 256, 0, st>>>(n_sid, mode, a, b, lnB, use_stats, d_stats, d_work);
+    k_finalize_c<<<(unsigned)((n_sid + 255) / 256), 256, 0, st>>>(n_sid, (int)gy, mode, a, b, lnB, use_stats, d_stats, d_work);
     PSTB_AFTER_LAUNCH("k_finalize_c");
     if (apply) {
-        long long total = n_iid * n_sid;
-        long long grid = (total + 255) / 256;
-        if (grid > (long long)sms * 16) grid = (long long)sms * 16;
-        k_apply_c<T><<<(unsigned)grid, 256, 0, st>>>(d_val, n_iid, n_sid, mode, d_work);
+        // the transform wants more CTAs than the statistics pass has row blocks: cut the rows finer
+        long long rows_apply = (n_iid + 63) / 64;
+        if (rows_apply < 16) rows_apply = 16;
+        const unsigned gya = (unsigned)((n_iid + rows_apply - 1) / rows_apply);
+        k_apply_c<T><<<dim3(gx, gya < 1 ? 1 : gya), 256, 0, st>>>(d_val, n_iid, n_sid, rows_apply, d_work);
         PSTB_AFTER_LAUNCH("k_apply_c");
     }
     return 0;
@@ -437,7 +457,7 @@ __global__ void __launch_bounds__(256) k_pack(const T* val, long long si, long l
 
 using namespace pstb;
 
-extern "C" int64_t pstb_standardize_work_bytes(int64_t n_sid) { return (int64_t)((6 + 2 * kMaxSplits) * (n_sid > 0 ? n_sid : 1) * sizeof(double)); }
+extern "C" int64_t pstb_standardize_work_bytes(int64_t n_sid) { return (int64_t)((2 + 3 * kMaxSplits) * (n_sid > 0 ? n_sid : 1) * sizeof(double)); }
 
 extern "C" int pstb_standardize(void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, int mode, double a, double b,
                                 int apply_in_place, int use_stats, double* d_stats, void* d_work, void* stream) {

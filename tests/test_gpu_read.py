@@ -392,6 +392,13 @@ def test_standardize_float_matrix_staged_columns(n, m, oracle, dev):
         # column 5 (mean 50, sd 0.01) amplifies a 4-ulp difference in the mean (summation order) by mean / sd = 5000
         for dtype, rtol, atol in ((np.float64, 1e-10, 1e-10), (np.float32, 2e-4, 2e-5)):
             ref, rst = oracle.standardize(np.array(src, dtype=dtype).astype(np.float64), **args)     # the values the GPU is given
+            # C order first: one statistics sweep (shifted sums per row block, merged pairwise) + one transform sweep
+            tc = torch.from_numpy(np.array(src, dtype=dtype, order="C")).cuda()
+            stc = dev.standardize(tc, std)
+            np.testing.assert_allclose(_np(tc), ref, rtol=rtol, atol=atol)
+            finc = np.isfinite(rst).all(axis=1)
+            np.testing.assert_allclose(_np(stc)[finc], rst[finc], rtol=1e-12 if dtype == np.float64 else 1e-6)
+            assert np.array_equal(np.isinf(_np(stc)[:, 1]), np.isinf(rst[:, 1]))
             t = torch.from_numpy(np.array(src, dtype=dtype, order="F")).cuda()
             assert t.t().is_contiguous()
             st = dev.standardize(t, std)

@@ -490,16 +490,26 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     store = gen_store_device(dev, torch, n, m_hi - m_lo, seed=2000 + rank)
     K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
     chunk = args.kernel_chunk
+    # N GPUs: the partial kernels live in compact lower-triangular tile storage, so the all-reduce moves the triangle only
+    compact = world > 1 and not args.square_allreduce
+    tiles = torch.zeros((len(dev.kernel_tile_coords(n)), 256, 256), dtype=torch.float32, device="cuda") if compact else None
 
     marks = []
 
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1))
+        if compact:
+            dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False)
+        else:
+            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1))
         ev[1].record()
-        if world > 1:
-            dist.all_reduce(K)                                                       # sum of partial K_r over NVLink
+        if compact:
+            dist.all_reduce(tiles)                                                   # sum of the partial triangles over NVLink
+            ev[2].record()
+            dev.kernel_from_tiles(tiles, n, K=K)                                     # -> full symmetric K
+        elif world > 1:
+            dist.all_reduce(K)
             ev[2].record()
             _lib.check(_lib.lib.pstb_mirror_lower(K.data_ptr(), n, n, torch.cuda.current_stream().cuda_stream))
         else:
@@ -524,10 +534,12 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     kclocks = sampler.window(tk0, tk1) if sampler else None
     breakdown = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
                  "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
-                 "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks]))}
+                 "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
+                 "allreduce": ("compact lower-triangular tiles ({0:.2f} GB), expanded to the square matrix in the 'mirror' slot".format(tiles.numel() * 4 / 1e9)
+                               if compact else ("square matrix" if world > 1 else "none"))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
     diag = float(K.diagonal().double().mean().item())
-    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks) if args.e2e else None
+    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks) if args.e2e else None
     cpu_baseline = None
     if rank == 0 and world == 1 and args.kernel_cpu:
         del K
@@ -548,7 +560,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
             "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
 
 
-def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, n, m, m_local, chunk, rank, world, barrier, max_over_ranks):
+def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local, chunk, rank, world, barrier, max_over_ranks):
     """cfg3 end to end from HOST buffers: pinned packed bytes -> K in pinned host memory, copies inside the timed region.
     One GPU: ONE call of pstb_snp_kernel_host (the C ABI a bed_reader-style binding would use).  N GPUs: every rank uploads its
     SNP shard, computes its partial K, NCCL all-reduce, rank 0 copies the float32 K to the host."""
@@ -580,9 +592,14 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, n, m, m_local, chunk,
         def step():
             d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
             store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
-            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False)
-            dist.all_reduce(K)
-            _lib.check(lib.pstb_mirror_lower(K.data_ptr(), n, n, stream))
+            if tiles is not None:
+                dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False)
+                dist.all_reduce(tiles)
+                dev.kernel_from_tiles(tiles, n, K=K)
+            else:
+                dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False)
+                dist.all_reduce(K)
+                _lib.check(lib.pstb_mirror_lower(K.data_ptr(), n, n, stream))
             if rank == 0:
                 t_K.copy_(K, non_blocking=True)                                     # D2H of the finished kernel
             torch.cuda.synchronize()
@@ -687,6 +704,7 @@ def main():
     ap.add_argument("--kernel-m", type=int, default=CFG3["n_sid"])
     ap.add_argument("--kernel-steps", type=int, default=2)
     ap.add_argument("--kernel-chunk", type=int, default=None)
+    ap.add_argument("--square-allreduce", action="store_true", help="A/B: all-reduce the square K instead of the compact lower triangle")
     ap.add_argument("--no-kernel-cpu", dest="kernel_cpu", action="store_false", help="skip the CPU SnpKernel sample (NumPy BLAS) of the kernel leg")
     ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")
     args = ap.parse_args()

@@ -127,6 +127,10 @@ int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count
                           int mode, double a, double b, int use_stats, double* d_stats,
                           float* d_tiles, int rank, int world, int accumulate,
                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* Expand compact tiles (the layout above, tiles of `rank` of `world`) into the full symmetric K [n_iid, n_iid] (both triangles;
+ * entries of other ranks' tiles are left untouched).  The SNP-sharded multi-GPU path accumulates into compact tiles
+ * (rank 0 of world 1 = the whole lower triangle), all-reduces them -- half the bytes of the square matrix -- and expands. */
+int pstb_kernel_from_tiles(const float* d_tiles, int64_t n_iid, int rank, int world, float* d_K, void* stream);
 /* Train x test kernel (what FaST-LMM builds from SnpKernel + the *Trained standardizers: unittrained.py:47-70,
  * betatrained.py:47-63 applied to a second iid set, then train.val.dot(test.val.T)):
  *   d_out [n_r, n_c] float32, C order (ld = n_c):  out[i, k] (+)= sum_j x_ij y_kj

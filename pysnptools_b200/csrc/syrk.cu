@@ -730,6 +730,30 @@ __global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long
     }
 }
 
+// compact tile storage [ntiles][256][256] (lower-triangular tiles of `coords`) -> full K, both triangles.  One CTA per 32 x 32
+// sub-block: a coalesced copy into the lower triangle and, through shared memory, its transpose into the upper one.  Of a
+// diagonal tile only the lower half is used, so K comes out exactly symmetric.
+__global__ void __launch_bounds__(256) k_untile(const float* tiles, const int2* coords, long long n, float* K, long long ldk) {
+    __shared__ float sub[32][33];
+    const int2 t = coords[blockIdx.x];
+    const int sr = blockIdx.y >> 3, sc = blockIdx.y & 7;
+    if (t.x == t.y && sc > sr) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* src = tiles + (long long)blockIdx.x * 65536 + (long long)(sr * 32) * 256 + sc * 32;
+    const long long i0 = (long long)t.x * 256 + sr * 32, k0 = (long long)t.y * 256 + sc * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = i0 + r, k = k0 + tx;
+        const float v = src[r * 256 + tx];
+        sub[r][tx] = v;
+        if (i < n && k < n && k <= i) K[i * ldk + k] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long k = k0 + r, i = i0 + tx;                 // writes K[k][i] = K[i][k] for k < i
+        if (i < n && k < n && k < i) K[k * ldk + i] = sub[tx][r];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_convert(const float* K, long long total, T* out, double scale) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
@@ -1311,5 +1335,21 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
         int rc = launch_cross(hi, lo, nr, rows_pad, nc, cols_pad, k_pad, d_out, nc, (accumulate || c0 > 0) ? 1 : 0, sc, st);
         if (rc) return rc;
     }
+    return 0;
+}
+
+// compact tiles of `rank` (pstb_snp_kernel_tiles layout) -> the full symmetric matrix; with world == 1 that is all of K.  The
+// SNP-sharded multi-GPU path all-reduces the compact lower triangle (half the bytes of the square matrix) and expands it here.
+extern "C" int pstb_kernel_from_tiles(const float* d_tiles, int64_t n_iid, int rank, int world, float* d_K, void* stream) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+    if (n_iid <= 0) return 0;
+    if (!d_tiles || !d_K) return fail("NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int2* coords = nullptr;
+    int ntiles = 0;
+    if (get_tiles(n_iid, 2, rank, world, st, &coords, &ntiles)) return 1;
+    if (ntiles < 1) return 0;
+    k_untile<<<dim3((unsigned)ntiles, 64), 256, 0, st>>>(d_tiles, coords, n_iid, d_K, n_iid);
+    PSTB_AFTER_LAUNCH("k_untile");
     return 0;
 }

@@ -325,6 +325,18 @@ def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standard
     return tiles, coords, d_stats
 
 
+def kernel_from_tiles(tiles, n_iid, rank=0, world=1, K=None):
+    """Compact tiles ``[count, 256, 256]`` (:func:`snp_kernel_tiles` layout) -> full symmetric float32 ``K`` [n, n]."""
+    _lib.require_gpu()
+    dev = tiles.device
+    with torch.cuda.device(dev):
+        if K is None:
+            K = torch.zeros((n_iid, n_iid), dtype=torch.float32, device=dev)
+        assert K.dtype == torch.float32 and K.is_contiguous() and tuple(K.shape) == (n_iid, n_iid) and tiles.is_contiguous()
+        check(lib.pstb_kernel_from_tiles(tiles.data_ptr(), n_iid, rank, world, K.data_ptr(), _stream()))
+    return K
+
+
 def float_kernel(val, chunk=None, K=None, accumulate=False, mirror=True):
     """``K = V V^T`` of a CUDA float tensor [n_iid, n_sid] (C- or F-contiguous) on the tensor cores (float32 result)."""
     _lib.require_gpu()

@@ -105,10 +105,14 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     lo, hi = shard_range(bed.sid_count, rank, world)
     packed = np.asarray(bed._packed_host()[lo:hi])
     store = device.PackedStore.from_host(packed, bed.iid_count)
-    K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=(world == 1))
-    if world > 1:
-        allreduce_sum_(K, group)
-        _lib.check(_lib.lib.pstb_mirror_lower(K.data_ptr(), K.shape[0], K.shape[0], torch.cuda.current_stream().cuda_stream))
+    if world == 1:
+        K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=True)
+    else:
+        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix
+        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk)
+        allreduce_sum_(tiles, group)
+        K = device.kernel_from_tiles(tiles, bed.iid_count)
+        del tiles
         counts = [shard_range(bed.sid_count, r, world)[1] - shard_range(bed.sid_count, r, world)[0] for r in range(world)]
         stats = allgather_rows(stats, counts, group)
     return K, stats

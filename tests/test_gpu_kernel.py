@@ -225,3 +225,29 @@ def test_snp_kernel_host_entry(pinned, oracle, dev, monkeypatch):
         del h_packed, K
         lib.pstb_host_free(p_in)
         lib.pstb_host_free(p_out)
+
+
+@pytest.mark.parametrize("n,m", [(300, 200), (700, 300), (1500, 130)])
+def test_kernel_from_tiles_matches_square_path(n, m, oracle, dev):
+    """Compact lower-triangular tiles -> full K (pstb_kernel_from_tiles): what the multi-GPU path does after all-reducing the
+    triangle.  Two SNP shards summed in tile storage == the one-pass square kernel; the result is exactly symmetric."""
+    import torch
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n)
+    store = dev.PackedStore.from_host(packed, n)
+    ref, _ = oracle.read_kernel(packed, n)
+    half = m // 2
+    # each "rank" standardizes its own SNPs (statistics are per SNP, so shards agree with the one-pass kernel)
+    t0, _c, _s = dev.snp_kernel_tiles(store, None, slice(0, half), chunk=64)
+    t1, _c, _s = dev.snp_kernel_tiles(store, None, slice(half, m), chunk=64)
+    K = dev.kernel_from_tiles(t0 + t1, n)
+    Kc = K.double().cpu().numpy()
+    assert np.array_equal(Kc, Kc.T) and rel_fro(Kc, ref) < K_TOL
+    Ks, _ = dev.snp_kernel(store, chunk=64)
+    assert rel_fro(Kc, Ks.double().cpu().numpy()) < 2e-6
+    # tiles of two ranks expanded into one matrix cover everything once
+    Kr = torch.full((n, n), float("nan"), device="cuda")
+    for rank in range(2):
+        tr, _c, _s = dev.snp_kernel_tiles(store, rank=rank, world=2, chunk=64)
+        dev.kernel_from_tiles(tr, n, rank=rank, world=2, K=Kr)
+    Krc = Kr.double().cpu().numpy()
+    assert not np.isnan(Krc).any() and rel_fro(Krc, ref) < K_TOL

@@ -373,6 +373,92 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
     }
 }
 
+// ---- K1/K2, F order, short records (N <= 2048): a warp takes a batch of R adjacent records ---------------------------------
+// k_read_f spends a fixed chain per record (wait for the copy, 15 shuffles, serial fp64 statistics, table) that a 75-250 byte
+// record cannot amortise (N = 300: 30 % of the HBM peak, N = 1 000: 61 %).  Here ONE bulk copy stages R records (they are
+// adjacent in the store), lane r counts record r on its own and computes its statistics and value table -- R records at once,
+// no shuffles -- and the warp then emits the records one after the other with the table broadcast from lane r.
+template <typename T>
+__device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <>
+__device__ __forceinline__ int8_t shfl_t<int8_t>(int8_t v, int src) { return (int8_t)__shfl_sync(0xffffffffu, (int)v, src); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_read_f_small(const ReadParams p, int R) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned buf_bytes = (unsigned)R * (unsigned)p.ld;
+    unsigned char* ws = smem_dyn + (size_t)w * (16u + 2u * buf_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ws);
+    unsigned char* raw0 = ws + 16;
+    const long long n_out = p.iid.n;
+    const long long nbatch = (p.sid.n + R - 1) / R, nwarps = (long long)gridDim.x * nw;
+    long long bt = (long long)blockIdx.x * nw + w;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    auto issue = [&](long long batch, int buf) {
+        const long long s0 = batch * R;
+        const unsigned bytes = (unsigned)min((long long)R, p.sid.n - s0) * (unsigned)p.ld;
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(raw0 + (size_t)buf * buf_bytes, p.packed + (p.sid.start + s0) * p.ld, bytes, &bars[buf]);
+    };
+    if (lane == 0 && bt < nbatch) issue(bt, 0);
+    const long long nwords = (n_out + 15) >> 4;
+    for (uint32_t it = 0; bt < nbatch; bt += nwarps, ++it) {
+        const int cur = (int)(it & 1u);
+        if (lane == 0 && bt + nwarps < nbatch) issue(bt + nwarps, cur ^ 1);
+        mbar_wait(&bars[cur], (it >> 1) & 1u);
+        const unsigned char* raw = raw0 + (size_t)cur * buf_bytes + p.byte_off;
+        const long long s0 = bt * R;
+        const int nr = (int)min((long long)R, p.sid.n - s0);
+        double mean = 0.0, sd = 1.0;
+        if (p.mode != PSTB_STD_NONE && lane < nr) {
+            if (p.use_stats) {
+                mean = p.stats[2 * (s0 + lane)];
+                sd = p.stats[2 * (s0 + lane) + 1];
+            } else {
+                const uint32_t* rec32 = reinterpret_cast<const uint32_t*>(raw + (size_t)lane * p.ld);
+                unsigned int c1 = 0, c2 = 0, c3 = 0;
+                for (long long k = 0; k < nwords; ++k) {
+                    uint32_t word = rec32[k];
+                    if (k == nwords - 1) {
+                        const unsigned rem = (unsigned)(n_out & 15);
+                        if (rem) word &= (1u << (2 * rem)) - 1u;
+                    }
+                    const uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
+                    c1 += __popc(lo & ~hi);
+                    c2 += __popc(hi & ~lo);
+                    c3 += __popc(hi & lo);
+                }
+                const long long c0 = n_out - (long long)c1 - (long long)c2 - (long long)c3;
+                stats_from_counts(p.count_a1 ? (long long)c3 : c0, (long long)c2, p.count_a1 ? c0 : (long long)c3, mean, sd);
+                if (c1 && p.miss_flag) *p.miss_flag = 1u;
+                if (p.stats) {
+                    p.stats[2 * (s0 + lane)] = mean;
+                    p.stats[2 * (s0 + lane) + 1] = sd;
+                }
+            }
+        }
+        if (p.out) {
+            const Lut4<T> mine = make_code_lut<T>(p.mode, p.count_a1, p.a, p.b, p.lnB, mean, sd);
+            T* o = reinterpret_cast<T*>(p.out) + s0 * p.out_ld;
+            for (int r = 0; r < nr; ++r, o += p.out_ld) {
+                Lut4<T> lut;
+                lut.c0 = shfl_t<T>(mine.c0, r);
+                lut.c1 = shfl_t<T>(mine.c1, r);
+                lut.c2 = shfl_t<T>(mine.c2, r);
+                lut.c3 = shfl_t<T>(mine.c3, r);
+                emit_column<T>(raw + (size_t)r * p.ld, o, n_out, lut, p.vec_ok, lane, 32);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- statistics only (no output), contiguous individuals --------------------------------------------------
 // The first pass of a C-order standardizing read and of every K3 chunk is a pure read: k_read_f's one-record-ahead TMA
 // staging is latency-bound there (2.6 TB/s on cfg2-sized records, 1.3 TB/s at 12.5 KB).  Here every warp streams whole
@@ -1259,6 +1345,25 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
             PSTB_AFTER_LAUNCH("k_read_f_gather");
             return 0;
         }
+    }
+    // short records, adjacent in the store: batches of R records per warp
+    if (p.dense && p.bulk_ok && p.ld <= 512 && p.sid.idx == nullptr && p.sid.step == 1 && p.byte_off % 4 == 0 &&
+        (p.mode == PSTB_STD_NONE || p.use_stats || p.byte_off + 4 * ((n_out + 15) / 16) <= p.ld) && !getenv("PSTB_READ_SMALL_V1")) {
+        int R = 32;
+        while (R > 1 && (long long)R * p.ld > 4096) R >>= 1;
+        const int warps = 8;
+        const unsigned smem = warps * (16u + 2u * (unsigned)R * (unsigned)p.ld);
+        PSTB_CUDA(cudaFuncSetAttribute(k_read_f_small<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int ctas_per_sm = 1;
+        PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f_small<T>, warps * 32, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        const long long nbatch = (p.sid.n + R - 1) / R;
+        long long grid = (long long)sms * ctas_per_sm;
+        if (grid > (nbatch + warps - 1) / warps) grid = (nbatch + warps - 1) / warps;
+        if (grid < 1) grid = 1;
+        k_read_f_small<T><<<(unsigned)grid, warps * 32, smem, st>>>(p, R);
+        PSTB_AFTER_LAUNCH("k_read_f_small");
+        return 0;
     }
     // warp-per-record when two raw buffers + the gather record stay small, else CTA-per-record
     const unsigned warp_group = 16u + 2u * rec16 + dense_bytes;

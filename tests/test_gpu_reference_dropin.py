@@ -166,6 +166,99 @@ REF_UNIT_TESTS = [
 ] + [("pysnptools.pstreader.test", "TestPstReader", "test_every_read"), ("pysnptools.util.test", "TestUtilTools", "test_sub_matrix")]
 
 
+REF_MAIN_TESTS = [("pysnptools.test", "TestPySnpTools", name) for name in (
+    "test_diagKtoN", "test_c_reader_bed", "test_c_reader_bed_count_A1", "test_p_reader_bed", "test_p_reader_bed_count_A1", "test_bed_int8",
+    "test_scalar_index", "test_some_std", "test_standardize_bed", "test_load_and_standardize_bed", "test_write_bed_f64cpp_0",
+    "test_write_bed_f64cpp_1", "test_write_bed_f64cpp_5", "test_write_x_x_cpp", "test_subset_view", "test_val_is_float", "test_read_dtype",
+    "test_val_assign", "test_c_reader_distributedbed")]
+# not runnable here: test_bed_2021 / test_write_bad_value_and_good / the doctest wrappers need files outside the package or the
+# network (example_file); the hdf5 / dat / ped / npz reader tests are other formats (out of scope) and need h5py or missing blobs
+
+
+@pytest.fixture(scope="module")
+def ref_main_tests(ref, ref_examples, oracle):
+    """pysnptools/test.py importable and fed: its bgen-dependent import stubbed, `tests/datasets` filled from this repo's fixtures,
+    and `force_python_only=True` reads -- the reference's request for its pure-Python twin, which its tests use as the CHECKER of the
+    native path -- answered by the CPU oracle.  Everything without that flag goes to the GPU library."""
+    import shutil
+    import types
+    import unittest
+    import bed_reader
+    if "pysnptools.distreader.test" not in sys.modules:                         # distreader/bgen.py needs the absent bgen_reader
+        dummy = types.ModuleType("pysnptools.distreader.test")
+        dummy.TestDistReaders = type("TestDistReaders", (unittest.TestCase,), {})
+        sys.modules["pysnptools.distreader.test"] = dummy
+    ds = os.path.join(REF_DIR, "tests", "datasets")
+    os.makedirs(ds, exist_ok=True)
+    for ext in ("bed", "bim", "fam"):
+        shutil.copyfile(os.path.join(DATA_DIR, "dbx." + ext), os.path.join(ds, "distributed_bed_test1_X." + ext))
+        shutil.copyfile(os.path.join(DATA_DIR, "n300." + ext), os.path.join(ds, "all_chr.maf0.001.N300." + ext))
+    gpu_read = bed_reader.open_bed.read
+
+    def read(self, index=None, dtype="float32", order="F", force_python_only=False, num_threads=None):
+        if not force_python_only:
+            return gpu_read(self, index=index, dtype=dtype, order=order, num_threads=num_threads)
+        if not isinstance(index, tuple):
+            index = (None, index)
+        n, m = self.iid_count, self.sid_count
+        packed = oracle.read_packed(self.filepath, n, m)
+        def resolve(ix, count):
+            if ix is None:
+                return None
+            if isinstance(ix, slice):
+                return np.arange(count, dtype=np.int64)[ix]
+            a = np.asarray(ix)
+            if a.dtype == bool:
+                return np.nonzero(a)[0].astype(np.int64)
+            a = np.atleast_1d(a).astype(np.int64)
+            return np.where(a < 0, a + count, a)
+        ii, si = resolve(index[0], n), resolve(index[1], m)
+        return oracle.decode(packed, n, ii, si, bool(self.count_A1), np.dtype(dtype), order)
+    bed_reader.open_bed.read = read
+    gpu_to_bed = bed_reader.to_bed
+
+    def to_bed(filepath, val, properties={}, count_A1=True, fam_filepath=None, bim_filepath=None, force_python_only=False, num_threads=None):
+        gpu_to_bed(filepath, val, properties=properties, count_A1=count_A1, fam_filepath=fam_filepath, bim_filepath=bim_filepath,
+                   num_threads=num_threads)
+        if force_python_only:                       # the python twin of the writer: the .bed bytes re-packed with NumPy
+            v = np.asarray(val)
+            miss = (v == -127) if v.dtype == np.int8 else np.isnan(v)
+            g = np.where(miss, 0, v).astype(np.int64)
+            code = np.where(miss, 1, np.array([3, 2, 0] if count_A1 else [0, 2, 3])[g]).astype(np.uint8)      # [n, m]
+            n, m = code.shape
+            pad = np.zeros(((n + 3) // 4 * 4, m), dtype=np.uint8)
+            pad[:n] = code
+            q = pad.reshape(-1, 4, m)
+            packed = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).T                        # [m, ceil(n/4)]
+            oracle.write_bed(str(filepath), np.ascontiguousarray(packed))
+    import pysnptools.snpreader.bed as ref_bed_module
+    bed_reader.to_bed = ref_bed_module.to_bed = to_bed
+    import pysnptools.test as main
+    yield main
+    bed_reader.open_bed.read = gpu_read
+    bed_reader.to_bed = ref_bed_module.to_bed = gpu_to_bed
+
+
+@pytest.mark.parametrize("module,cls,name", REF_MAIN_TESTS, ids=[t[2] for t in REF_MAIN_TESTS])
+def test_reference_main_unit_test(ref, ref_main_tests, module, cls, name):
+    """pysnptools/test.py::TestPySnpTools, unmodified: native decode == python decode, int8, standardize (Unit / Beta, C / F, f32 / f64),
+    read + standardize with reversed-stride subsets, Bed write round trips, DistributedBed, view semantics."""
+    import unittest
+    case_cls = getattr(ref_main_tests, cls)
+    if name not in unittest.defaultTestLoader.getTestCaseNames(case_cls):
+        pytest.skip("{0}.{1} has no {2} in this reference version".format(module, cls, name))
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(ref_main_tests.__file__))
+    try:
+        result = unittest.TestResult()
+        unittest.TestSuite([case_cls(name)]).run(result)
+    finally:
+        os.chdir(cwd)
+    problems = result.failures + result.errors
+    assert not problems, problems[0][1]
+    assert result.testsRun == 1
+
+
 @pytest.fixture(scope="module")
 def ref_examples(ref, golden):
     """`pysnptools/examples/` of the installed reference, filled from the fixtures this repo carries (the pip install has no data)."""

@@ -170,7 +170,9 @@ REF_MAIN_TESTS = [("pysnptools.test", "TestPySnpTools", name) for name in (
     "test_diagKtoN", "test_c_reader_bed", "test_c_reader_bed_count_A1", "test_p_reader_bed", "test_p_reader_bed_count_A1", "test_bed_int8",
     "test_scalar_index", "test_some_std", "test_standardize_bed", "test_load_and_standardize_bed", "test_write_bed_f64cpp_0",
     "test_write_bed_f64cpp_1", "test_write_bed_f64cpp_5", "test_write_x_x_cpp", "test_subset_view", "test_val_is_float", "test_read_dtype",
-    "test_val_assign", "test_c_reader_distributedbed")]
+    "test_val_assign", "test_c_reader_distributedbed")] + [
+    ("pysnptools.snpreader.snpgen", "TestSnpGen", "test1"),                      # generator output == the committed snpgen.bed
+    ("pysnptools.snpreader.distributedbed", "TestDistributedBed", "test1")]      # SnpGen -> DistributedBed pieces == committed pieces == *_X.bed
 # not runnable here: test_bed_2021 / test_write_bad_value_and_good / the doctest wrappers need files outside the package or the
 # network (example_file); the hdf5 / dat / ped / npz reader tests are other formats (out of scope) and need h5py or missing blobs
 
@@ -193,6 +195,10 @@ def ref_main_tests(ref, ref_examples, oracle):
     for ext in ("bed", "bim", "fam"):
         shutil.copyfile(os.path.join(DATA_DIR, "dbx." + ext), os.path.join(ds, "distributed_bed_test1_X." + ext))
         shutil.copyfile(os.path.join(DATA_DIR, "n300." + ext), os.path.join(ds, "all_chr.maf0.001.N300." + ext))
+        shutil.copyfile(os.path.join(DATA_DIR, "snpgen." + ext), os.path.join(ds, "snpgen." + ext))
+    if os.path.isdir(os.path.join(ds, "distributed_bed_test1")):
+        shutil.rmtree(os.path.join(ds, "distributed_bed_test1"))
+    shutil.copytree(os.path.join(DATA_DIR, "distributed_bed_test1"), os.path.join(ds, "distributed_bed_test1"))
     gpu_read = bed_reader.open_bed.read
 
     def read(self, index=None, dtype="float32", order="F", force_python_only=False, num_threads=None):
@@ -239,16 +245,18 @@ def ref_main_tests(ref, ref_examples, oracle):
     bed_reader.to_bed = ref_bed_module.to_bed = gpu_to_bed
 
 
-@pytest.mark.parametrize("module,cls,name", REF_MAIN_TESTS, ids=[t[2] for t in REF_MAIN_TESTS])
+@pytest.mark.parametrize("module,cls,name", REF_MAIN_TESTS, ids=[t[2] if t[2] != "test1" else t[1] + ".test1" for t in REF_MAIN_TESTS])
 def test_reference_main_unit_test(ref, ref_main_tests, module, cls, name):
     """pysnptools/test.py::TestPySnpTools, unmodified: native decode == python decode, int8, standardize (Unit / Beta, C / F, f32 / f64),
     read + standardize with reversed-stride subsets, Bed write round trips, DistributedBed, view semantics."""
+    import importlib
     import unittest
-    case_cls = getattr(ref_main_tests, cls)
+    mod = importlib.import_module(module)
+    case_cls = getattr(mod, cls)
     if name not in unittest.defaultTestLoader.getTestCaseNames(case_cls):
         pytest.skip("{0}.{1} has no {2} in this reference version".format(module, cls, name))
     cwd = os.getcwd()
-    os.chdir(os.path.dirname(ref_main_tests.__file__))
+    os.chdir(os.path.dirname(mod.__file__))
     try:
         result = unittest.TestResult()
         unittest.TestSuite([case_cls(name)]).run(result)

@@ -496,6 +496,9 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
 
     marks = []
 
+    low_term = dev.syrk_low_term_for(m, n)                       # SNP shards: the low-term mode follows the whole kernel's SNP count
+    low_term.__enter__()
+
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
@@ -546,17 +549,24 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
         torch.cuda.empty_cache()
         cpu_baseline = cpu_kernel_baseline(_oracle_lib(), n, args.ref_kernel_sid, os.cpu_count() or 1)
         K = torch.zeros((1, 1), device="cuda")
+    fp8lo = dev.get_syrk_low_term() == "fp8" or (dev.get_syrk_low_term() == "auto" and m >= n and m >= 256)
+    low_term.__exit__()
     t256 = (n + 255) // 256
     tiles = t256 * (t256 + 1) // 2                                                 # lower-triangular 256 x 256 tiles per rank
     # synthetic cfg3 has no missing genotypes: every chunk takes the 2-term exact-dosage GEMM (3 terms with PSTB_SYRK_3TERM=1)
     terms = 3 if os.environ.get("PSTB_SYRK_3TERM", "0") not in ("", "0") or os.environ.get("PSTB_SYRK_V1", "0") not in ("", "0") else 2
-    executed = terms * 2.0 * 256 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
+    # tensor-pipe work in fp16-equivalent terms: an fp8 (e4m3) MMA term costs half the cycles of an fp16 one
+    pipe_terms = 1.5 if (terms == 2 and fp8lo) else float(terms)
+    executed = pipe_terms * 2.0 * 256 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "e2e": e2e, "cpu_baseline": cpu_baseline, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
             "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32, SNP-sharded + NCCL allreduce".format(n, m),
-                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": "exact fp16 dosage x fp16 hi/lo weights ({0} MMA terms per k-step; 3-term hi/lo split when a chunk has missing data), lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)".format(terms)},
+                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": ("exact fp16 dosage x fp16 high part of the weighted dosage + e4m3 x e4m3 low term on the fp8 pipe (1 fp16 + 1 fp8 MMA term per k-step = 1.5 fp16-equivalent terms)"
+                                 if (terms == 2 and fp8lo) else "exact fp16 dosage x fp16 hi/lo weights ({0} MMA terms per k-step)".format(terms))
+                                + "; 3-term hi/lo split when a chunk has missing data; lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)",
+                       "low_term": "fp8" if fp8lo else "fp16"},
             "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
-                         "note": "executed MMA flops per rank ({0} terms x lower-triangular tiles) / time; peak = MEASURED_PEAKS bf16_tflops_sustained".format(terms)},
+                         "note": "executed tensor-pipe work per rank in fp16-equivalent flops ({0} terms x lower-triangular tiles; an fp8 term counts half) / time; peak = MEASURED_PEAKS bf16_tflops_sustained".format(pipe_terms)},
             "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
 
 

@@ -108,6 +108,14 @@ int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_
  *   split fp16 hi/lo (3 MMA terms, fp32 accumulation in tensor memory): relative Frobenius error
  *   vs float64 ~3e-7. */
 int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk);
+/* Precision / speed of the exact-dosage path (chunks without missing genotypes): K = h (w h)^T with (w h) = hi + lo in fp16.
+ * The low term h lo^T only has to carry 4-5 bits, so it can run on the fp8 pipe (e4m3 x e4m3, half the tensor cycles):
+ * relative Frobenius error (3..6)e-6 instead of ~1e-6 (north_star gate: 1e-5), ~23 % faster on cfg3.
+ * PSTB_LOW_TERM_AUTO (default; environment PSTB_SYRK_FP8LO=0/1 overrides it): fp8 when a call multiplies at least as many SNPs
+ * as individuals and at least 256 (the error estimate is statistical).  A caller that shards the SNPs of one kernel over several calls / GPUs knows the global SNP count and may
+ * choose.  Process-wide; returns the previous mode. */
+enum { PSTB_LOW_TERM_FP16 = 0, PSTB_LOW_TERM_FP8 = 1, PSTB_LOW_TERM_AUTO = 2 };
+int pstb_set_syrk_low_term(int mode);
 int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
                     pstb_axis iid, pstb_axis sid, int count_a1,
                     int mode, double a, double b, int use_stats, double* d_stats,

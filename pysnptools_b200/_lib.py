@@ -54,6 +54,7 @@ def _load():
         "pstb_kernel_tile_coords": (c_int, [c_int64, c_int, c_int, c_void_p]),
         "pstb_snp_kernel_tiles": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
                                           c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+        "pstb_set_syrk_low_term": (c_int, [c_int]),
         "pstb_kernel_from_tiles": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
         "pstb_cross_kernel_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
         "pstb_snp_cross_kernel": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int,

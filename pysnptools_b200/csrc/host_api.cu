@@ -518,7 +518,7 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
         pstb_axis sid_ax{nullptr, 0, 1, ns};
         rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
                               (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp,
-                              (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0));
+                              (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
         if (rc) break;
         if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
         used_pending[slot] = true;

@@ -113,10 +113,11 @@ __device__ __forceinline__ int8_t from_double<int8_t>(double v) { return (int8_t
 // float32 -> float32 / float64 copy of `total` contiguous entries with a scalar factor (syrk.cu)
 int convert_range(const float* d_K, long long total, void* d_out, int dtype, double scale, void* stream);
 
-// one slice of a streamed pstb_snp_kernel (syrk.cu): phase bit 0 = first slice, bit 1 = last slice; the same d_work throughout
+// one slice of a streamed pstb_snp_kernel (syrk.cu): phase bit 0 = first slice, bit 1 = last slice; the same d_work throughout;
+// total_sid = SNPs of the whole kernel (the low-term mode "auto" decides on it)
 int snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
                      int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
-                     void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase);
+                     void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase, int64_t total_sid);
 
 }  // namespace pstb
 

@@ -23,6 +23,8 @@
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <vector>
+#include <atomic>
+#include <cuda_fp8.h>
 #include "pstb_common.cuh"
 
 namespace pstb {
@@ -109,7 +111,8 @@ struct PlaneParams {
     const Scalars* sc;
     __half* hi;             // plane 0: x_hi   (exact-dosage path: h)
     __half* lo;             // plane 1: x_lo   (exact-dosage path: (w h)_hi)
-    __half* p2;             // plane 2: unused (exact-dosage path: (w h)_lo)
+    __half* p2;             // plane 2: unused (exact-dosage path: (w h)_lo; with fp8lo: two byte planes, (w h)_lo then h, e4m3)
+    int fp8lo;              // exact-dosage path with the low term on the fp8 pipe (see k_syrk2)
     double* u;              // [n_pad] rank-one vector of the exact-dosage path, accumulated over chunks
     double* csum;           // scalar c of the exact-dosage path
     long long n_pad, k_pad;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
     }
     const bool fast = p.sc->any_missing == 0u;
     __shared__ __half lut_p2[PT_S][4];
+    __shared__ __align__(4) unsigned char lut_l8[PT_S][4], lut_h8[PT_S][4];   // fp8 (e4m3) low term and dosage
     __shared__ float lut_u[PT_S][4];
     if (threadIdx.x < PT_S) {
         const int s = threadIdx.x;
@@ -191,11 +195,15 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
                 lut_hi[s][c] = h;
                 lut_lo[s][c] = l;
                 lut_p2[s][c] = __float2half_rn(0.0f);
+                lut_l8[s][c] = lut_h8[s][c] = 0;
                 lut_u[s][c] = 0.0f;
             } else {
                 lut_hi[s][c] = __float2half_rn((float)hv[c]);   // exact: |h| <= 2 with 10 fractional bits
                 lut_lo[s][c] = h;
                 lut_p2[s][c] = l;
+                // low term for the fp8 pipe: the residual x - hi itself (|.| <= half an ulp of hi <= 8) and h, both e4m3
+                lut_l8[s][c] = (unsigned char)__nv_cvt_float_to_fp8((float)(x - (double)__half2float(h)), __NV_SATFINITE, __NV_E4M3);
+                lut_h8[s][c] = (unsigned char)__nv_cvt_float_to_fp8((float)hv[c], __NV_SATFINITE, __NV_E4M3);
                 lut_u[s][c] = (float)(wd * hv[c]);
             }
         }
@@ -212,6 +220,9 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         ua[c] = lut_u[2 * lane][c];
         ub[c] = lut_u[2 * lane + 1][c];
     }
+    // the four fp8 table values of a SNP packed in one word: byte `code`
+    const uint32_t l8a = *reinterpret_cast<const uint32_t*>(lut_l8[2 * lane]), l8b = *reinterpret_cast<const uint32_t*>(lut_l8[2 * lane + 1]);
+    const uint32_t h8a = *reinterpret_cast<const uint32_t*>(lut_h8[2 * lane]), h8b = *reinterpret_cast<const uint32_t*>(lut_h8[2 * lane + 1]);
     const unsigned char* c0 = codes[2 * lane];
     const unsigned char* c1 = codes[2 * lane + 1];
     auto sel = [](const __half2 (&t)[4], uint32_t ca, uint32_t cb) {
@@ -225,7 +236,14 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         *reinterpret_cast<__half2*>(p.hi + off) = sel(h01, ca, cb);
         *reinterpret_cast<__half2*>(p.lo + off) = sel(l01, ca, cb);
         if (fast) {
-            *reinterpret_cast<__half2*>(p.p2 + off) = sel(q01, ca, cb);
+            if (p.fp8lo) {
+                unsigned char* l8 = reinterpret_cast<unsigned char*>(p.p2);
+                unsigned char* h8 = l8 + p.n_pad * p.k_pad;
+                *reinterpret_cast<uint16_t*>(l8 + off) = (uint16_t)(((l8a >> (8 * ca)) & 0xffu) | (((l8b >> (8 * cb)) & 0xffu) << 8));
+                *reinterpret_cast<uint16_t*>(h8 + off) = (uint16_t)(((h8a >> (8 * ca)) & 0xffu) | (((h8b >> (8 * cb)) & 0xffu) << 8));
+            } else {
+                *reinterpret_cast<__half2*>(p.p2 + off) = sel(q01, ca, cb);
+            }
             float uv = ((ca & 2u) ? ((ca & 1u) ? ua[3] : ua[2]) : ((ca & 1u) ? ua[1] : ua[0])) +
                        ((cb & 2u) ? ((cb & 1u) ? ub[3] : ub[2]) : ((cb & 1u) ? ub[1] : ub[0]));
 #pragma unroll
@@ -296,6 +314,7 @@ struct SyrkParams {
     // rows [row0, row0 + n) the row operand; tiles are (I, J) with 256 I >= row0 > 256 J; output row = plane row - row0,
     // n_cols columns.  Symmetric product: row0 = 0, n_cols = n.
     long long row0, n_cols;
+    int fp8lo;              // 2-term path with the low term on the fp8 pipe: map_p2 / map_h8 are byte (e4m3) planes
 };
 
 __global__ void __launch_bounds__(SYRK_THREADS, 1)
@@ -496,6 +515,24 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major byte tile, 64-byte swizzle: rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
@@ -507,7 +544,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
 k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_p2,
-        const SyrkParams p) {
+        const __grid_constant__ CUtensorMap map_h8, const SyrkParams p) {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[STAGES2 + 1], bar_empty[STAGES2 + 1], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -522,9 +559,13 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         prefetch_tmap(&map_hi);
         prefetch_tmap(&map_lo);
         prefetch_tmap(&map_p2);
+        prefetch_tmap(&map_h8);
     }
     // exact-dosage chunk (no missing data): A = h (plane 0), B = (w h)_hi, (w h)_lo (planes 1, 2): two MMAs per k-step
     const bool fast = p.sc != nullptr && p.sc->any_missing == 0u;
+    // fp8lo: the low term h * (w h)_lo runs on the fp8 pipe (e4m3 x e4m3, K = 32 per instruction: half the tensor cycles of the
+    // fp16 low term).  It only has to carry 4-5 bits: (w h)_lo is <= 2^-11 of (w h)_hi.  map_p2 / map_h8 are byte planes then.
+    const bool fp8lo = fast && p.fp8lo != 0;
     // the 2-term loop spends a third less time per k-block, so it gets a fourth (smaller) stage from the same 192 KiB ring
     const uint32_t nstages = fast ? STAGES2 + 1 : STAGES2, stage_bytes = fast ? 3u * T_BYTES : STAGE2_BYTES;
     if (warp == 1 && lane == 0) {
@@ -560,7 +601,12 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                         if (leader) mbar_expect_tx(&bar_full[stage], 2u * 3u * T_BYTES);
                         tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
                         tma_load_2d_2sm(sb + T_BYTES, &map_lo, kc, row_b, full);
-                        tma_load_2d_2sm(sb + 2 * T_BYTES, &map_p2, kc, row_b, full);
+                        if (fp8lo) {
+                            tma_load_2d_2sm(sb + 2 * T_BYTES, &map_h8, kc, row_a, full);                 // h, e4m3: 8 KiB
+                            tma_load_2d_2sm(sb + 2 * T_BYTES + T_BYTES / 2, &map_p2, kc, row_b, full);   // (w h)_lo, e4m3: 8 KiB
+                        } else {
+                            tma_load_2d_2sm(sb + 2 * T_BYTES, &map_p2, kc, row_b, full);
+                        }
                     } else {
                         if (leader) mbar_expect_tx(&bar_full[stage], 2u * STAGE2_BYTES);
                         tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
@@ -591,6 +637,23 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                         const uint64_t a_hi = make_smem_desc(sb), a_lo = make_smem_desc(sb + T_BYTES);
                         const uint64_t b_hi = make_smem_desc(sb + (fast ? 1 : 2) * T_BYTES), b_lo = make_smem_desc(sb + (fast ? 2 : 3) * T_BYTES);
                         const uint32_t first = (kb == r * run_kb) ? 0u : 1u;
+                        if (fp8lo) {
+                            // slots: [h fp16 | B (w h)_hi fp16 | h e4m3 (8 KiB) | B (w h)_lo e4m3 (8 KiB)]
+                            const uint64_t a8 = make_smem_desc_sw64(sb + 2 * T_BYTES), b8 = make_smem_desc_sw64(sb + 2 * T_BYTES + T_BYTES / 2);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, kIdesc2, (k == 0) ? first : 1u);
+                            }
+#pragma unroll
+                            for (int k = 0; k < BK / 32; ++k) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                                umma_f8_2sm(d_tmem, a8 + adv, b8 + adv, kIdesc2, 1u);
+                            }
+                            tc_commit_mc2(smem_u32(&bar_empty[stage]));
+                            if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                            continue;
+                        }
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
@@ -832,6 +895,21 @@ int make_plane_map(CUtensorMap* map, const void* plane, long long n_pad, long lo
     return 0;
 }
 
+// byte (e4m3) plane [n_pad][k_pad]: boxes of 64 bytes x 128 rows, 64-byte swizzle
+int make_byte_plane_map(CUtensorMap* map, const void* plane, long long n_pad, long long k_pad) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad};
+    cuuint32_t box[2] = {BK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(plane), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (byte plane) failed with code %d", (int)r);
+    return 0;
+}
+
 // lower-triangular tile list, rasterised in GROUP_I x GROUP_J super-blocks so concurrently running CTAs share operand rows
 void build_tiles(long long n, std::vector<int2>& out) {
     out.clear();
@@ -890,12 +968,20 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad, long long k_pad, float* K, long long ldk,
                 int accumulate, const Scalars* sc, float out_scale, cudaStream_t st, int rank = 0, int world = 1, int compact = 0,
-                const __half* p2 = nullptr, const int2** tiles_out = nullptr, int* ntiles_out = nullptr) {
+                const __half* p2 = nullptr, const int2** tiles_out = nullptr, int* ntiles_out = nullptr, int fp8lo = 0) {
     if (n_pad % ROW_PAD || k_pad % BK || n_pad < n) return fail("planes must be padded to %d rows / %d columns", ROW_PAD, BK);
     if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
-    CUtensorMap map_hi, map_lo, map_p2;
+    CUtensorMap map_hi, map_lo, map_p2, map_h8;
     if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
-    if (make_plane_map(&map_p2, p2 ? p2 : lo, n_pad, k_pad)) return 1;
+    if (fp8lo && p2) {
+        // the third plane's bytes hold two e4m3 planes: (w h)_lo, then h
+        const unsigned char* l8 = reinterpret_cast<const unsigned char*>(p2);
+        if (make_byte_plane_map(&map_p2, l8, n_pad, k_pad) || make_byte_plane_map(&map_h8, l8 + n_pad * k_pad, n_pad, k_pad)) return 1;
+    } else {
+        fp8lo = 0;
+        if (make_plane_map(&map_p2, p2 ? p2 : lo, n_pad, k_pad)) return 1;
+        map_h8 = map_p2;
+    }
     static const int env_version = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ? 1 : 2;   // 1-CTA 128x256 kept for A/B runs
     const int version = compact ? 2 : env_version;
     const int2* d_tiles = nullptr;
@@ -916,6 +1002,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.sc = sc;
     p.out_scale = out_scale;
     p.compact = compact;
+    p.fp8lo = fp8lo;
     static const int run_kb_fast_env = getenv("PSTB_RUN_KB_FAST") ? atoi(getenv("PSTB_RUN_KB_FAST")) : 0;
     p.run_kb_fast = (run_kb_fast_env >= 1 && run_kb_fast_env <= 16) ? run_kb_fast_env : 6;
     // per launch, not cached: the attribute belongs to the (function, device) pair and a thread may switch devices
@@ -925,7 +1012,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     if (version == 2) {
         int clusters = sm_count_cached() / 2;
         if (clusters > ntiles) clusters = ntiles;
-        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, p);   // __cluster_dims__(2,1,1)
+        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, p);   // __cluster_dims__(2,1,1)
         PSTB_AFTER_LAUNCH("k_syrk2");
         return 0;
     }
@@ -1001,7 +1088,7 @@ int launch_cross(const __half* hi, const __half* lo, long long n_rows, long long
     if (ntiles < 1) return 0;
     int clusters = sm_count_cached() / 2;
     if (clusters > ntiles) clusters = ntiles;
-    v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_lo, p);
+    v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_lo, map_lo, p);
     PSTB_AFTER_LAUNCH("k_syrk2");
     return 0;
 }
@@ -1059,10 +1146,20 @@ int pstb::convert_range(const float* d_K, long long total, void* d_out, int dtyp
 // phase: bit 0 = first call of a streamed sequence (clear the rank-one accumulators of the exact-dosage path), bit 1 = last call
 // (add the rank-one part to K).  A plain call sets both; pstb_snp_kernel_host streams slices through the same workspace and
 // applies the rank-one part once.
+static std::atomic<int> g_low_term{[] {
+    const char* e = getenv("PSTB_SYRK_FP8LO");                  // default for pstb_set_syrk_low_term: 0 = fp16, 1 = fp8, unset = auto
+    return e ? (atoi(e) != 0 ? PSTB_LOW_TERM_FP8 : PSTB_LOW_TERM_FP16) : PSTB_LOW_TERM_AUTO;
+}()};
+
+extern "C" int pstb_set_syrk_low_term(int mode) {
+    if (mode != PSTB_LOW_TERM_FP16 && mode != PSTB_LOW_TERM_FP8 && mode != PSTB_LOW_TERM_AUTO) return g_low_term.load();
+    return g_low_term.exchange(mode);
+}
+
 static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                            pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
                            float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
-                           void* stream, int rank, int world, int compact, int phase = 3) {
+                           void* stream, int rank, int world, int compact, int phase = 3, int64_t total_sid = -1) {
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
@@ -1100,6 +1197,16 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     static const bool env_slow = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ||
                                  (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
     const bool force_slow = use_stats || env_slow;
+    const bool env_version2_ok = true;                           // env_slow covers PSTB_SYRK_V1 (the 1-CTA kernel has no fp8 path)
+    // the low term of the 2-term path on the fp8 pipe: 25 % fewer tensor cycles (cfg3: 1 035 -> 1 276 TFLOP/s on one box); the
+    // error grows from ~1e-6 to (3..6)e-6 relative Frobenius, ~7e-6 * sqrt(N / (M + N)) by the rounding model (gate: 1e-5).
+    // auto: when this call multiplies at least as many SNPs as individuals (<= 5e-6)
+    const int lt = g_low_term.load();
+    // (a streamed call passes the SNP count of the whole kernel in total_sid)
+    // -- and at least 256 SNPs: the estimate is statistical, a handful of products does not average the e4m3 rounding out (a
+    // single product can be off by 3e-5 relative)
+    const int64_t snps = total_sid >= 0 ? total_sid : sid.n;
+    const int fp8lo = (lt == PSTB_LOW_TERM_FP8 || (lt == PSTB_LOW_TERM_AUTO && snps >= iid.n && snps >= 256)) ? 1 : 0;
     if (phase & 1) PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     const int2* d_tiles = nullptr;
     int ntiles = 0;
@@ -1136,6 +1243,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         pp.hi = hi;
         pp.lo = lo;
         pp.p2 = p2;
+        pp.fp8lo = (!force_slow && env_version2_ok) ? fp8lo : 0;
         pp.u = u;
         pp.csum = csum;
         pp.n_pad = n_pad;
@@ -1146,7 +1254,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
         PSTB_AFTER_LAUNCH("k_planes");
         int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact, p2,
-                             &d_tiles, &ntiles);
+                             &d_tiles, &ntiles, pp.fp8lo);
         if (rc) return rc;
     }
     if (!force_slow && (phase & 2)) {
@@ -1174,9 +1282,9 @@ extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_
 
 int pstb::snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
                            int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
-                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase) {
+                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase, int64_t total_sid) {
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate, 0,
-                           d_work, work_bytes, chunk, stream, 0, 1, 0, phase);
+                           d_work, work_bytes, chunk, stream, 0, 1, 0, phase, total_sid);
 }
 
 // ---- K-tile sharding (cfg5: N = 500 000, K = 1 TB does not fit one GPU) -----------------------------------------

@@ -325,6 +325,40 @@ def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standard
     return tiles, coords, d_stats
 
 
+_LOW_TERM = {"fp16": 0, "fp8": 1, "auto": 2}
+
+
+def set_syrk_low_term(mode):
+    """'fp16' | 'fp8' | 'auto' (default): where the low term of the exact-dosage SYRK runs (``pstb_set_syrk_low_term``: fp8 is ~23 %
+    faster at (3..6)e-6 instead of ~1e-6 relative Frobenius error).  Returns the previous mode's name."""
+    prev = int(lib.pstb_set_syrk_low_term(_LOW_TERM[mode]))
+    return {v: k for k, v in _LOW_TERM.items()}[prev]
+
+
+def get_syrk_low_term():
+    return {v: k for k, v in _LOW_TERM.items()}[int(lib.pstb_set_syrk_low_term(-1))]        # an invalid mode only reports
+
+
+class syrk_low_term_for(object):
+    """Context manager for a kernel whose SNPs are spread over several calls (SNP shards, DistributedBed pieces): 'auto' looks at
+    one call's SNP count, this resolves it with the count of the whole kernel.  An explicit 'fp16' / 'fp8' setting is left alone."""
+
+    def __init__(self, total_sid_count, n_iid):
+        self.choice = "fp8" if (total_sid_count >= n_iid and total_sid_count >= 256) else "fp16"
+        self.active = False
+
+    def __enter__(self):
+        if get_syrk_low_term() == "auto":
+            set_syrk_low_term(self.choice)
+            self.active = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            set_syrk_low_term("auto")
+        return False
+
+
 def kernel_from_tiles(tiles, n_iid, rank=0, world=1, K=None):
     """Compact tiles ``[count, 256, 256]`` (:func:`snp_kernel_tiles` layout) -> full symmetric float32 ``K`` [n, n]."""
     _lib.require_gpu()

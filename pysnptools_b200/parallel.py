@@ -75,7 +75,8 @@ def distributed_bed_partial_kernel(dbed, rank, world, standardizer_spec=("unit",
     for k in mine:
         piece = dbed._pieces[k]
         store = device.PackedStore.from_host(np.asarray(piece._packed_host()), n)
-        K, st = device.snp_kernel(store, count_A1=piece.count_A1, standardizer=standardizer_spec, chunk=chunk, K=K, accumulate=True, mirror=False)
+        with device.syrk_low_term_for(dbed.sid_count, n):
+            K, st = device.snp_kernel(store, count_A1=piece.count_A1, standardizer=standardizer_spec, chunk=chunk, K=K, accumulate=True, mirror=False)
         stats.append(st)
         where.append(np.arange(dbed._starts[k], dbed._starts[k + 1], dtype=np.int64))
     stats = torch.cat(stats) if stats else torch.zeros((0, 2), dtype=torch.float64, device="cuda")
@@ -108,8 +109,10 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     if world == 1:
         K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=True)
     else:
-        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix
-        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk)
+        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix.
+        # The low-term mode "auto" looks at one call's SNP count; this kernel's is the global one.
+        with device.syrk_low_term_for(bed.sid_count, bed.iid_count):
+            tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk)
         allreduce_sum_(tiles, group)
         K = device.kernel_from_tiles(tiles, bed.iid_count)
         del tiles

@@ -251,3 +251,31 @@ def test_kernel_from_tiles_matches_square_path(n, m, oracle, dev):
         dev.kernel_from_tiles(tr, n, rank=rank, world=2, K=Kr)
     Krc = Kr.double().cpu().numpy()
     assert not np.isnan(Krc).any() and rel_fro(Krc, ref) < K_TOL
+
+
+@pytest.mark.parametrize("n,m", [(515, 300), (700, 4096), (2100, 700)])
+def test_low_term_modes(n, m, oracle, dev):
+    """Exact-dosage path (no missing genotypes): the low term on the fp8 pipe (e4m3 x e4m3) stays inside the 1e-5 gate for M >> N,
+    M ~ N and M << N; the fp16 low term lands near 1e-6; 'auto' picks fp8 when a call has at least as many SNPs as individuals."""
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.0, seed=n + m)
+    store = dev.PackedStore.from_host(packed, n)
+    assert dev.get_syrk_low_term() == "auto"
+    try:
+        errs = {}
+        for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+            ref, _ = oracle.read_kernel(packed, n, **args)
+            for mode in ("fp16", "fp8", "auto"):
+                assert dev.set_syrk_low_term(mode) in ("fp16", "fp8", "auto")
+                K, _ = dev.snp_kernel(store, standardizer=std, chunk=256)
+                Kc = K.double().cpu().numpy()
+                assert np.array_equal(Kc, Kc.T)
+                errs[(std[0], mode)] = rel_fro(Kc, ref)
+        assert all(e < K_TOL for e in errs.values()), errs
+        assert all(errs[(s, "fp16")] < 3e-6 for s in ("unit", "beta")), errs
+        want_auto = "fp8" if m >= n else "fp16"
+        assert all(errs[(s, "auto")] == errs[(s, want_auto)] for s in ("unit", "beta")), errs
+    finally:
+        dev.set_syrk_low_term("auto")
+    with dev.syrk_low_term_for(10 * n, n):                                   # a sharded kernel with many SNPs in total
+        assert dev.get_syrk_low_term() == "fp8"
+    assert dev.get_syrk_low_term() == "auto"

@@ -275,3 +275,34 @@ def test_assign_pieces_balances_and_partitions():
             loads = [int(sum(sizes[k] for k in o)) for o in owned]
             if count >= world:
                 assert max(loads) - min(loads) <= int(sizes.max())           # greedy longest-first bound
+
+
+def test_syrk_low_term_switch_needs_no_gpu():
+    """pstb_set_syrk_low_term / the context manager sharded callers use: process-wide mode, 'auto' resolved with the whole kernel's SNP count."""
+    from pysnptools_b200 import device as dev
+    start = dev.get_syrk_low_term()
+    try:
+        dev.set_syrk_low_term("auto")
+        with dev.syrk_low_term_for(500_000, 50_000):
+            assert dev.get_syrk_low_term() == "fp8"
+        assert dev.get_syrk_low_term() == "auto"
+        with dev.syrk_low_term_for(100_000, 500_000):                      # fewer SNPs than individuals: fp16
+            assert dev.get_syrk_low_term() == "fp16"
+        with dev.syrk_low_term_for(100, 10):                               # too few SNPs to average the e4m3 rounding out
+            assert dev.get_syrk_low_term() == "fp16"
+        assert dev.set_syrk_low_term("fp16") == "auto"
+        with dev.syrk_low_term_for(500_000, 50_000):                       # an explicit choice is left alone
+            assert dev.get_syrk_low_term() == "fp16"
+        assert dev.get_syrk_low_term() == "fp16"
+        with pytest.raises(KeyError):
+            dev.set_syrk_low_term("bf16")
+    finally:
+        dev.set_syrk_low_term(start)
+
+
+def test_workspace_sizes_are_monotonic():
+    from pysnptools_b200 import _lib
+    lib = _lib.lib
+    assert lib.pstb_kernel_workspace_bytes(1000, 1024) < lib.pstb_kernel_workspace_bytes(5000, 1024) < lib.pstb_kernel_workspace_bytes(5000, 4096)
+    assert lib.pstb_cross_kernel_workspace_bytes(1000, 300, 1024) >= lib.pstb_kernel_workspace_bytes(1300, 1024)
+    assert lib.pstb_standardize_work_bytes(1000) == 38 * 1000 * 8 and lib.pstb_packed_ld(10000) == 2512 and lib.pstb_packed_ld(0) == 0

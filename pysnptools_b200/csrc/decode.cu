@@ -373,11 +373,17 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
     }
 }
 
-// ---- K1/K2, F order, short records (N <= 2048): a warp takes a batch of R adjacent records ---------------------------------
+// ---- K1/K2, F order, short records (N <= 4096): a warp takes a batch of R adjacent records ---------------------------------
 // k_read_f spends a fixed chain per record (wait for the copy, 15 shuffles, serial fp64 statistics, table) that a 75-250 byte
 // record cannot amortise (N = 300: 30 % of the HBM peak, N = 1 000: 61 %).  Here ONE bulk copy stages R records (they are
 // adjacent in the store), lane r counts record r on its own and computes its statistics and value table -- R records at once,
 // no shuffles -- and the warp then emits the records one after the other with the table broadcast from lane r.
+static const long long kSmallLd = [] {                           // records up to this pitch take the batched kernel (A/B knob: PSTB_SMALL_LD)
+    const char* e = getenv("PSTB_SMALL_LD");
+    const long long v = e ? atoll(e) : 0;
+    return (v >= 16 && v <= 4096) ? v : 1024;                  // measured: 1024 gains 1-2.5 points for N = 2 049 .. 4 096; 2048 loses 20 at N = 6 000
+}();
+
 template <typename T>
 __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <>
@@ -1347,7 +1353,7 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         }
     }
     // short records, adjacent in the store: batches of R records per warp
-    if (p.dense && p.bulk_ok && p.ld <= 512 && p.sid.idx == nullptr && p.sid.step == 1 && p.byte_off % 4 == 0 &&
+    if (p.dense && p.bulk_ok && p.ld <= kSmallLd && p.sid.idx == nullptr && p.sid.step == 1 && p.byte_off % 4 == 0 &&
         (p.mode == PSTB_STD_NONE || p.use_stats || p.byte_off + 4 * ((n_out + 15) / 16) <= p.ld) && !getenv("PSTB_READ_SMALL_V1")) {
         int R = 32;
         while (R > 1 && (long long)R * p.ld > 4096) R >>= 1;

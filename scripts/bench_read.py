@@ -118,6 +118,10 @@ if "nfine" in which:
     for n in (8192, 9984, 10000, 10016, 10240, 10496, 11264, 12288, 16384):
         m = int(8e9 // (4 * n)) // 8 * 8
         run("decode+Unit f32 F N=%d" % n, n, m, np.float32, "F", ("unit",))
+if "nmid" in which:
+    for n in (2400, 3000, 4000, 6000):
+        m = int(4e9 // (4 * n)) // 8 * 8
+        run("decode+Unit f32 F N=%d" % n, n, m, np.float32, "F", ("unit",))
 if "nsweep" in which:
     for n in (300, 1000, 2000, 4000, 8000, 16000, 24000, 32000):
         m = int(4e9 // (4 * n)) // 8 * 8

@@ -9,8 +9,8 @@ import os
 
 import numpy as np
 
-from .snpreader import Bed, SnpData, SnpReader, _kernel_chunk
-from .standardizer import Identity, Standardizer, _no_python_path
+from .snpreader import Bed, SnpReader, _kernel_chunk
+from .standardizer import _no_python_path
 
 
 class DistributedBed(SnpReader):

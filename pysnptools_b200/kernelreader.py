@@ -6,7 +6,7 @@ Mirrors ``SnpKernel`` (kernelreader/snpkernel.py:43-132), ``KernelReader.read`` 
 import numpy as np
 
 from .snpreader import _compose, _resolve_indexer
-from .standardizer import DiagKtoN, Identity, _is_tensor
+from .standardizer import DiagKtoN, _is_tensor
 
 
 class KernelReader(object):

@@ -7,7 +7,6 @@ The dispatch the reference does in ``Standardizer._standardize_unit_and_beta`` (
 to the Rust ``standardize_f32/f64``) goes to ``pstb_standardize_host`` (host arrays) or ``pstb_standardize``
 (CUDA tensors).  ``force_python_only=True`` raises: this package has no CPU path.
 """
-import ctypes
 import warnings
 
 import numpy as np

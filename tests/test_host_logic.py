@@ -306,3 +306,55 @@ def test_workspace_sizes_are_monotonic():
     assert lib.pstb_kernel_workspace_bytes(1000, 1024) < lib.pstb_kernel_workspace_bytes(5000, 1024) < lib.pstb_kernel_workspace_bytes(5000, 4096)
     assert lib.pstb_cross_kernel_workspace_bytes(1000, 300, 1024) >= lib.pstb_kernel_workspace_bytes(1300, 1024)
     assert lib.pstb_standardize_work_bytes(1000) == 38 * 1000 * 8 and lib.pstb_packed_ld(10000) == 2512 and lib.pstb_packed_ld(0) == 0
+
+
+def _gloo_pieces_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import bed_oracle
+    from pysnptools_b200 import DistributedBed
+    from pysnptools_b200.parallel import allgather_rows, allreduce_sum_, assign_pieces
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1"))
+    d._run_once()
+    sizes = [p.sid_count for p in d._pieces]
+    owned = assign_pieces(sizes, world)
+    n = d.iid_count
+    K_r, stats_r = np.zeros((n, n)), []
+    for k in owned[rank]:                                      # this rank reads only its own piece files
+        piece = d._pieces[k]
+        packed = bed_oracle.read_packed(piece.filename, n, piece.sid_count)
+        Kp, st = bed_oracle.read_kernel(packed, n, count_A1=True)
+        K_r += Kp
+        stats_r.append(st)
+    K = allreduce_sum_(torch.from_numpy(K_r))
+    counts = [int(sum(sizes[k] for k in o)) for o in owned]
+    local = torch.from_numpy(np.concatenate(stats_r)) if stats_r else torch.zeros((0, 2), dtype=torch.float64)
+    stats = allgather_rows(local, counts)
+    where = np.concatenate([np.arange(d._starts[k], d._starts[k + 1]) for o in owned for k in o])
+    ordered = np.empty((d.sid_count, 2))
+    ordered[where] = stats.numpy()
+    if rank == 0:
+        q.put((K.numpy(), ordered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_bed_pieces_sharded_over_gloo(golden):
+    """world_size 2 on CPU: DistributedBed pieces as rank shards (assign_pieces) + all-reduce == the golden K of the same data."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_pieces_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    K, stats = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(K, golden["dbx_unit_K"], rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(stats, golden["dbx_unit_stats"], rtol=1e-12)

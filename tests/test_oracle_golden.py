@@ -124,3 +124,21 @@ def test_synth_is_reproducible_by_range(oracle):
     a = oracle.synth_packed(50, 0, 20, 0.05, seed=1)
     b = oracle.synth_packed(50, 7, 13, 0.05, seed=1)
     assert np.array_equal(a[7:13], b)
+
+
+def test_cross_kernel_oracle_pinned_by_trained_goldens(golden, oracle):
+    """oracle.read_cross_kernel (the checker of pstb_snp_cross_kernel): train x test with the train statistics.  Its test-side values
+    are the reference's own UnitTrained / BetaTrained outputs (goldens), and train x train degenerates to the symmetric kernel."""
+    packed, n, m = fixture_packed("n300")
+    train, test = np.arange(10, n), np.arange(10)
+    for key, args in (("unit", {}), ("beta", dict(is_beta=True, a=1, b=25))):
+        K, st = oracle.read_cross_kernel(packed, n, packed, n, iid_index_r=train, iid_index_c=test, **args)
+        np.testing.assert_allclose(st, golden["n300_trained_{0}_stats".format(key)], rtol=1e-12)
+        xr, _ = oracle.standardize(oracle.decode(packed, n, train), **args)
+        np.testing.assert_allclose(K, xr @ golden["n300_trained_{0}_test_val".format(key)].T, rtol=1e-9, atol=1e-9)
+    Ks, _ = oracle.read_cross_kernel(packed, n, packed, n)
+    np.testing.assert_allclose(Ks, golden["n300_unit_K"], rtol=1e-10, atol=1e-8)
+    # statistics given explicitly == statistics learned from the row side
+    K2, _ = oracle.read_cross_kernel(packed, n, packed, n, iid_index_r=train, iid_index_c=test, stats=golden["n300_trained_unit_stats"])
+    K1, _ = oracle.read_cross_kernel(packed, n, packed, n, iid_index_r=train, iid_index_c=test)
+    np.testing.assert_allclose(K2, K1, rtol=1e-12, atol=1e-12)

@@ -519,7 +519,7 @@ class SnpData(SnpReader):
             pos = np.full((len(self._col), 3), np.nan)
         self._col_property = np.array(pos, dtype=np.float64).reshape(-1, 3)
         if not _is_tensor(val):
-            val = np.asarray(val) if isinstance(val, np.ndarray) else np.array(val, dtype=np.float64)
+            val = val if isinstance(val, np.ndarray) else np.array(val, dtype=np.float64)       # an np.memmap stays one (view_ok reads)
             if _require_float32_64 and val.dtype not in (np.float32, np.float64):
                 val = val.astype(np.float64)
             if val.ndim != 2:
@@ -625,4 +625,7 @@ def __getattr__(name):
     if name == "DistributedBed":
         from .distributedbed import DistributedBed
         return DistributedBed
+    if name == "SnpMemMap":
+        from .snpmemmap import SnpMemMap
+        return SnpMemMap
     raise AttributeError("module {0!r} has no attribute {1!r}".format(__name__, name))

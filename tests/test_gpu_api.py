@@ -326,6 +326,31 @@ def test_distributed_bed_pieces_as_rank_shards(golden):
     assert sum(len(o) for o in assign_pieces([p.sid_count for p in d._pieces], 3)) == len(d._pieces)
 
 
+def test_snpmemmap_staging(golden, tmp_path):
+    """SnpMemMap as host-side staging: Bed -> (fused decode + standardize per SNP block) -> mapped file; kernels streamed from a mapped file."""
+    from pysnptools_b200 import Beta, Identity, SnpKernel, SnpMemMap, Unit
+    bed = _bed("n300")
+    raw = SnpMemMap.write(str(tmp_path / "raw.snp.memmap"), bed, block_size=333)                    # Identity: the decoded matrix
+    assert isinstance(raw.val, np.memmap) and raw.val.dtype == np.float64 and raw.val.flags["F_CONTIGUOUS"]
+    assert np.array_equal(raw.val, i8_to_float(golden["n300_decode_i8"]), equal_nan=True)
+    assert np.array_equal(raw.sid, bed.sid) and np.array_equal(raw.iid, bed.iid) and np.array_equal(raw.pos, bed.pos, equal_nan=True)
+    for std, key in ((Unit(), "unit"), (Beta(1, 25), "beta_1_25")):
+        for order, dtype, tol in (("F", np.float64, 1e-9), ("C", np.float32, 2e-6)):
+            sm = SnpMemMap.write(str(tmp_path / "std.snp.memmap"), bed, standardizer=std, order=order, dtype=dtype, block_size=100)
+            want = golden["n300_{0}_val".format(key)]
+            assert sm.val.dtype == dtype and sm.val.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+            assert np.max(np.abs(sm.val[:, : want.shape[1]] - want)) <= tol * max(1.0, np.max(np.abs(want)))
+    # kernels streamed from mapped files: raw values standardized on the device block by block, or already standardized values
+    K, trained = raw._read_kernel(Unit(), block_size=300, return_trained=True)
+    assert rel_fro(K, golden["n300_unit_K"]) < 1e-5 and np.array_equal(K, K.T)
+    np.testing.assert_allclose(trained.stats, golden["n300_unit_stats"], rtol=1e-12)
+    assert rel_fro(SnpKernel(raw, Beta(1, 25), block_size=500).read().val, golden["n300_beta_1_25_K"]) < 1e-5
+    sm = SnpMemMap.write(str(tmp_path / "unit.snp.memmap"), bed, standardizer=Unit())
+    assert rel_fro(sm.read_kernel(Identity(), block_size=400).val, golden["n300_unit_K"]) < 1e-5
+    dbx = SnpMemMap.write(str(tmp_path / "dbx.snp.memmap"), _bed("dbx"))                             # missing values in the file
+    assert rel_fro(dbx.read_kernel(Unit(), block_size=30).val, golden["dbx_unit_K"]) < 1e-5
+
+
 def test_intersect_apply_with_kernel(golden):
     from pysnptools_b200 import SnpKernel, Unit
     from pysnptools_b200.util import intersect_apply

@@ -358,3 +358,64 @@ def test_distributed_bed_pieces_sharded_over_gloo(golden):
         assert p.exitcode == 0
     np.testing.assert_allclose(K, golden["dbx_unit_K"], rtol=1e-11, atol=1e-9)
     np.testing.assert_allclose(stats, golden["dbx_unit_stats"], rtol=1e-12)
+
+
+def test_snpmemmap_host_side(tmp_path):
+    """SnpMemMap without a GPU (TestSnpMemMap.test1, snpmemmap.py:204-242): empty / write-through / flush / reopen, view semantics,
+    host-side subsetting of the mapped file, pickling, writing an in-memory SnpData."""
+    from pysnptools_b200 import SnpData, SnpMemMap
+    from pysnptools_b200.standardizer import Identity
+    f = str(tmp_path / "tiny.snp.memmap")
+    m = SnpMemMap.empty(iid=[["fam0", "iid0"], ["fam0", "iid1"]], sid=["snp334", "snp349", "snp921"], filename=f, order="F", dtype=np.float64)
+    assert isinstance(m.val, np.memmap)
+    m.val[:, :] = [[0.0, 2.0, 0.0], [0.0, 1.0, 2.0]]
+    assert np.array_equal(m[[1], [1]].read(view_ok=True).val, np.array([[1.0]]))
+    m.flush()
+    assert isinstance(m.val, np.memmap) and np.array_equal(m[[1], [1]].read(view_ok=True).val, np.array([[1.0]]))
+    m.flush()
+    m3 = SnpMemMap(f)
+    assert m3.iid_count == 2 and m3.sid_count == 3 and isinstance(m3.val, np.memmap) and m3.offset > 0 and m3.filename == f
+    assert isinstance(m3.read(view_ok=True).val, np.memmap)                        # the mapping itself
+    copy = m3.read()
+    assert not isinstance(copy.val, np.memmap) and np.array_equal(copy.val, m3.val) and copy.val.flags["F_CONTIGUOUS"]
+    assert m3.read(order="C", dtype=np.float32).val.flags["C_CONTIGUOUS"]
+    assert np.array_equal(m3[::-1, [2, 0]].read().val, np.array([[2.0, 0.0], [0.0, 0.0]]))
+    with pytest.raises(Exception):
+        m3.val = np.zeros((2, 3))
+    assert repr(pickle.loads(pickle.dumps(m3))) == "SnpMemMap('{0}')".format(f)
+    sd = SnpData(iid=[["a", "b"], ["c", "d"], ["e", "f"]], sid=["s1", "s2"], val=np.array([[0.0, 1.0], [2.0, np.nan], [1.0, 1.0]]),
+                 pos=[[1, 0.5, 100], [2, 0.7, 200]])
+    w = SnpMemMap.write(str(tmp_path / "w.snp.memmap"), sd, standardizer=Identity())
+    assert np.array_equal(w.val, sd.val, equal_nan=True) and np.array_equal(w.pos, sd.pos) and np.array_equal(w.iid, sd.iid)
+    empty = SnpMemMap.empty(iid=np.empty((0, 2), dtype=str), sid=["s"], filename=str(tmp_path / "e.snp.memmap"))
+    assert empty.val.shape == (0, 1)
+
+
+def test_snpmemmap_interop_with_reference(tmp_path):
+    """Files written here open in the reference's SnpMemMap and the other way round (build container only: needs baseline/_ref)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "pysnptools")):
+        pytest.skip("baseline/_ref is not present")
+    code = r"""
+import sys, warnings
+import numpy as np
+warnings.simplefilter('ignore'); np.NAN = np.NaN = np.nan
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests/golden/_refstub'); sys.path.insert(0, {ref!r})
+from pysnptools.snpreader import SnpMemMap as RefMM, SnpData as RefSD
+from pysnptools_b200 import SnpMemMap, SnpData
+d = {tmp!r}
+ours = SnpMemMap.empty(iid=[['f', 'a'], ['f', 'b']], sid=['s1', 's2', 's3'], filename=d + '/ours.memmap', pos=[[1, 2, 3]] * 3, order='C', dtype=np.float32)
+ours.val[:, :] = [[0, 1, 2], [2, np.nan, 0]]
+ours.flush()
+r = RefMM(d + '/ours.memmap')
+assert r.val.dtype == np.float32 and np.array_equal(r.val, [[0, 1, 2], [2, np.nan, 0]], equal_nan=True) and list(r.sid) == ['s1', 's2', 's3']
+assert np.array_equal(r.pos, [[1, 2, 3]] * 3) and r.val.flags['C_CONTIGUOUS']
+rd = RefSD(iid=[['a', 'b'], ['c', 'd'], ['e', 'f']], sid=['x', 'y'], val=np.asfortranarray([[0., 1.], [2., np.nan], [1., 1.]]), pos=[[1, .5, 100], [2, .7, 200]])
+RefMM.write(d + '/ref.memmap', rd)
+o = SnpMemMap(d + '/ref.memmap')
+assert np.array_equal(o.val, rd.val, equal_nan=True) and np.array_equal(o.iid, rd.iid) and np.array_equal(o.pos, rd.pos) and o.val.flags['F_CONTIGUOUS']
+print('interop ok')
+""".format(root=ROOT, ref=ref_dir, tmp=str(tmp_path))
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "interop ok" in out.stdout, out.stderr[-2000:]

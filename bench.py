@@ -496,16 +496,15 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
 
     marks = []
 
-    low_term = dev.syrk_low_term_for(m, n)                       # SNP shards: the low-term mode follows the whole kernel's SNP count
-    low_term.__enter__()
+    low_term = dev.low_term_for(m, n)                             # SNP shards: the low-term mode follows the whole kernel's SNP count
 
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         if compact:
-            dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False)
+            dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
         else:
-            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1))
+            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1), low_term=low_term)
         ev[1].record()
         if compact:
             dist.all_reduce(tiles)                                                   # sum of the partial triangles over NVLink
@@ -542,15 +541,14 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                                if compact else ("square matrix" if world > 1 else "none"))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
     diag = float(K.diagonal().double().mean().item())
-    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks) if args.e2e else None
+    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks, low_term) if args.e2e else None
     cpu_baseline = None
     if rank == 0 and world == 1 and args.kernel_cpu:
         del K
         torch.cuda.empty_cache()
         cpu_baseline = cpu_kernel_baseline(_oracle_lib(), n, args.ref_kernel_sid, os.cpu_count() or 1)
         K = torch.zeros((1, 1), device="cuda")
-    fp8lo = dev.get_syrk_low_term() == "fp8" or (dev.get_syrk_low_term() == "auto" and m >= n and m >= 256)
-    low_term.__exit__()
+    fp8lo = low_term == "fp8"
     t256 = (n + 255) // 256
     tiles = t256 * (t256 + 1) // 2                                                 # lower-triangular 256 x 256 tiles per rank
     # synthetic cfg3 has no missing genotypes: every chunk takes the 2-term exact-dosage GEMM (3 terms with PSTB_SYRK_3TERM=1)
@@ -570,7 +568,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
             "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
 
 
-def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local, chunk, rank, world, barrier, max_over_ranks):
+def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local, chunk, rank, world, barrier, max_over_ranks, low_term="default"):
     """cfg3 end to end from HOST buffers: pinned packed bytes -> K in pinned host memory, copies inside the timed region.
     One GPU: ONE call of pstb_snp_kernel_host (the C ABI a bed_reader-style binding would use).  N GPUs: every rank uploads its
     SNP shard, computes its partial K, NCCL all-reduce, rank 0 copies the float32 K to the host."""
@@ -592,7 +590,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
     if world == 1:
         def step():
             _lib.check(lib.pstb_snp_kernel_host(h_pk, n, m_local, None, n, None, m_local, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
-                                                h_stats.ctypes.data, h_K, _lib.F32, chunk))
+                                                h_stats.ctypes.data, h_K, _lib.F32, chunk, dev._LOW_TERM[low_term]))
         api = "pstb_snp_kernel_host (host-buffer C ABI): pinned packed bytes in, pinned float32 K out"
     else:
         t_pk = torch.from_numpy(h_packed)
@@ -603,11 +601,11 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
             d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
             store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
             if tiles is not None:
-                dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False)
+                dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
                 dist.all_reduce(tiles)
                 dev.kernel_from_tiles(tiles, n, K=K)
             else:
-                dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False)
+                dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False, low_term=low_term)
                 dist.all_reduce(K)
                 _lib.check(lib.pstb_mirror_lower(K.data_ptr(), n, n, stream))
             if rank == 0:

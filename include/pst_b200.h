@@ -104,23 +104,29 @@ int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_
  * pstb_snp_kernel: K (float32, [n_iid, n_iid], ld = n_iid, both triangles filled) =
  *   sum over the selected SNPs of x_j x_j^T, where x_j is the standardized column of SNP j.
  *   accumulate != 0 adds to the existing lower triangle of d_K before mirroring (multi-call
- *   streaming).  d_stats [n_sid][2] float64 is written (or read when use_stats).  The operands are
- *   split fp16 hi/lo (3 MMA terms, fp32 accumulation in tensor memory): relative Frobenius error
- *   vs float64 ~3e-7. */
+ *   streaming).  d_stats [n_sid][2] float64 is written (or read when use_stats).  Missing genotypes
+ *   contribute 0 (mean imputation, standardizer.py:145-163).  Exact-dosage 2-term tensor-core path
+ *   (see `low_term` below), fp32 accumulation in tensor memory: relative Frobenius error vs float64
+ *   ~1e-6 (fp16 low term) / (2..5)e-6 (fp8 low term). */
 int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk);
-/* Precision / speed of the exact-dosage path (chunks without missing genotypes): K = h (w h)^T with (w h) = hi + lo in fp16.
- * The low term h lo^T only has to carry 4-5 bits, so it can run on the fp8 pipe (e4m3 x e4m3, half the tensor cycles):
- * relative Frobenius error (3..6)e-6 instead of ~1e-6 (north_star gate: 1e-5), ~23 % faster on cfg3.
- * PSTB_LOW_TERM_AUTO (default; environment PSTB_SYRK_FP8LO=0/1 overrides it): fp8 when a call multiplies at least as many SNPs
- * as individuals and at least 256 (the error estimate is statistical).  A caller that shards the SNPs of one kernel over several calls / GPUs knows the global SNP count and may
- * choose.  Process-wide; returns the previous mode. */
-enum { PSTB_LOW_TERM_FP16 = 0, PSTB_LOW_TERM_FP8 = 1, PSTB_LOW_TERM_AUTO = 2 };
+/* Precision / speed of the exact-dosage path: K = L B^T with L = g - mu' exact in fp16 (missing -> fp16(mu - mu'), so that mean
+ * imputation is exact whatever the missing pattern) and B = w m (g - mu) = hi + lo in fp16.  The low term L lo^T only has to
+ * carry 4-5 bits, so it can run on the fp8 pipe (e4m3 x e4m3, half the tensor cycles): relative Frobenius error (2..5)e-6
+ * instead of ~1e-6 (north_star gate: 1e-5), ~23 % faster on cfg3.  Every kernel entry point takes the mode PER CALL
+ * (`low_term`), so concurrent callers cannot race on it:
+ *   PSTB_LOW_TERM_FP16 / PSTB_LOW_TERM_FP8: as named;
+ *   PSTB_LOW_TERM_AUTO: fp8 when the call multiplies at least as many SNPs as individuals (4 x as many for Beta, whose weights
+ *     concentrate on the rare SNPs) and at least 256 -- the error estimate is statistical.  A caller that shards the SNPs of
+ *     one kernel over several calls / GPUs knows the global SNP count and passes FP8 / FP16 explicitly;
+ *   PSTB_LOW_TERM_DEFAULT: the process-wide default, initially AUTO (environment PSTB_SYRK_FP8LO=0/1 overrides it), which
+ *     pstb_set_syrk_low_term changes (returns the previous default; an invalid mode only reports). */
+enum { PSTB_LOW_TERM_DEFAULT = -1, PSTB_LOW_TERM_FP16 = 0, PSTB_LOW_TERM_FP8 = 1, PSTB_LOW_TERM_AUTO = 2 };
 int pstb_set_syrk_low_term(int mode);
 int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
                     pstb_axis iid, pstb_axis sid, int count_a1,
                     int mode, double a, double b, int use_stats, double* d_stats,
                     float* d_K, int accumulate, int mirror,
-                    void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+                    void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream);
 /* K-tile sharding for kernels that do not fit one GPU (BASELINE cfg5: 500 000 iids -> K = 1 TB): the lower triangle is cut
  * into 256 x 256 tiles, rank r of `world` owns every world-th tile of a fixed rasterisation and computes them for ALL
  * selected SNPs from its own copy of the packed store -- no reduction, no collective.
@@ -134,7 +140,7 @@ int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count
                           pstb_axis iid, pstb_axis sid, int count_a1,
                           int mode, double a, double b, int use_stats, double* d_stats,
                           float* d_tiles, int rank, int world, int accumulate,
-                          void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+                          void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream);
 /* Expand compact tiles (the layout above, tiles of `rank` of `world`) into the full symmetric K [n_iid, n_iid] (both triangles;
  * entries of other ranks' tiles are left untouched).  The SNP-sharded multi-GPU path accumulates into compact tiles
  * (rank 0 of world 1 = the whole lower triangle), all-reduces them -- half the bytes of the square matrix -- and expands. */
@@ -145,14 +151,15 @@ int pstb_kernel_from_tiles(const float* d_tiles, int64_t n_iid, int rank, int wo
  * x = the `_r` (row / train) selection, y = the `_c` (column / test) selection, possibly of two different stores; both sides
  * select the same number of SNPs (position j of sid_r pairs with position j of sid_c).  Both are standardized with ONE set of
  * per-SNP statistics: use_stats == 0 computes them from the ROW side and writes d_stats [n_sid][2]; use_stats != 0 reads them.
- * Missing genotypes contribute 0 (mean imputation).  Same fp16 hi/lo tensor-core path as pstb_snp_kernel (3 MMA terms). */
+ * Missing genotypes contribute 0 (mean imputation).  Same exact-dosage tensor-core path as pstb_snp_kernel (the row side is the
+ * exact left operand, the column side the weighted right operand). */
 int64_t pstb_cross_kernel_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t chunk);
 int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, int64_t iid_count_r, int64_t sid_count_r,
                           pstb_axis iid_r, pstb_axis sid_r, int count_a1_r,
                           const uint8_t* d_packed_c, int64_t ld_c, int64_t iid_count_c, int64_t sid_count_c,
                           pstb_axis iid_c, pstb_axis sid_c, int count_a1_c,
                           int mode, double a, double b, int use_stats, double* d_stats,
-                          float* d_out, int accumulate, void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+                          float* d_out, int accumulate, void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream);
 /* K = V V^T for a float matrix V [n_iid, n_sid] already in HBM (float32 / float64, C or F order): replaces the
  * val.dot(val.T) of SnpData._read_kernel (snpdata.py:203-206).  Same fp16 hi/lo tensor-core path and workspace. */
 int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
@@ -181,7 +188,7 @@ int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count
 int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count,
                          const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
                          int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
-                         void* h_K, int dtype, int64_t chunk);
+                         void* h_K, int dtype, int64_t chunk, int low_term);
 /* standardize_f32/f64 equivalent on a host array (H2D, K2f, D2H). */
 int pstb_standardize_host(void* h_val, int dtype, int order, int64_t n_iid, int64_t n_sid,
                           int mode, double a, double b, int apply_in_place, int use_stats, double* h_stats);

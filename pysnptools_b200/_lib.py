@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PSTB_LIB_PATH") or os.path.join(_HERE, "libpst_b200.s
 F32, F64, I8 = 0, 1, 2
 ORDER_F, ORDER_C = 0, 1
 STD_NONE, STD_UNIT, STD_BETA = 0, 1, 2
+LOW_TERM_DEFAULT, LOW_TERM_FP16, LOW_TERM_FP8, LOW_TERM_AUTO = -1, 0, 1, 2
 
 
 class Axis(Structure):
@@ -49,17 +50,17 @@ def _load():
         "pstb_pack": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
         "pstb_kernel_workspace_bytes": (c_int64, [c_int64, c_int64]),
         "pstb_snp_kernel": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
-                                    c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+                                    c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
         "pstb_kernel_tile_count": (c_int64, [c_int64, c_int, c_int]),
         "pstb_kernel_tile_coords": (c_int, [c_int64, c_int, c_int, c_void_p]),
         "pstb_snp_kernel_tiles": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
-                                          c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+                                          c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
         "pstb_set_syrk_low_term": (c_int, [c_int]),
         "pstb_kernel_from_tiles": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
         "pstb_cross_kernel_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
         "pstb_snp_cross_kernel": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int,
                                           c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int,
-                                          c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+                                          c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
         "pstb_float_kernel": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
         "pstb_syrk_planes": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p]),
         "pstb_mirror_lower": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
@@ -67,7 +68,7 @@ def _load():
         "pstb_read_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double,
                                    c_double, c_int, c_void_p, c_void_p, c_int, c_int]),
         "pstb_snp_kernel_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double,
-                                         c_double, c_int, c_void_p, c_void_p, c_int, c_int64]),
+                                         c_double, c_int, c_void_p, c_void_p, c_int, c_int64, c_int]),
         "pstb_standardize_host": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_double, c_double, c_int, c_int, c_void_p]),
         "pstb_subset_host": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int, c_int]),

@@ -138,7 +138,18 @@ class open_bed(object):
         return val
 
 
+def _require_writeable(a):
+    """The C ABI writes through raw pointers: refuse read-only arrays (a memory map opened with mode='r' would take the process
+    down; the Rust extension raises for non-writeable arrays as well)."""
+    if not a.flags.writeable:
+        raise ValueError("assignment destination is read-only")
+
+
 def _standardize(snps, is_beta, a, b, apply_in_place, use_stats, stats, num_threads, code):
+    if apply_in_place:
+        _require_writeable(snps)
+    if not use_stats:
+        _require_writeable(stats)
     n_iid, n_sid = snps.shape
     st64 = np.array(stats, dtype=np.float64, order="C") if use_stats else np.empty((n_sid, 2), dtype=np.float64)
     order = _lib.ORDER_C if snps.flags["C_CONTIGUOUS"] else _lib.ORDER_F
@@ -161,6 +172,7 @@ def standardize_f32(snps, is_beta, a, b, apply_in_place, use_stats, stats, num_t
 def _subset(val, rows, cols, out, num_threads, ci, co):
     rows = np.ascontiguousarray(rows, dtype=np.int64)
     cols = np.ascontiguousarray(cols, dtype=np.int64)
+    _require_writeable(out)
     if out.size:
         _lib.require_gpu()
         _lib.check(_lib.lib.pstb_subset_host(val.ctypes.data, ci, _lib.ORDER_C if val.flags["C_CONTIGUOUS"] else _lib.ORDER_F, val.shape[0],

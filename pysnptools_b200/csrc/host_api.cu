@@ -420,7 +420,7 @@ extern "C" int pstb_subset_host(const void* h_in, int dtype_in, int order_in, in
 // device and only the finished matrix travels back, converted to the requested dtype band by band.
 extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
                                     int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
-                                    int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk) {
+                                    int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk, int low_term) {
     if (iid_count < 0 || sid_count < 0) return fail("negative iid_count / sid_count");
     if (!h_iid_idx) n_iid = iid_count;
     if (!h_sid_idx) n_sid = sid_count;
@@ -517,7 +517,7 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
         }
         pstb_axis sid_ax{nullptr, 0, 1, ns};
         rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
-                              (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp,
+                              (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, low_term, comp,
                               (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
         if (rc) break;
         if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }

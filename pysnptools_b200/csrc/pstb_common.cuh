@@ -117,7 +117,7 @@ int convert_range(const float* d_K, long long total, void* d_out, int dtype, dou
 // total_sid = SNPs of the whole kernel (the low-term mode "auto" decides on it)
 int snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
                      int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
-                     void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase, int64_t total_sid);
+                     void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream, int phase, int64_t total_sid);
 
 }  // namespace pstb
 

@@ -71,3 +71,35 @@ extern "C" int pstb_host_free(void* p) {
     if (e != cudaSuccess) return pstb::fail("cudaFreeHost -> %s", cudaGetErrorString(e));
     return 0;
 }
+
+// Occupancy probe for kernel experiments (not part of the reference-facing ABI): how many clusters of `cluster_size` CTAs with
+// `threads` threads and `smem_bytes` of dynamic shared memory can be co-resident on the current device.
+namespace pstb {
+__global__ void k_cluster_probe(int* out) {
+    extern __shared__ uint8_t probe_smem[];
+    if (out && threadIdx.x == 0 && blockIdx.x == 0x7fffffff) *out = (int)probe_smem[0];
+}
+}  // namespace pstb
+
+extern "C" int pstb_debug_max_active_clusters(int cluster_size, int threads, int smem_bytes) {
+    if (cluster_size < 1 || threads < 1 || smem_bytes < 0) return -1;
+    if (cudaFuncSetAttribute(pstb::k_cluster_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -2;
+    if (cluster_size > 8 && cudaFuncSetAttribute(pstb::k_cluster_probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -3;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cluster_size * 64), 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, pstb::k_cluster_probe, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return -4;
+    }
+    return n;
+}

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <atomic>
 #include <cuda_fp8.h>
@@ -49,16 +50,26 @@ constexpr int GROUP_I = 16, GROUP_J = 8;                  // tile rasterisation:
 // scalars block in the workspace
 struct Scalars {
     unsigned int absmax_bits;    // float bits of max |x| over the chunk (atomicMax on positive floats): 3-term split of x
-    unsigned int absmax_w_bits;  // float bits of max |w * h| over the chunk: exact-dosage path
-    unsigned int any_missing;    // != 0: some selected genotype of the chunk is missing (or the statistics were given): 3-term path
+    unsigned int absmax_w_bits;  // float bits of max |w (g - mean)| over the chunk: exact-dosage path
+    unsigned int need_3term;     // != 0: the chunk cannot take the exact-dosage path (a trained mean outside [0, 2], or forced): 3-term split
     unsigned int pad[61];
 };
 
-// Exact-dosage path (chunks without missing data): x = (g - mu) * f with f = 1/sd (Unit) or BetaPDF (Beta).  Round mu to 10
-// fractional bits, mu' = mu + delta: h = g - mu' is EXACT in fp16 (|h| <= 2, 10 fractional bits) and centred, so
-//   K = sum_j w_j h_i h_k  +  (u_i + u_k)  +  c,   w = f^2,  u_i = sum_j w_j delta_j h_ij,  c = sum_j w_j delta_j^2.
-// The GEMM is h * (w h)^T with only the right operand split hi + lo: 2 MMAs per k-step instead of 3, no dropped term; the
-// rank-one part is accumulated in fp64 by k_planes and added once per call by k_apply_rank1.
+// Exact-dosage path.  x = m (g - mu) f with m = 1 for an observed genotype, 0 for a missing one (mean imputation,
+// standardizer.py:145-163), f = 1/sd (Unit) or BetaPDF (Beta), w = f^2:   K_ik = sum_j T_ij w_j T_kj,  T = m (g - mu).
+// Round mu to 10 fractional bits, mu' = mu + delta.  The LEFT plane holds
+//     L_ij = g_ij - mu'_j      (observed)   -- exact in fp16: |L| <= 2 with 10 fractional bits
+//          = fp16(-delta_j)    (missing)    -- |delta| <= 2^-11, so fp16 carries it to 2^-22
+// so that T_ij = L_ij + delta_j for EVERY entry (missing ones to 2^-22), whatever the missing pattern.  The RIGHT plane holds
+// the exact weighted value B_kj = w_j T_kj (0 for a missing genotype), split hi + lo.  Then
+//     K_ik = sum_j L_ij B_kj  +  v_k,      v_k = sum_j delta_j B_kj   (rank one, accumulated in fp64 by k_planes)
+// : 2 MMAs per k-step instead of 3, no dropped term, for data WITH missing genotypes and for trained statistics as well (the
+// round-1 kernel fell back to the 3-term split whenever a chunk had one missing code).  Because L is centred the products have
+// the magnitude of K itself, so the truncating accumulator is as harmless as in the 3-term path.
+// Low term on the fp8 pipe: e4m3 carries 4 significant bits, so with mu'' = mu' rounded to a multiple of 1/8 the left factor
+// g - mu'' is EXACT in e4m3 as well; L = (g - mu'') + d, d = mu'' - mu' (|d| <= 1/16), and the d part is rank one again:
+//     sum_j L_ij lo_kj = sum_j (g_ij - mu''_j) lo8_kj + sum_j d_j lo8_kj       (only lo is rounded: sqrt(2) less error than
+// rounding both factors; CPU emulation scripts/emulate_masked_split.py).
 __device__ __forceinline__ double round_mu(double mean) { return rint(mean * 1024.0) * (1.0 / 1024.0); }
 __device__ __forceinline__ double weight_of(int mode, double mean, double sd, double a, double b, double lnB) {
     if (!(sd == sd) || isinf(sd) || !(mean == mean)) return 0.0;
@@ -85,9 +96,11 @@ __global__ void k_absmax(const double* stats, long long ns, int mode, double a, 
             double v = fabs(std_value(mode, (double)g, mean, sd, f));
             if (v == v && v < 1e300) m = fmaxf(m, __double2float_ru(v));
         }
-        const double w = weight_of(mode, mean, sd, a, b, lnB), mu = round_mu(mean);
-        const double hv = w * fmax(fabs(mu), fabs(2.0 - mu));
+        const double w = weight_of(mode, mean, sd, a, b, lnB);
+        const double hv = w * fmax(fabs(mean), fabs(2.0 - mean)) * (1.0 + 1e-6);
         if (hv == hv && hv < 1e300) mw = fmaxf(mw, __double2float_ru(hv));
+        // a (trained) mean outside [0, 2]: g - mu' would need more than 11 significant bits
+        if (w > 0.0 && !(mean >= 0.0 && mean <= 2.0)) sc->need_3term = 1u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -111,10 +124,10 @@ struct PlaneParams {
     const Scalars* sc;
     __half* hi;             // plane 0: x_hi   (exact-dosage path: h)
     __half* lo;             // plane 1: x_lo   (exact-dosage path: (w h)_hi)
-    __half* p2;             // plane 2: unused (exact-dosage path: (w h)_lo; with fp8lo: two byte planes, (w h)_lo then h, e4m3)
+    __half* p2;             // plane 2: unused (exact-dosage path: B_lo; with fp8lo: two byte planes, B_lo then g - mu'', e4m3)
+    long long p2_row0, p2_rows;   // rows of plane 2 before this operand / in total (0: this operand alone, n_pad rows)
     int fp8lo;              // exact-dosage path with the low term on the fp8 pipe (see k_syrk2)
-    double* u;              // [n_pad] rank-one vector of the exact-dosage path, accumulated over chunks
-    double* csum;           // scalar c of the exact-dosage path
+    double* u;              // [n_pad] rank-one vector v of the exact-dosage path, accumulated over chunks (NULL: not wanted)
     long long n_pad, k_pad;
     int dense;
     long long byte_off;
@@ -155,14 +168,16 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         }
         codes[s][q] = (unsigned char)byte;
     }
-    const bool fast = p.sc->any_missing == 0u;
+    const bool fast = p.sc->need_3term == 0u;
     __shared__ __half lut_p2[PT_S][4];
-    __shared__ __align__(4) unsigned char lut_l8[PT_S][4], lut_h8[PT_S][4];   // fp8 (e4m3) low term and dosage
+    __shared__ __align__(4) unsigned char lut_l8[PT_S][4], lut_h8[PT_S][4];   // fp8 (e4m3) low term and left factor
     __shared__ float lut_u[PT_S][4];
     if (threadIdx.x < PT_S) {
         const int s = threadIdx.x;
-        double v[4] = {0.0, 0.0, 0.0, 0.0};                     // by 2-bit code (code 1 = missing stays 0)
-        double hv[4] = {0.0, 0.0, 0.0, 0.0}, wd = 0.0;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};                     // right operand by 2-bit code (code 1 = missing stays 0)
+        double hv[4] = {0.0, 0.0, 0.0, 0.0};                    // exact-dosage path: left operand L
+        double h8v[4] = {0.0, 0.0, 0.0, 0.0};                   // ... and its e4m3-exact twin g - mu''
+        double delta = 0.0, d8 = 0.0, inv_scale = 0.0;
         if (b0 + s < p.sid.n) {
             const double mean = p.stats[2 * (b0 + s)], sd = p.stats[2 * (b0 + s) + 1];
             if (!fast) {
@@ -174,15 +189,21 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
                 v[2] = v1;
                 v[3] = p.count_a1 ? v0 : v2;
             } else {
-                const double w = weight_of(p.mode, mean, sd, p.a, p.b, p.lnB), mu = round_mu(mean);
-                const double scale = ldexp(1.0, scale_exponent(p.sc->absmax_w_bits));
-                const double h0 = 0.0 - mu, h1 = 1.0 - mu, h2 = 2.0 - mu;
-                hv[0] = p.count_a1 ? h2 : h0;
-                hv[2] = h1;
-                hv[3] = p.count_a1 ? h0 : h2;
-                v[0] = w * hv[0] * scale; v[2] = w * hv[2] * scale; v[3] = w * hv[3] * scale;
-                wd = (w > 0.0) ? w * (mu - mean) : 0.0;
-                if (ti == 0 && w > 0.0) atomicAdd(p.csum, w * (mu - mean) * (mu - mean));
+                const double w = weight_of(p.mode, mean, sd, p.a, p.b, p.lnB);
+                if (w > 0.0 && w < 1e300) {                     // SNC / all-missing / NaN statistics: the SNP contributes nothing
+                    const double mu = round_mu(mean), mu8 = rint(mu * 8.0) * 0.125;
+                    const int se = scale_exponent(p.sc->absmax_w_bits);
+                    const double scale = ldexp(1.0, se);
+                    inv_scale = ldexp(1.0, -se);
+                    delta = mu - mean;
+                    d8 = mu8 - mu;
+                    const double g0 = p.count_a1 ? 2.0 : 0.0, g3 = p.count_a1 ? 0.0 : 2.0;
+                    hv[0] = g0 - mu;  hv[2] = 1.0 - mu;  hv[3] = g3 - mu;
+                    hv[1] = (double)__half2float(__float2half_rn((float)(-delta)));          // missing: T = L + delta = 0 to 2^-22
+                    h8v[0] = g0 - mu8; h8v[2] = 1.0 - mu8; h8v[3] = g3 - mu8;
+                    h8v[1] = -d8;                                                             // missing: (g - mu'') + d ~ 0
+                    v[0] = w * (g0 - mean) * scale; v[2] = w * (1.0 - mean) * scale; v[3] = w * (g3 - mean) * scale;
+                }
             }
         }
 #pragma unroll
@@ -190,7 +211,8 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
             double x = v[c];
             if (!(x == x) || fabs(x) > 60000.0) x = 0.0;        // NaN statistics (all-missing SNP) contribute nothing
             const __half h = __float2half_rn((float)x);
-            const __half l = __float2half_rn((float)(x - (double)__half2float(h)));
+            const double res = x - (double)__half2float(h);
+            const __half l = __float2half_rn((float)res);
             if (!fast) {
                 lut_hi[s][c] = h;
                 lut_lo[s][c] = l;
@@ -198,13 +220,17 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
                 lut_l8[s][c] = lut_h8[s][c] = 0;
                 lut_u[s][c] = 0.0f;
             } else {
-                lut_hi[s][c] = __float2half_rn((float)hv[c]);   // exact: |h| <= 2 with 10 fractional bits
+                lut_hi[s][c] = __float2half_rn((float)hv[c]);   // exact: |L| <= 2 with 10 fractional bits
                 lut_lo[s][c] = h;
                 lut_p2[s][c] = l;
-                // low term for the fp8 pipe: the residual x - hi itself (|.| <= half an ulp of hi <= 8) and h, both e4m3
-                lut_l8[s][c] = (unsigned char)__nv_cvt_float_to_fp8((float)(x - (double)__half2float(h)), __NV_SATFINITE, __NV_E4M3);
-                lut_h8[s][c] = (unsigned char)__nv_cvt_float_to_fp8((float)hv[c], __NV_SATFINITE, __NV_E4M3);
-                lut_u[s][c] = (float)(wd * hv[c]);
+                // low term for the fp8 pipe: the residual x - hi itself (|.| <= half an ulp of hi <= 8) and g - mu'', both e4m3
+                const __nv_fp8_storage_t l8 = __nv_cvt_float_to_fp8((float)res, __NV_SATFINITE, __NV_E4M3);
+                lut_l8[s][c] = (unsigned char)l8;
+                lut_h8[s][c] = (unsigned char)__nv_cvt_float_to_fp8((float)h8v[c], __NV_SATFINITE, __NV_E4M3);
+                // rank-one part v_k: delta * B (+ d * lo8 when the low term uses g - mu'' instead of g - mu')
+                double uu = delta * x * inv_scale;
+                if (p.fp8lo) uu += d8 * (double)__half2float(__half(__nv_cvt_fp8_to_halfraw(l8, __NV_E4M3))) * inv_scale;
+                lut_u[s][c] = (float)uu;
             }
         }
     }
@@ -236,19 +262,21 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         *reinterpret_cast<__half2*>(p.hi + off) = sel(h01, ca, cb);
         *reinterpret_cast<__half2*>(p.lo + off) = sel(l01, ca, cb);
         if (fast) {
+            // plane 2 may be shared with a second operand stacked above / below this one (train x test): its own row offset
+            const long long offp = (p.p2_row0 + i0 + r) * p.k_pad + b0 + 2 * lane;
             if (p.fp8lo) {
                 unsigned char* l8 = reinterpret_cast<unsigned char*>(p.p2);
-                unsigned char* h8 = l8 + p.n_pad * p.k_pad;
-                *reinterpret_cast<uint16_t*>(l8 + off) = (uint16_t)(((l8a >> (8 * ca)) & 0xffu) | (((l8b >> (8 * cb)) & 0xffu) << 8));
-                *reinterpret_cast<uint16_t*>(h8 + off) = (uint16_t)(((h8a >> (8 * ca)) & 0xffu) | (((h8b >> (8 * cb)) & 0xffu) << 8));
+                unsigned char* h8 = l8 + (p.p2_rows ? p.p2_rows : p.n_pad) * p.k_pad;
+                *reinterpret_cast<uint16_t*>(l8 + offp) = (uint16_t)(((l8a >> (8 * ca)) & 0xffu) | (((l8b >> (8 * cb)) & 0xffu) << 8));
+                *reinterpret_cast<uint16_t*>(h8 + offp) = (uint16_t)(((h8a >> (8 * ca)) & 0xffu) | (((h8b >> (8 * cb)) & 0xffu) << 8));
             } else {
-                *reinterpret_cast<__half2*>(p.p2 + off) = sel(q01, ca, cb);
+                *reinterpret_cast<__half2*>(p.p2 + offp) = sel(q01, ca, cb);
             }
             float uv = ((ca & 2u) ? ((ca & 1u) ? ua[3] : ua[2]) : ((ca & 1u) ? ua[1] : ua[0])) +
                        ((cb & 2u) ? ((cb & 1u) ? ub[3] : ub[2]) : ((cb & 1u) ? ub[1] : ub[0]));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) uv += __shfl_xor_sync(0xffffffffu, uv, o);
-            if (lane == 0 && uv != 0.0f && i0 + r < n_out) atomicAdd(p.u + i0 + r, (double)uv);
+            if (lane == 0 && uv != 0.0f && i0 + r < n_out && p.u) atomicAdd(p.u + i0 + r, (double)uv);
         }
     }
 }
@@ -315,6 +343,9 @@ struct SyrkParams {
     // n_cols columns.  Symmetric product: row0 = 0, n_cols = n.
     long long row0, n_cols;
     int fp8lo;              // 2-term path with the low term on the fp8 pipe: map_p2 / map_h8 are byte (e4m3) planes
+    int tma_out;            // K leaves through 32 x 32 staging tiles and TMA bulk tensor stores / reduce-adds (map_out)
+    int red_add;            // accumulate with red.global.add.v4.f32 (no read round trip in the epilogue) instead of load + add + store
+    int dbg;                // timing experiments only (PSTB_SYRK_DBG): bit 1 = no K write at all, bit 2 = no operand loads
 };
 
 __global__ void __launch_bounds__(SYRK_THREADS, 1)
@@ -484,7 +515,8 @@ constexpr int TM = 256, TN = 256;                          // tile of the pair
 constexpr int STAGES2 = 3;
 constexpr int T_BYTES = 128 * BK * 2;                      // 16 KiB: one 128-row fp16 plane tile
 constexpr int STAGE2_BYTES = 4 * T_BYTES;                  // A hi, A lo, B-half hi, B-half lo
-constexpr int SYRK2_SMEM = STAGES2 * STAGE2_BYTES + 1024;
+constexpr int OUT_STAGE_BYTES = 32 * 32 * 4;                // one 32 x 32 fp32 block per epilogue warp, staged for the TMA store of K
+constexpr int SYRK2_SMEM = STAGES2 * STAGE2_BYTES + 8 * OUT_STAGE_BYTES + 1024;
 constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr int GROUP2 = 8;                                  // 8 x 8 tiles = 2048 x 2048 super-blocks
 
@@ -544,7 +576,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
 k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_p2,
-        const __grid_constant__ CUtensorMap map_h8, const SyrkParams p) {
+        const __grid_constant__ CUtensorMap map_h8, const __grid_constant__ CUtensorMap map_out, const SyrkParams p) {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[STAGES2 + 1], bar_empty[STAGES2 + 1], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -560,9 +592,10 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         prefetch_tmap(&map_lo);
         prefetch_tmap(&map_p2);
         prefetch_tmap(&map_h8);
+        if (p.tma_out) prefetch_tmap(&map_out);
     }
     // exact-dosage chunk (no missing data): A = h (plane 0), B = (w h)_hi, (w h)_lo (planes 1, 2): two MMAs per k-step
-    const bool fast = p.sc != nullptr && p.sc->any_missing == 0u;
+    const bool fast = p.sc != nullptr && p.sc->need_3term == 0u;
     // fp8lo: the low term h * (w h)_lo runs on the fp8 pipe (e4m3 x e4m3, K = 32 per instruction: half the tensor cycles of the
     // fp16 low term).  It only has to carry 4-5 bits: (w h)_lo is <= 2^-11 of (w h)_hi.  map_p2 / map_h8 are byte planes then.
     const bool fp8lo = fast && p.fp8lo != 0;
@@ -597,6 +630,11 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
                     const uint32_t sb = tiles_base + stage * stage_bytes;
                     const uint32_t full = smem_u32(&bar_full[stage]) & 0xFEFFFFFFu;   // the leader CTA's barrier
                     const int kc = kb * BK;
+                    if (p.dbg & 4) {                                              // timing experiment: MMAs on whatever is in smem
+                        if (leader) mbar_arrive(&bar_full[stage]);
+                        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     if (fast) {
                         if (leader) mbar_expect_tx(&bar_full[stage], 2u * 3u * T_BYTES);
                         tma_load_2d_2sm(sb, &map_hi, kc, row_a, full);
@@ -712,13 +750,63 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
             float* kbase = p.compact ? p.K + (long long)t * (TM * TN) + (long long)(rank * 128 + quad * 32 + lane) * TN + half * 128
                                      : p.K + row * p.ldk + col0;
             const bool vec_t = p.compact || vec;
+            if (p.tma_out) {
+                // K (+)= block through shared memory and the TMA: the warp's 32 x 32 block (lane = row) is written to a 128-byte-swizzled
+                // staging tile (conflict-free 128-bit stores) and leaves as ONE bulk tensor store -- or reduce-add, performed at L2 --
+                // instead of 256 scattered 16-byte accesses per warp (REDG costs ~1.3 cycles per lane: ~10 k cycles per tile, during
+                // which the MMA thread ran out of accumulators).  Rows / columns beyond the matrix are clipped by the tensor map.
+                const uint32_t stage_out = tiles_base + STAGES2 * STAGE2_BYTES + (uint32_t)(warp - 2) * OUT_STAGE_BYTES;
+                const int out_row = p.compact ? t * TM + (int)rank * 128 + quad * 32
+                                              : (int)((long long)tile.x * TM + rank * 128 + quad * 32 - p.row0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long cc = col0 + c * 32;
+                    if ((!p.compact && cc > row_hi) || cc >= p.n_cols || (p.dbg & 2)) continue;       // warp-uniform
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous block has left the staging tile
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t dst = stage_out + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(sum[c * 32 + 4 * q] * scale),
+                                     "f"(sum[c * 32 + 4 * q + 1] * scale), "f"(sum[c * 32 + 4 * q + 2] * scale), "f"(sum[c * 32 + 4 * q + 3] * scale)
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int oc = p.compact ? half * 128 + c * 32 : (int)cc;
+                        if (p.accumulate)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_out),
+                                         "r"(stage_out), "r"(oc), "r"(out_row)
+                                         : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_out),
+                                         "r"(stage_out), "r"(oc), "r"(out_row)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const long long cc = col0 + c * 32;
                 if ((!p.compact && cc > row_hi) || cc >= p.n_cols) continue;
                 if (row < p.n) {
                     float* dst = kbase + c * 32;
+                    if (p.dbg & 2) continue;                                       // timing experiment: no K traffic
                     if (vec_t && cc + 32 <= p.n_cols) {
+                        if (p.accumulate && p.red_add) {
+                            // K += sum as a fire-and-forget vector reduction performed at L2: the epilogue warps do not wait for
+                            // a DRAM round trip per 32 columns, so the MMA thread gets its accumulator back sooner
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(sum[c * 32 + 4 * q] * scale),
+                                             "f"(sum[c * 32 + 4 * q + 1] * scale), "f"(sum[c * 32 + 4 * q + 2] * scale),
+                                             "f"(sum[c * 32 + 4 * q + 3] * scale)
+                                             : "memory");
+                            continue;
+                        }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             float4 o = make_float4(sum[c * 32 + 4 * q] * scale, sum[c * 32 + 4 * q + 1] * scale,
@@ -741,6 +829,7 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
             }
         }
     }
+    if (p.tma_out && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     cluster_sync_all();
     if (warp == 2) {
@@ -749,32 +838,36 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     }
 }
 
-void build_tiles2(long long n, std::vector<int2>& out) {
+void build_tiles2(long long n, std::vector<int2>& out, int group = GROUP2) {
     out.clear();
     const int t = (int)((n + TM - 1) / TM);
-    for (int gi = 0; gi < t; gi += GROUP2)
-        for (int gj = 0; gj <= gi; gj += GROUP2)
-            for (int I = gi; I < gi + GROUP2 && I < t; ++I)
-                for (int J = gj; J < gj + GROUP2 && J <= I; ++J) out.push_back(make_int2(I, J));
+    for (int gi = 0; gi < t; gi += group)
+        for (int gj = 0; gj <= gi; gj += group)
+            for (int I = gi; I < gi + group && I < t; ++I)
+                for (int J = gj; J < gj + group && J <= I; ++J) out.push_back(make_int2(I, J));
 }
 }  // namespace v2
 
-// exact-dosage path: K_ik += u_i + u_k + c on the lower triangle (once per call, before the mirror)
-__global__ void __launch_bounds__(256) k_apply_rank1(float* K, long long n, long long ldk, const double* u, const double* csum) {
+// exact-dosage path: K_ik += v_k on the lower triangle (once per call, before the mirror)
+__global__ void __launch_bounds__(256) k_apply_rank1(float* K, long long n, long long ldk, const double* u) {
     const long long i = blockIdx.x;
-    const double ui = u[i] + *csum;
     for (long long k = (long long)blockIdx.y * blockDim.x + threadIdx.x; k <= i; k += (long long)gridDim.y * blockDim.x)
-        K[i * ldk + k] = (float)((double)K[i * ldk + k] + ui + u[k]);
+        K[i * ldk + k] = (float)((double)K[i * ldk + k] + u[k]);
 }
 // the same on compact tile storage [ntiles][256][256]
-__global__ void __launch_bounds__(256) k_apply_rank1_tiles(float* tiles, const int2* coords, long long n, const double* u, const double* csum) {
+__global__ void __launch_bounds__(256) k_apply_rank1_tiles(float* tiles, const int2* coords, long long n, const double* u) {
     const int2 t = coords[blockIdx.x];
     float* base = tiles + (long long)blockIdx.x * 65536;
-    const double c = *csum;
     for (int e = threadIdx.x; e < 65536; e += blockDim.x) {
         const long long i = (long long)t.x * 256 + (e >> 8), k = (long long)t.y * 256 + (e & 255);
-        if (i < n && k < n) base[e] = (float)((double)base[e] + u[i] + u[k] + c);
+        if (i < n && k < n) base[e] = (float)((double)base[e] + u[k]);
     }
+}
+// the same for a rectangular (train x test) product: out[i, k] += v_k
+__global__ void __launch_bounds__(256) k_apply_colvec(float* out, long long n_rows, long long n_cols, long long ldo, const double* u) {
+    const long long i = blockIdx.x;
+    for (long long k = (long long)blockIdx.y * blockDim.x + threadIdx.x; k < n_cols; k += (long long)gridDim.y * blockDim.x)
+        out[i * ldo + k] = (float)((double)out[i * ldo + k] + u[k]);
 }
 
 __global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long ldk) {
@@ -866,6 +959,29 @@ __global__ void __launch_bounds__(256) k_split_planes(const T* val, long long si
 }
 
 // ---- host helpers --------------------------------------------------------------------------------------------
+// Tuning knobs, read from the environment on every launch (kernel experiments; the defaults are the shipped configuration).
+struct Knobs {
+    int run_kb_fast;   // PSTB_RUN_KB_FAST: k-blocks per TMEM run on the 2-term path (default 6)
+    int tma_out;       // PSTB_SYRK_TMA_OUT: 1 = K leaves through staging tiles + TMA bulk tensor store / reduce-add (default), 0 = per-thread path
+    int red_add;       // PSTB_SYRK_RED: per-thread path: 1 = red.global.add.v4.f32 (default), 0 = load + add + store
+    int dbg;           // PSTB_SYRK_DBG: timing experiments only (results are wrong): 2 = no K write, 4 = no operand loads
+    int clusters;      // PSTB_SYRK_CLUSTERS: CTA pairs to launch (default: SM count / 2)
+    int group;         // PSTB_SYRK_GROUP: tiles per side of a rasterisation super-block (default 8 = 2048 x 2048)
+};
+Knobs knobs() {
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
+    Knobs k;
+    k.run_kb_fast = geti("PSTB_RUN_KB_FAST", 6);
+    if (k.run_kb_fast < 1 || k.run_kb_fast > 64) k.run_kb_fast = 6;
+    k.tma_out = geti("PSTB_SYRK_TMA_OUT", 1) != 0 ? 1 : 0;
+    k.red_add = geti("PSTB_SYRK_RED", 1) != 0 ? 1 : 0;
+    k.dbg = geti("PSTB_SYRK_DBG", 0);
+    k.clusters = geti("PSTB_SYRK_CLUSTERS", 0);
+    k.group = geti("PSTB_SYRK_GROUP", 8);
+    if (k.group < 1 || k.group > 64) k.group = 8;
+    return k;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -910,6 +1026,25 @@ int make_byte_plane_map(CUtensorMap* map, const void* plane, long long n_pad, lo
     return 0;
 }
 
+// float32 output matrix [rows][cols] with leading dimension ld (elements): boxes of 32 x 32, 128-byte swizzle (the epilogue's staging
+// tiles).  Returns 0 and sets *ok = 1 when the matrix can be addressed by a tensor map (16-byte aligned base and row pitch).
+int make_out_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int* ok) {
+    *ok = 0;
+    memset(map, 0, sizeof(*map));
+    if (rows < 1 || cols < 1 || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0 || rows > 0x7fffffffLL || cols > 0x7fffffffLL) return 0;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return 0;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) *ok = 1;
+    return 0;
+}
+
 // lower-triangular tile list, rasterised in GROUP_I x GROUP_J super-blocks so concurrently running CTAs share operand rows
 void build_tiles(long long n, std::vector<int2>& out) {
     out.clear();
@@ -924,7 +1059,7 @@ void build_tiles(long long n, std::vector<int2>& out) {
 struct TileCache {
     long long n = -1;
     int device = -1;
-    int version = 0, rank = 0, world = 1;
+    int version = 0, rank = 0, world = 1, group = 0;
     int2* d_tiles = nullptr;
     int ntiles = 0;
 };
@@ -933,7 +1068,7 @@ struct TileCache {
 // tiles a rank works on concurrently stay inside one super-block)
 void owned_tiles(long long n, int version, int rank, int world, std::vector<int2>& out) {
     std::vector<int2> all;
-    if (version == 2) v2::build_tiles2(n, all); else build_tiles(n, all);
+    if (version == 2) v2::build_tiles2(n, all, knobs().group); else build_tiles(n, all);
     if (world <= 1) { out.swap(all); return; }
     out.clear();
     for (size_t t = (size_t)rank; t < all.size(); t += (size_t)world) out.push_back(all[t]);
@@ -943,7 +1078,8 @@ int get_tiles(long long n, int version, int rank, int world, cudaStream_t st, co
     static thread_local TileCache c;
     int dev = 0;
     PSTB_CUDA(cudaGetDevice(&dev));
-    if (c.n != n || c.device != dev || c.version != version || c.rank != rank || c.world != world) {
+    const int group = knobs().group;
+    if (c.n != n || c.device != dev || c.version != version || c.rank != rank || c.world != world || c.group != group) {
         std::vector<int2> tiles;
         owned_tiles(n, version, rank, world, tiles);
         PSTB_CUDA(cudaStreamSynchronize(st));
@@ -958,6 +1094,7 @@ int get_tiles(long long n, int version, int rank, int world, cudaStream_t st, co
         c.version = version;
         c.rank = rank;
         c.world = world;
+        c.group = group;
     }
     *d_tiles = c.d_tiles;
     *ntiles = c.ntiles;
@@ -1003,16 +1140,24 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.out_scale = out_scale;
     p.compact = compact;
     p.fp8lo = fp8lo;
-    static const int run_kb_fast_env = getenv("PSTB_RUN_KB_FAST") ? atoi(getenv("PSTB_RUN_KB_FAST")) : 0;
-    p.run_kb_fast = (run_kb_fast_env >= 1 && run_kb_fast_env <= 16) ? run_kb_fast_env : 6;
+    const Knobs kn = knobs();
+    p.run_kb_fast = kn.run_kb_fast;
+    p.red_add = kn.red_add;
+    p.dbg = kn.dbg;
+    CUtensorMap map_out;
+    int out_ok = 0;
+    if (compact) make_out_map(&map_out, K, (long long)ntiles * v2::TM, v2::TN, v2::TN, &out_ok);
+    else make_out_map(&map_out, K, n, n, ldk, &out_ok);
+    p.tma_out = (kn.tma_out && out_ok) ? 1 : 0;
     // per launch, not cached: the attribute belongs to the (function, device) pair and a thread may switch devices
     PSTB_CUDA(cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SYRK_SMEM));
     PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
     if (ntiles < 1) return 0;
     if (version == 2) {
         int clusters = sm_count_cached() / 2;
+        if (kn.clusters > 0 && kn.clusters < clusters) clusters = kn.clusters;
         if (clusters > ntiles) clusters = ntiles;
-        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, p);   // __cluster_dims__(2,1,1)
+        v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, map_out, p);   // __cluster_dims__(2,1,1)
         PSTB_AFTER_LAUNCH("k_syrk2");
         return 0;
     }
@@ -1061,15 +1206,24 @@ int get_cross_tiles(long long row_blocks, long long col_blocks, cudaStream_t st,
 }
 
 // out[n_rows, n_cols] (+)= X_rows X_cols^T: planes hold the column operand in rows [0, cols_pad) and the row operand in rows
-// [cols_pad, cols_pad + rows_pad); always the 3-term hi/lo split (sc->any_missing is set by the caller)
-int launch_cross(const __half* hi, const __half* lo, long long n_rows, long long rows_pad, long long n_cols, long long cols_pad,
-                 long long k_pad, float* out, long long ldo, int accumulate, const Scalars* sc, cudaStream_t st) {
+// [cols_pad, cols_pad + rows_pad).  Same paths as the symmetric kernel (sc->need_3term chooses on the device): on the 2-term path
+// the row side is read from plane 0 (L, and its e4m3 twin), the column side from planes 1 / 2 (B hi / lo).
+int launch_cross(const __half* hi, const __half* lo, const __half* p2, int fp8lo, long long n_rows, long long rows_pad, long long n_cols,
+                 long long cols_pad, long long k_pad, float* out, long long ldo, int accumulate, const Scalars* sc, cudaStream_t st) {
     const long long n_pad = rows_pad + cols_pad;
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi, map_lo, map_p2, map_h8;
     if (make_plane_map(&map_hi, hi, n_pad, k_pad) || make_plane_map(&map_lo, lo, n_pad, k_pad)) return 1;
+    if (fp8lo) {
+        const unsigned char* l8 = reinterpret_cast<const unsigned char*>(p2);
+        if (make_byte_plane_map(&map_p2, l8, n_pad, k_pad) || make_byte_plane_map(&map_h8, l8 + n_pad * k_pad, n_pad, k_pad)) return 1;
+    } else {
+        if (make_plane_map(&map_p2, p2, n_pad, k_pad)) return 1;
+        map_h8 = map_p2;
+    }
     const int2* d_tiles = nullptr;
     int ntiles = 0;
     if (get_cross_tiles(rows_pad / v2::TM, cols_pad / v2::TN, st, &d_tiles, &ntiles)) return 1;
+    const Knobs kn = knobs();
     SyrkParams p{};
     p.tiles = d_tiles;
     p.ntiles = ntiles;
@@ -1083,12 +1237,19 @@ int launch_cross(const __half* hi, const __half* lo, long long n_rows, long long
     p.sc = sc;
     p.out_scale = 1.0f;
     p.compact = 0;
-    p.run_kb_fast = 6;
+    p.fp8lo = fp8lo;
+    p.run_kb_fast = kn.run_kb_fast;
+    p.red_add = kn.red_add;
+    p.dbg = kn.dbg;
+    CUtensorMap map_out;
+    int out_ok = 0;
+    make_out_map(&map_out, out, n_rows, n_cols, ldo, &out_ok);
+    p.tma_out = (kn.tma_out && out_ok) ? 1 : 0;
     PSTB_CUDA(cudaFuncSetAttribute(v2::k_syrk2, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SYRK2_SMEM));
     if (ntiles < 1) return 0;
     int clusters = sm_count_cached() / 2;
     if (clusters > ntiles) clusters = ntiles;
-    v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_lo, map_lo, p);
+    v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, map_out, p);
     PSTB_AFTER_LAUNCH("k_syrk2");
     return 0;
 }
@@ -1156,9 +1317,19 @@ extern "C" int pstb_set_syrk_low_term(int mode) {
     return g_low_term.exchange(mode);
 }
 
+// 1 = low term on the fp8 pipe.  `low_term` is the per-call argument (PSTB_LOW_TERM_DEFAULT = the process-wide default above).
+// AUTO: the e4m3 rounding error of the low term averages out over the SNPs of the kernel -- relative Frobenius error
+// ~5e-6 * sqrt(N / (M_eff + N)) (scripts/emulate_masked_split.py) -- so it is taken when the kernel multiplies at least as many
+// SNPs as individuals (Beta weights concentrate on the rare SNPs: 4 x as many) and at least 256.
+static int resolve_fp8lo(int low_term, int64_t snps, int64_t n_iid, int mode) {
+    int lt = (low_term == PSTB_LOW_TERM_FP16 || low_term == PSTB_LOW_TERM_FP8 || low_term == PSTB_LOW_TERM_AUTO) ? low_term : g_low_term.load();
+    if (lt == PSTB_LOW_TERM_AUTO) return (snps >= n_iid * (mode == PSTB_STD_BETA ? 4 : 1) && snps >= 256) ? 1 : 0;
+    return lt == PSTB_LOW_TERM_FP8 ? 1 : 0;
+}
+
 static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                            pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
-                           float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
+                           float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk, int low_term,
                            void* stream, int rank, int world, int compact, int phase = 3, int64_t total_sid = -1) {
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
@@ -1190,23 +1361,14 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     __half* p2 = lo + n_pad * k_cap;
     Scalars* sc = reinterpret_cast<Scalars*>(p2 + n_pad * k_cap);
     double* u = reinterpret_cast<double*>(sc + 1);
-    double* csum = u + n_pad;
     const int dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
-    // the 2-term exact-dosage GEMM needs the dosage counts of this call (to know that a chunk has no missing data) and the
-    // CTA-pair kernel; trained statistics, PSTB_SYRK_V1=1 or PSTB_SYRK_3TERM=1 keep every chunk on the 3-term split
-    static const bool env_slow = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ||
-                                 (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
-    const bool force_slow = use_stats || env_slow;
-    const bool env_version2_ok = true;                           // env_slow covers PSTB_SYRK_V1 (the 1-CTA kernel has no fp8 path)
-    // the low term of the 2-term path on the fp8 pipe: 25 % fewer tensor cycles (cfg3: 1 035 -> 1 276 TFLOP/s on one box); the
-    // error grows from ~1e-6 to (3..6)e-6 relative Frobenius, ~7e-6 * sqrt(N / (M + N)) by the rounding model (gate: 1e-5).
-    // auto: when this call multiplies at least as many SNPs as individuals (<= 5e-6)
-    const int lt = g_low_term.load();
+    // every chunk takes the 2-term exact-dosage GEMM -- missing genotypes and trained statistics included -- unless a trained
+    // mean lies outside [0, 2] (k_absmax raises the flag on the device) or PSTB_SYRK_V1=1 / PSTB_SYRK_3TERM=1 (A/B runs) force
+    // the 3-term hi/lo split (the 1-CTA kernel has no 2-term path)
+    const bool force_slow = (getenv("PSTB_SYRK_V1") && atoi(getenv("PSTB_SYRK_V1")) != 0) ||
+                            (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
     // (a streamed call passes the SNP count of the whole kernel in total_sid)
-    // -- and at least 256 SNPs: the estimate is statistical, a handful of products does not average the e4m3 rounding out (a
-    // single product can be off by 3e-5 relative)
-    const int64_t snps = total_sid >= 0 ? total_sid : sid.n;
-    const int fp8lo = (lt == PSTB_LOW_TERM_FP8 || (lt == PSTB_LOW_TERM_AUTO && snps >= iid.n && snps >= 256)) ? 1 : 0;
+    const int fp8lo = force_slow ? 0 : resolve_fp8lo(low_term, total_sid >= 0 ? total_sid : sid.n, iid.n, mode);
     if (phase & 1) PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     const int2* d_tiles = nullptr;
     int ntiles = 0;
@@ -1218,10 +1380,10 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         if (sid.idx) sub.idx = sid.idx + c0; else sub.start = sid.start + c0 * sid.step;
         double* st_chunk = d_stats + 2 * c0;
         PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
-        if (force_slow) PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));
+        if (force_slow) PSTB_CUDA(cudaMemsetAsync(&sc->need_3term, 0xFF, sizeof(unsigned int), st));
         if (!use_stats) {
             int rc = read_impl_ex(d_packed, ld, iid_count, sid_count, iid, sub, count_a1, mode, a, b, 0, st_chunk, nullptr, PSTB_F32,
-                                  PSTB_ORDER_F, stream, &sc->any_missing);
+                                  PSTB_ORDER_F, stream, nullptr);
             if (rc) return rc;
         }
         k_absmax<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(st_chunk, ns, mode, a, b, lnB, sc);
@@ -1243,9 +1405,8 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         pp.hi = hi;
         pp.lo = lo;
         pp.p2 = p2;
-        pp.fp8lo = (!force_slow && env_version2_ok) ? fp8lo : 0;
+        pp.fp8lo = fp8lo;
         pp.u = u;
-        pp.csum = csum;
         pp.n_pad = n_pad;
         pp.k_pad = k_pad;
         pp.dense = dense;
@@ -1260,11 +1421,11 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     if (!force_slow && (phase & 2)) {
         if (compact) {
             if (ntiles > 0) {
-                k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(d_K, d_tiles, n, u, csum);
+                k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(d_K, d_tiles, n, u);
                 PSTB_AFTER_LAUNCH("k_apply_rank1_tiles");
             }
         } else {
-            k_apply_rank1<<<dim3((unsigned)n, (unsigned)((n + 2047) / 2048 > 64 ? 64 : (n + 2047) / 2048)), 256, 0, st>>>(d_K, n, n, u, csum);
+            k_apply_rank1<<<dim3((unsigned)n, (unsigned)((n + 2047) / 2048 > 64 ? 64 : (n + 2047) / 2048)), 256, 0, st>>>(d_K, n, n, u);
             PSTB_AFTER_LAUNCH("k_apply_rank1");
         }
     }
@@ -1275,16 +1436,16 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
 extern "C" int pstb_snp_kernel(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                                pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
                                float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk,
-                               void* stream) {
+                               int low_term, void* stream) {
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate,
-                           mirror, d_work, work_bytes, chunk, stream, 0, 1, 0);
+                           mirror, d_work, work_bytes, chunk, low_term, stream, 0, 1, 0);
 }
 
 int pstb::snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
                            int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
-                           void* d_work, int64_t work_bytes, int64_t chunk, void* stream, int phase, int64_t total_sid) {
+                           void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream, int phase, int64_t total_sid) {
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_K, accumulate, 0,
-                           d_work, work_bytes, chunk, stream, 0, 1, 0, phase, total_sid);
+                           d_work, work_bytes, chunk, low_term, stream, 0, 1, 0, phase, total_sid);
 }
 
 // ---- K-tile sharding (cfg5: N = 500 000, K = 1 TB does not fit one GPU) -----------------------------------------
@@ -1307,10 +1468,10 @@ extern "C" int pstb_kernel_tile_coords(int64_t n_iid, int rank, int world, int32
 extern "C" int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                                      pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
                                      float* d_tiles, int rank, int world, int accumulate, void* d_work, int64_t work_bytes,
-                                     int64_t chunk, void* stream) {
+                                     int64_t chunk, int low_term, void* stream) {
     if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_tiles, accumulate,
-                           0, d_work, work_bytes, chunk, stream, rank, world, 1);
+                           0, d_work, work_bytes, chunk, low_term, stream, rank, world, 1);
 }
 
 extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
@@ -1337,7 +1498,7 @@ extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_
     const long long si = (order == PSTB_ORDER_C) ? n_sid : 1, sj = (order == PSTB_ORDER_C) ? 1 : n_iid;
     const long long total = n * n_sid;
     PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
-    PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));       // arbitrary floats: always the 3-term split
+    PSTB_CUDA(cudaMemsetAsync(&sc->need_3term, 0xFF, sizeof(unsigned int), st));       // arbitrary floats: always the 3-term split
     long long g = (total + 255) / 256;
     if (g > (long long)sm_count_cached() * 16) g = (long long)sm_count_cached() * 16;
     if (dtype == PSTB_F32) k_absmax_float<float><<<(unsigned)g, 256, 0, st>>>((const float*)d_val, total, sc);
@@ -1368,7 +1529,7 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
                                      pstb_axis sid_r, int count_a1_r, const uint8_t* d_packed_c, int64_t ld_c, int64_t iid_count_c,
                                      int64_t sid_count_c, pstb_axis iid_c, pstb_axis sid_c, int count_a1_c, int mode, double a, double b,
                                      int use_stats, double* d_stats, float* d_out, int accumulate, void* d_work, int64_t work_bytes,
-                                     int64_t chunk, void* stream) {
+                                     int64_t chunk, int low_term, void* stream) {
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid_r.n < 0 || iid_c.n < 0 || sid_r.n < 0 || sid_c.n < 0) return fail("negative selection length");
@@ -1392,7 +1553,10 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
     __half* lo = hi + n_pad * k_cap;
     __half* p2 = lo + n_pad * k_cap;
     Scalars* sc = reinterpret_cast<Scalars*>(p2 + n_pad * k_cap);
-    double* u = reinterpret_cast<double*>(sc + 1);
+    double* u = reinterpret_cast<double*>(sc + 1);                                        // rank-one vector v of the column side
+    const bool force_slow = getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0;
+    const int fp8lo = force_slow ? 0 : resolve_fp8lo(low_term, sid_r.n, nr > nc ? nr : nc, mode);
+    PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     for (long long c0 = 0; c0 < sid_r.n; c0 += chunk) {
         const long long ns = (c0 + chunk <= sid_r.n) ? chunk : sid_r.n - c0;
         const long long k_pad = round_up(ns, BK);
@@ -1402,7 +1566,7 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
         if (sid_c.idx) sub_c.idx = sid_c.idx + c0; else sub_c.start = sid_c.start + c0 * sid_c.step;
         double* st_chunk = d_stats + 2 * c0;
         PSTB_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
-        PSTB_CUDA(cudaMemsetAsync(&sc->any_missing, 0xFF, sizeof(unsigned int), st));      // always the 3-term split
+        if (force_slow) PSTB_CUDA(cudaMemsetAsync(&sc->need_3term, 0xFF, sizeof(unsigned int), st));
         if (!use_stats) {                                                                 // statistics of the row (train) side
             int rc = read_impl_ex(d_packed_r, ld_r, iid_count_r, sid_count_r, iid_r, sub_r, count_a1_r, mode, a, b, 0, st_chunk, nullptr,
                                   PSTB_F32, PSTB_ORDER_F, stream, nullptr);
@@ -1410,6 +1574,8 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
         }
         k_absmax<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(st_chunk, ns, mode, a, b, lnB, sc);
         PSTB_AFTER_LAUNCH("k_absmax");
+        // the e4m3 byte planes of the fp8 low term are addressed over the whole stacked matrix: byte plane 0 ((w h)_lo) at p2,
+        // byte plane 1 (g - mu'') at p2 + n_pad * k_pad bytes
         for (int side = 0; side < 2; ++side) {                                            // 0: column operand (rows 0..), 1: row operand
             const pstb_axis& iid = side ? iid_r : iid_c;
             PlaneParams pp{};
@@ -1430,8 +1596,10 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
             pp.hi = hi + off;
             pp.lo = lo + off;
             pp.p2 = p2;
-            pp.u = u;
-            pp.csum = u;
+            pp.p2_row0 = side ? cols_pad : 0;
+            pp.p2_rows = n_pad;
+            pp.fp8lo = fp8lo;
+            pp.u = side ? nullptr : u;                                                    // v_k belongs to the column side
             pp.n_pad = side ? rows_pad : cols_pad;
             pp.k_pad = k_pad;
             pp.dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
@@ -1440,8 +1608,12 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
             k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
             PSTB_AFTER_LAUNCH("k_planes");
         }
-        int rc = launch_cross(hi, lo, nr, rows_pad, nc, cols_pad, k_pad, d_out, nc, (accumulate || c0 > 0) ? 1 : 0, sc, st);
+        int rc = launch_cross(hi, lo, p2, fp8lo, nr, rows_pad, nc, cols_pad, k_pad, d_out, nc, (accumulate || c0 > 0) ? 1 : 0, sc, st);
         if (rc) return rc;
+    }
+    if (!force_slow) {
+        k_apply_colvec<<<dim3((unsigned)nr, (unsigned)((nc + 2047) / 2048 > 64 ? 64 : (nc + 2047) / 2048)), 256, 0, st>>>(d_out, nr, nc, nc, u);
+        PSTB_AFTER_LAUNCH("k_apply_colvec");
     }
     return 0;
 }

@@ -10,6 +10,8 @@ from . import _lib
 from ._lib import Axis, lib, check
 
 BED_MAGIC = bytes([0x6C, 0x1B, 0x01])
+_LOW_TERM = {"default": -1, "fp16": 0, "fp8": 1, "auto": 2}
+_LOW_TERM_NAME = {0: "fp16", 1: "fp8", 2: "auto"}
 _DT = {np.dtype(np.float32): (_lib.F32, torch.float32), np.dtype(np.float64): (_lib.F64, torch.float64),
        np.dtype(np.int8): (_lib.I8, torch.int8)}
 
@@ -209,10 +211,11 @@ def pack(val, count_A1=False):
 
 
 def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
-               K=None, accumulate=False, mirror=True):
+               K=None, accumulate=False, mirror=True, low_term="default"):
     """``K = sum_j x_j x_j^T`` over the selected SNPs on tcgen05 tensor cores (float32 CUDA tensor [n, n]).
 
     Returns ``(K, stats)``.  ``K`` given + ``accumulate`` => the partial sum is added (streaming / sharding).
+    ``low_term``: 'fp16' | 'fp8' | 'auto' | 'default' -- per call, see :func:`low_term_for`.
     """
     _lib.require_gpu()
     dev = store.device
@@ -237,12 +240,12 @@ def snp_kernel(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=(
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         check(lib.pstb_snp_kernel(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
                                   int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), K.data_ptr(),
-                                  int(bool(accumulate)), int(bool(mirror)), work.data_ptr(), wbytes, chunk, _stream()))
+                                  int(bool(accumulate)), int(bool(mirror)), work.data_ptr(), wbytes, chunk, _LOW_TERM[low_term], _stream()))
     return K, d_stats
 
 
 def snp_cross_kernel(store_r, store_c, iid_r=None, iid_c=None, sid_r=None, sid_c=None, count_A1_r=False, count_A1_c=False,
-                     standardizer=("unit",), stats=None, chunk=None, out=None, accumulate=False):
+                     standardizer=("unit",), stats=None, chunk=None, out=None, accumulate=False, low_term="default"):
     """Train x test kernel ``out[i, k] = sum_j x_ij y_kj`` (float32 CUDA tensor [n_r, n_c]) on the tensor cores.
 
     ``store_r`` / ``store_c`` are the row (train) and column (test) packed stores (may be the same store with different iid
@@ -278,7 +281,7 @@ def snp_cross_kernel(store_r, store_c, iid_r=None, iid_c=None, sid_r=None, sid_c
         check(lib.pstb_snp_cross_kernel(store_r.tensor.data_ptr(), store_r.ld, store_r.iid_count, store_r.sid_count, ir.axis(), sr.axis(),
                                         int(bool(count_A1_r)), store_c.tensor.data_ptr(), store_c.ld, store_c.iid_count, store_c.sid_count,
                                         ic.axis(), sc.axis(), int(bool(count_A1_c)), mode, a, b, use_stats, d_stats.data_ptr(),
-                                        out.data_ptr(), int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _stream()))
+                                        out.data_ptr(), int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _LOW_TERM[low_term], _stream()))
     return out, d_stats
 
 
@@ -292,7 +295,7 @@ def kernel_tile_coords(n_iid, rank=0, world=1):
 
 
 def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
-                     rank=0, world=1, tiles=None, accumulate=False):
+                     rank=0, world=1, tiles=None, accumulate=False, low_term="default"):
     """K-tile sharded kinship: this rank's 256 x 256 tiles of ``K = X X^T`` over ALL selected SNPs (cfg5; no collective).
 
     Returns ``(tiles, coords, stats)``: float32 CUDA tensor [count, 256, 256], the (I, J) of each tile, per-SNP statistics.
@@ -321,42 +324,31 @@ def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standard
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         check(lib.pstb_snp_kernel_tiles(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
                                         int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), tiles.data_ptr(), rank, world,
-                                        int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _stream()))
+                                        int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _LOW_TERM[low_term], _stream()))
     return tiles, coords, d_stats
 
 
-_LOW_TERM = {"fp16": 0, "fp8": 1, "auto": 2}
-
-
 def set_syrk_low_term(mode):
-    """'fp16' | 'fp8' | 'auto' (default): where the low term of the exact-dosage SYRK runs (``pstb_set_syrk_low_term``: fp8 is ~23 %
-    faster at (3..6)e-6 instead of ~1e-6 relative Frobenius error).  Returns the previous mode's name."""
+    """'fp16' | 'fp8' | 'auto': the process-wide DEFAULT of the kernel entry points' per-call ``low_term`` argument
+    (``pstb_set_syrk_low_term``).  Returns the previous default's name."""
     prev = int(lib.pstb_set_syrk_low_term(_LOW_TERM[mode]))
-    return {v: k for k, v in _LOW_TERM.items()}[prev]
+    return _LOW_TERM_NAME[prev]
 
 
 def get_syrk_low_term():
-    return {v: k for k, v in _LOW_TERM.items()}[int(lib.pstb_set_syrk_low_term(-1))]        # an invalid mode only reports
+    return _LOW_TERM_NAME[int(lib.pstb_set_syrk_low_term(-1))]        # an invalid mode only reports
 
 
-class syrk_low_term_for(object):
-    """Context manager for a kernel whose SNPs are spread over several calls (SNP shards, DistributedBed pieces): 'auto' looks at
-    one call's SNP count, this resolves it with the count of the whole kernel.  An explicit 'fp16' / 'fp8' setting is left alone."""
-
-    def __init__(self, total_sid_count, n_iid):
-        self.choice = "fp8" if (total_sid_count >= n_iid and total_sid_count >= 256) else "fp16"
-        self.active = False
-
-    def __enter__(self):
-        if get_syrk_low_term() == "auto":
-            set_syrk_low_term(self.choice)
-            self.active = True
-        return self
-
-    def __exit__(self, *exc):
-        if self.active:
-            set_syrk_low_term("auto")
-        return False
+def low_term_for(total_sid_count, n_iid, standardizer=("unit",)):
+    """The ``low_term`` a kernel call should pass when the SNPs of ONE kernel are spread over several calls (SNP shards,
+    DistributedBed pieces, file slices): 'auto' inside the library looks at one call's SNP count, this applies the same rule to
+    the count of the whole kernel.  An explicit process-wide 'fp16' / 'fp8' default is respected.  No global state is touched,
+    so concurrent callers with different shapes cannot race (the round-1 context manager switched a process-wide mode)."""
+    default = get_syrk_low_term()
+    if default != "auto":
+        return default
+    need = n_iid * (4 if standardizer is not None and standardizer[0] == "beta" else 1)
+    return "fp8" if (total_sid_count >= need and total_sid_count >= 256) else "fp16"
 
 
 def kernel_from_tiles(tiles, n_iid, rank=0, world=1, K=None):

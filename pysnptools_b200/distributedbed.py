@@ -67,10 +67,9 @@ class DistributedBed(SnpReader):
             out.append((int(k), sid[where] - self._starts[k], where))
         return sid, out
 
-    def _read(self, iid_index_or_none, sid_index_or_none, order, dtype, force_python_only, view_ok, num_threads, to_device=False,
-              _standardize=None):
+    def _read(self, iid_index_or_none, sid_index_or_none, order, dtype, force_python_only, view_ok, num_threads, to_device=False):
         _no_python_path(force_python_only)
-        assert not to_device and _standardize is None, "DistributedBed returns NumPy arrays; use its pieces for device results"
+        assert not to_device, "DistributedBed returns NumPy arrays; use its pieces for device results"
         dtype = np.dtype(dtype)
         sid, parts = self._split(sid_index_or_none)
         n_iid = self.iid_count if iid_index_or_none is None else len(iid_index_or_none)
@@ -93,12 +92,14 @@ class DistributedBed(SnpReader):
         K = None
         stats = np.empty((len(sid), 2), dtype=np.float64)
         n_iid = self.iid_count if iid_idx is None else len(iid_idx)
+        low_term = device.low_term_for(len(sid), n_iid, spec)     # the precision mode follows the SNP count of the whole kernel
         for k, local, where in parts:
             piece = self._pieces[k]
             store, _ = piece._store_for(None)
             K, st = device.snp_kernel(store, iid_idx, local, count_A1=True, standardizer=spec,
                                       stats=None if stats_in is None else np.asarray(stats_in)[where],
-                                      chunk=_kernel_chunk(block_size, n_iid, len(local)), K=K, accumulate=K is not None, mirror=False)
+                                      chunk=_kernel_chunk(block_size, n_iid, len(local)), K=K, accumulate=K is not None, mirror=False,
+                                      low_term=low_term)
             stats[where] = st.cpu().numpy()
             piece._device_store = None                # one piece resident at a time
         import torch

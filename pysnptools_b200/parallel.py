@@ -75,8 +75,8 @@ def distributed_bed_partial_kernel(dbed, rank, world, standardizer_spec=("unit",
     for k in mine:
         piece = dbed._pieces[k]
         store = device.PackedStore.from_host(np.asarray(piece._packed_host()), n)
-        with device.syrk_low_term_for(dbed.sid_count, n):
-            K, st = device.snp_kernel(store, count_A1=piece.count_A1, standardizer=standardizer_spec, chunk=chunk, K=K, accumulate=True, mirror=False)
+        K, st = device.snp_kernel(store, count_A1=piece.count_A1, standardizer=standardizer_spec, chunk=chunk, K=K, accumulate=True, mirror=False,
+                                  low_term=device.low_term_for(dbed.sid_count, n, standardizer_spec))
         stats.append(st)
         where.append(np.arange(dbed._starts[k], dbed._starts[k + 1], dtype=np.int64))
     stats = torch.cat(stats) if stats else torch.zeros((0, 2), dtype=torch.float64, device="cuda")
@@ -111,8 +111,8 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     else:
         # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix.
         # The low-term mode "auto" looks at one call's SNP count; this kernel's is the global one.
-        with device.syrk_low_term_for(bed.sid_count, bed.iid_count):
-            tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk)
+        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
+                                                        low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec))
         allreduce_sum_(tiles, group)
         K = device.kernel_from_tiles(tiles, bed.iid_count)
         del tiles

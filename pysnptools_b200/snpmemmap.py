@@ -174,7 +174,7 @@ class SnpMemMap(SnpData):
             standardizer.standardize(snpreader, num_threads=num_threads)
             out.val[:, :] = snpreader.val
         else:
-            fused = isinstance(standardizer, Standardizer) and standardizer._device_spec() is not None
+            fused = isinstance(standardizer, Standardizer) and standardizer._device_spec() is not None and snpreader._can_fuse()
             for start in range(0, snpreader.sid_count, block_size):
                 block = snpreader[:, start:start + block_size]
                 if fused:

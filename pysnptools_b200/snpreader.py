@@ -144,12 +144,24 @@ class SnpReader(object):
         page-locked one from :func:`pysnptools_b200.util.pinned_empty` the result arrives at PCIe speed (no staging copy).
         """
         dtype = np.dtype(dtype)
-        if standardizer is None or isinstance(standardizer, Identity):
-            kw = {} if out is None else {"_out": out}
-            val = self._read(None, None, order, dtype, force_python_only, view_ok, num_threads, to_device=to_device, **kw)
+        plain = standardizer is None or isinstance(standardizer, Identity)
+        spec = None if plain else standardizer._device_spec()
+        if plain or spec is None or not self._can_fuse():
+            # no fused decode + standardize for this reader / standardizer (in-memory data, DistributedBed, a mapped file, DiagKtoN ...):
+            # read, then standardize the fresh copy in place -- what the reference does (snpreader.py:419-478 + snpdata.py:138-188)
+            takes_out = out is not None and self._can_fuse()
+            val = self._read(None, None, order, dtype, force_python_only, view_ok and plain, num_threads, to_device=to_device,
+                             **({"_out": out} if takes_out else {}))
+            if out is not None and not takes_out:
+                if _is_tensor(val) or not (isinstance(out, np.ndarray) and out.shape == val.shape and out.dtype == val.dtype and out.flags["WRITEABLE"]):
+                    raise ValueError("out= must be a writeable ndarray of shape {0} and dtype {1}".format(tuple(val.shape), dtype))
+                out[...] = val
+                val = out
             data = SnpData(self.iid, self.sid, val, pos=self.pos, name=str(self), _require_float32_64=_require_float32_64)
-            return (data, standardizer) if return_trained else data
-        spec = standardizer._device_spec()
+            if plain:
+                return (data, standardizer) if return_trained else data
+            data, trained = data.standardize(standardizer, return_trained=True, force_python_only=force_python_only, num_threads=num_threads)
+            return (data, trained) if return_trained else data
         stats_in = standardizer._trained_stats_for(self.sid)
         kw = {} if out is None else {"_out": out}
         val, stats = self._read(None, None, order, dtype, force_python_only, view_ok, num_threads, to_device=to_device,
@@ -159,6 +171,11 @@ class SnpReader(object):
         if return_trained:
             return data, standardizer._make_trained(self.sid, np.asarray(stats, dtype=dtype))
         return data
+
+    def _can_fuse(self):
+        """True when ``_read`` accepts ``_standardize=`` / ``_out=`` (a packed .bed store behind it): decode + standardize in one GPU
+        pass.  Readers without one (SnpData, DistributedBed, SnpMemMap) read first and standardize the copy."""
+        return False
 
     def read_kernel(self, standardizer=None, block_size=None, order="A", dtype=np.float64, force_python_only=False,
                     view_ok=False, num_threads=None):
@@ -179,7 +196,14 @@ class SnpReader(object):
         _no_python_path(force_python_only)
         from . import device
         dtype = np.dtype(dtype)
-        root, iid_idx, sid_idx = self._root_and_indices()
+        try:
+            root, iid_idx, sid_idx = self._root_and_indices()
+        except NotImplementedError:
+            # a subset of in-memory / memory-mapped values (e.g. what util.intersect_apply builds): materialise it and take the
+            # float-matrix kernel (snpdata.py:190-214), as the reference does through SnpReader._as_snpdata
+            data = self.read(order="A", dtype=dtype if dtype in (np.float32, np.float64) else np.float64, view_ok=True, num_threads=num_threads)
+            return data._read_kernel(standardizer, block_size=block_size, order=order, dtype=dtype, force_python_only=force_python_only,
+                                     view_ok=view_ok, return_trained=return_trained, num_threads=num_threads, to_device=to_device)
         if hasattr(root, "_read_kernel_pieces"):                  # DistributedBed: one packed store per piece, K accumulated
             if not isinstance(standardizer, Standardizer) or (standardizer._device_spec() is None and not isinstance(standardizer, Identity)):
                 raise NotImplementedError("read_kernel on the GPU supports Unit, Beta, their trained forms and Identity")
@@ -269,6 +293,9 @@ class _SnpSubset(SnpReader):
             kw["_out"] = _out
         return self._internal._read(_compose(self._iid_index, iid_index_or_none), _compose(self._sid_index, sid_index_or_none),
                                     order, dtype, force_python_only, view_ok, num_threads, to_device=to_device, **kw)
+
+    def _can_fuse(self):
+        return self._internal._can_fuse()
 
     def _root_and_indices(self):
         root, ii, si = self._internal._root_and_indices()
@@ -390,6 +417,9 @@ class Bed(SnpReader):
     def _root_and_indices(self):
         return self, None, None
 
+    def _can_fuse(self):
+        return True
+
     def _kernel_host(self, iid_idx, sid_idx, spec, stats_in, dtype, chunk):
         """``pstb_snp_kernel_host``: memory-mapped file bytes -> K as a NumPy array (C order, symmetric) + float64 statistics."""
         packed = self._packed_host()
@@ -409,7 +439,7 @@ class Bed(SnpReader):
             _lib.require_gpu()
             _lib.check(_lib.lib.pstb_snp_kernel_host(packed.ctypes.data if m else None, n, m, ii.ctypes.data if ii is not None else None, ni,
                                                      si.ctypes.data if si is not None else None, ns, int(bool(self.count_A1)), mode, a, b,
-                                                     use_stats, stats.ctypes.data, K.ctypes.data, _DT_CODE[np.dtype(dtype)], int(chunk)))
+                                                     use_stats, stats.ctypes.data, K.ctypes.data, _DT_CODE[np.dtype(dtype)], int(chunk), _lib.LOW_TERM_DEFAULT))
         return K, stats
 
     # --- read (bed.py:318-345 -> bed_reader read_f32/f64/i8) ---

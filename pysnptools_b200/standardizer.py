@@ -35,6 +35,10 @@ def _standardize_unit_and_beta(val, is_beta, a, b, apply_in_place, use_stats, st
         return st.to(val.dtype)
     assert val.dtype in (np.float32, np.float64), "snps must be a float in order to standardize in place."
     assert val.flags["C_CONTIGUOUS"] or val.flags["F_CONTIGUOUS"], "Expect snps to be order 'C' or order 'F'"
+    if apply_in_place and not val.flags.writeable:
+        # the C ABI writes through the raw pointer: a read-only mapping (SnpMemMap opens its file with mode='r') would take the
+        # process down, a writeable=False ndarray would be mutated silently; NumPy's in-place arithmetic raises exactly this
+        raise ValueError("assignment destination is read-only")
     _lib.require_gpu()
     n_iid, n_sid = val.shape
     st64 = np.empty((n_sid, 2), dtype=np.float64)
@@ -63,7 +67,7 @@ class Standardizer(object):
 
     # what the fused GPU kernels need: None (identity) | ("unit",) | ("beta", a, b)
     def _device_spec(self):
-        raise NotImplementedError("{0} has no fused GPU path".format(self.__class__.__name__))
+        return None                                     # no fused GPU path: callers read first, then call .standardize
 
     def _trained_stats_for(self, sid):
         return None

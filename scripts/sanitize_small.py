@@ -29,7 +29,7 @@ for n, m in ((5, 3), (203, 31), (1003, 17), (4099, 5), (30001, 3)):
         Kh = np.empty((n, n), dtype=np.float64)
         sth = np.empty((m, 2))
         _lib.check(_lib.lib.pstb_snp_kernel_host(packed.ctypes.data, n, m, None, n, None, m, 0, _lib.STD_UNIT, 0.0, 0.0, 0,
-                                                 sth.ctypes.data, Kh.ctypes.data, _lib.F64, 64))
+                                                 sth.ctypes.data, Kh.ctypes.data, _lib.F64, 64, -1))
 tight = torch.from_numpy(o.synth_packed(203, 0, 9, 0.1, seed=1)).cuda()
 dev.read(dev.PackedStore(tight, 203, 9), dtype=np.float32, standardizer=("unit",))
 nomiss = o.synth_packed(300, 0, 128, 0.0, seed=2)

@@ -159,7 +159,7 @@ def test_cross_kernel_vs_oracle(n_r, n_c, m, chunk, oracle, dev):
     # train x train through the rectangular path == the symmetric kernel
     Ks, _ = dev.snp_kernel(sr, chunk=chunk)
     Kx, _ = dev.snp_cross_kernel(sr, sr, chunk=chunk)
-    assert rel_fro(Kx.double().cpu().numpy(), Ks.double().cpu().numpy()) < 2e-6
+    assert rel_fro(Kx.double().cpu().numpy(), Ks.double().cpu().numpy()) < 4e-6      # L_i B_k above the diagonal here, the mirrored L_k B_i there
 
 
 def test_cross_kernel_edges(oracle, dev):
@@ -205,22 +205,22 @@ def test_snp_kernel_host_entry(pinned, oracle, dev, monkeypatch):
                 stats = np.empty((ns, 2))
                 check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None if iid_idx is None else iid_idx.ctypes.data, ni,
                                                None if sid_idx is None else sid_idx.ctypes.data, ns, 0, mode, ab[0], ab[1], 0,
-                                               stats.ctypes.data, K.ctypes.data, code, 64))
+                                               stats.ctypes.data, K.ctypes.data, code, 64, -1))
                 assert rel_fro(K.astype(np.float64), ref) < K_TOL and np.array_equal(K, K.T)
                 np.testing.assert_allclose(stats, rst, rtol=1e-12)
                 K2 = np.empty((ni, ni), dtype=dtype)
                 check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None if iid_idx is None else iid_idx.ctypes.data, ni,
                                                None if sid_idx is None else sid_idx.ctypes.data, ns, 0, mode, ab[0], ab[1], 1,
-                                               stats.ctypes.data, K2.ctypes.data, code, 128))
+                                               stats.ctypes.data, K2.ctypes.data, code, 128, -1))
                 assert rel_fro(K2.astype(np.float64), ref) < K_TOL
     # no SNPs -> zeros; bad index -> error
     Kz = np.full((n, n), 3.0, dtype=np.float32)
     st0 = np.empty((0, 2))
     empty = np.zeros(0, dtype=np.int64)
-    check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, empty.ctypes.data, 0, 0, STD_UNIT, 0.0, 0.0, 0, st0.ctypes.data, Kz.ctypes.data, F32, 64))
+    check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, empty.ctypes.data, 0, 0, STD_UNIT, 0.0, 0.0, 0, st0.ctypes.data, Kz.ctypes.data, F32, 64, -1))
     assert not Kz.any()
     bad = np.array([m], dtype=np.int64)
-    assert lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, bad.ctypes.data, 1, 0, STD_UNIT, 0.0, 0.0, 0, np.empty((1, 2)).ctypes.data, Kz.ctypes.data, F32, 64) != 0
+    assert lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None, n, bad.ctypes.data, 1, 0, STD_UNIT, 0.0, 0.0, 0, np.empty((1, 2)).ctypes.data, Kz.ctypes.data, F32, 64, -1) != 0
     if pinned:
         del h_packed, K
         lib.pstb_host_free(p_in)
@@ -254,28 +254,104 @@ def test_kernel_from_tiles_matches_square_path(n, m, oracle, dev):
 
 
 @pytest.mark.parametrize("n,m", [(515, 300), (700, 4096), (2100, 700)])
-def test_low_term_modes(n, m, oracle, dev):
-    """Exact-dosage path (no missing genotypes): the low term on the fp8 pipe (e4m3 x e4m3) stays inside the 1e-5 gate for M >> N,
-    M ~ N and M << N; the fp16 low term lands near 1e-6; 'auto' picks fp8 when a call has at least as many SNPs as individuals."""
-    packed = oracle.synth_packed(n, 0, m, missing_rate=0.0, seed=n + m)
+@pytest.mark.parametrize("missing", [0.0, 0.05])
+def test_low_term_modes(n, m, missing, oracle, dev):
+    """Exact-dosage path, with and without missing genotypes: the low term on the fp8 pipe (e4m3 x e4m3) stays inside the 1e-5 gate
+    for M >> N, M ~ N and M << N; the fp16 low term lands near 1e-6; 'auto' picks fp8 when a call has at least as many SNPs as
+    individuals (4 x as many for Beta).  The mode is a per-call argument; the process-wide default only feeds 'default'."""
+    packed = oracle.synth_packed(n, 0, m, missing_rate=missing, seed=n + m)
     store = dev.PackedStore.from_host(packed, n)
     assert dev.get_syrk_low_term() == "auto"
+    errs = {}
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        ref, _ = oracle.read_kernel(packed, n, **args)
+        for mode in ("fp16", "fp8", "auto", "default"):
+            K, _ = dev.snp_kernel(store, standardizer=std, chunk=256, low_term=mode)
+            Kc = K.double().cpu().numpy()
+            assert np.array_equal(Kc, Kc.T)
+            errs[(std[0], mode)] = rel_fro(Kc, ref)
+    assert all(e < K_TOL for e in errs.values()), errs
+    assert all(errs[(s, "fp16")] < 3e-6 for s in ("unit", "beta")), errs
+    for s, need in (("unit", n), ("beta", 4 * n)):
+        want_auto = "fp8" if m >= need else "fp16"
+        assert errs[(s, "auto")] == errs[(s, want_auto)] == errs[(s, "default")], errs
+        assert dev.low_term_for(m, n, (s,)) == want_auto
+    assert dev.low_term_for(10 * n, n) == "fp8"                             # a sharded kernel with many SNPs in total
     try:
-        errs = {}
-        for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
-            ref, _ = oracle.read_kernel(packed, n, **args)
-            for mode in ("fp16", "fp8", "auto"):
-                assert dev.set_syrk_low_term(mode) in ("fp16", "fp8", "auto")
-                K, _ = dev.snp_kernel(store, standardizer=std, chunk=256)
-                Kc = K.double().cpu().numpy()
-                assert np.array_equal(Kc, Kc.T)
-                errs[(std[0], mode)] = rel_fro(Kc, ref)
-        assert all(e < K_TOL for e in errs.values()), errs
-        assert all(errs[(s, "fp16")] < 3e-6 for s in ("unit", "beta")), errs
-        want_auto = "fp8" if m >= n else "fp16"
-        assert all(errs[(s, "auto")] == errs[(s, want_auto)] for s in ("unit", "beta")), errs
+        assert dev.set_syrk_low_term("fp16") == "auto"                      # the process default feeds 'default' only
+        K, _ = dev.snp_kernel(store, chunk=256)
+        assert rel_fro(K.double().cpu().numpy(), oracle.read_kernel(packed, n)[0]) == errs[("unit", "fp16")]
+        K, _ = dev.snp_kernel(store, chunk=256, low_term="fp8")
+        assert rel_fro(K.double().cpu().numpy(), oracle.read_kernel(packed, n)[0]) == errs[("unit", "fp8")]
     finally:
         dev.set_syrk_low_term("auto")
-    with dev.syrk_low_term_for(10 * n, n):                                   # a sharded kernel with many SNPs in total
-        assert dev.get_syrk_low_term() == "fp8"
-    assert dev.get_syrk_low_term() == "auto"
+
+
+def test_exact_dosage_path_with_missing_and_trained_stats(oracle, dev, monkeypatch):
+    """Round 2: chunks with missing genotypes and trained statistics take the 2-term exact-dosage GEMM (missing entries of the left
+    plane hold fp16(mu - mu'), so mean imputation stays exact).  Checks: the heavy-missing case against the float64 oracle, that
+    the result differs from the forced 3-term split only by rounding, trained statistics of another iid set, an all-missing SNP,
+    an SNC SNP, and a trained mean outside [0, 2] (falls back to the 3-term split on the device)."""
+    n, m = 900, 1400
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.3, seed=11)
+    packed[5, :] = 0x55                                                     # SNP 5: every genotype missing
+    packed[9, :] = 0x00                                                     # SNP 9: constant (SNC)
+    store = dev.PackedStore.from_host(packed, n)
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        ref, rst = oracle.read_kernel(packed, n, **args)
+        for lt in ("fp16", "fp8"):
+            K, st = dev.snp_kernel(store, standardizer=std, chunk=512, low_term=lt)
+            Kc = K.double().cpu().numpy()
+            assert not np.isnan(Kc).any() and np.array_equal(Kc, Kc.T)
+            assert rel_fro(Kc, ref) < (3e-6 if lt == "fp16" else K_TOL), (std, lt, rel_fro(Kc, ref))
+        np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12, equal_nan=True)
+    # trained statistics from a different iid subset, applied to the other individuals (UnitTrained, unittrained.py:47-70)
+    train, test = np.arange(0, 600), np.arange(600, n)
+    _, st_train = oracle.read_kernel(packed, n, iid_index=train)
+    x_t, _ = oracle.standardize(oracle.decode(packed, n, test), use_stats=True, stats=st_train)
+    ref_t = x_t @ x_t.T
+    Kt, _ = dev.snp_kernel(store, test, None, stats=st_train, chunk=512, low_term="fp16")
+    assert rel_fro(Kt.double().cpu().numpy(), ref_t) < 3e-6
+    # the forced 3-term split agrees
+    monkeypatch.setenv("PSTB_SYRK_3TERM", "1")
+    K3, _ = dev.snp_kernel(store, chunk=512)
+    monkeypatch.delenv("PSTB_SYRK_3TERM")
+    K2, _ = dev.snp_kernel(store, chunk=512, low_term="fp16")
+    ref, _ = oracle.read_kernel(packed, n)
+    assert rel_fro(K3.double().cpu().numpy(), ref) < 3e-6 and rel_fro(K2.double().cpu().numpy(), K3.double().cpu().numpy()) < 3e-6
+    # a trained mean outside [0, 2] cannot be centred exactly in fp16: that chunk takes the 3-term split, the others do not
+    st_odd = oracle.read_kernel(packed, n)[1].copy()
+    st_odd[700] = (3.75, 0.5)
+    st_odd[20] = (-0.3, 2.0)
+    x_o, _ = oracle.standardize(oracle.decode(packed, n), use_stats=True, stats=st_odd)
+    ref_o = x_o @ x_o.T
+    Ko, _ = dev.snp_kernel(store, stats=st_odd, chunk=512, low_term="fp8")
+    assert rel_fro(Ko.double().cpu().numpy(), ref_o) < K_TOL
+
+
+def test_low_term_is_per_call_under_threads(oracle, dev):
+    """Two Python threads run kernels with different per-call modes at the same time (the C ABI promises concurrent callers on
+    different streams): every result equals the single-threaded result of its own mode bit for bit."""
+    import threading
+    import torch
+    n, m = 600, 2048
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.02, seed=3)
+    store = dev.PackedStore.from_host(packed, n)
+    want = {lt: dev.snp_kernel(store, chunk=256, low_term=lt)[0].cpu().numpy() for lt in ("fp16", "fp8")}
+    assert not np.array_equal(want["fp16"], want["fp8"])
+    torch.cuda.synchronize()
+    bad = []
+
+    def worker(lt):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(6):
+                K, _ = dev.snp_kernel(store, chunk=256, low_term=lt)
+                s.synchronize()
+                if not np.array_equal(K.cpu().numpy(), want[lt]):
+                    bad.append(lt)
+
+    th = [threading.Thread(target=worker, args=(lt,)) for lt in ("fp16", "fp8")]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not bad, bad

@@ -278,21 +278,20 @@ def test_assign_pieces_balances_and_partitions():
 
 
 def test_syrk_low_term_switch_needs_no_gpu():
-    """pstb_set_syrk_low_term / the context manager sharded callers use: process-wide mode, 'auto' resolved with the whole kernel's SNP count."""
+    """The low-term mode is a per-call argument of the kernel entry points; `low_term_for` resolves 'auto' with the SNP count of a
+    whole (sharded) kernel without touching process-wide state; pstb_set_syrk_low_term only changes the default."""
     from pysnptools_b200 import device as dev
     start = dev.get_syrk_low_term()
     try:
         dev.set_syrk_low_term("auto")
-        with dev.syrk_low_term_for(500_000, 50_000):
-            assert dev.get_syrk_low_term() == "fp8"
-        assert dev.get_syrk_low_term() == "auto"
-        with dev.syrk_low_term_for(100_000, 500_000):                      # fewer SNPs than individuals: fp16
-            assert dev.get_syrk_low_term() == "fp16"
-        with dev.syrk_low_term_for(100, 10):                               # too few SNPs to average the e4m3 rounding out
-            assert dev.get_syrk_low_term() == "fp16"
+        assert dev.low_term_for(500_000, 50_000) == "fp8"
+        assert dev.get_syrk_low_term() == "auto"                           # nothing global changed
+        assert dev.low_term_for(100_000, 500_000) == "fp16"                # fewer SNPs than individuals: fp16
+        assert dev.low_term_for(100, 10) == "fp16"                         # too few SNPs to average the e4m3 rounding out
+        assert dev.low_term_for(150_000, 50_000, ("beta", 1, 25)) == "fp16"   # Beta weights concentrate on rare SNPs: 4 x as many
+        assert dev.low_term_for(250_000, 50_000, ("beta", 1, 25)) == "fp8"
         assert dev.set_syrk_low_term("fp16") == "auto"
-        with dev.syrk_low_term_for(500_000, 50_000):                       # an explicit choice is left alone
-            assert dev.get_syrk_low_term() == "fp16"
+        assert dev.low_term_for(500_000, 50_000) == "fp16"                 # an explicit process-wide default is respected
         assert dev.get_syrk_low_term() == "fp16"
         with pytest.raises(KeyError):
             dev.set_syrk_low_term("bf16")

@@ -100,6 +100,10 @@ bool is_pinned(const void* p) {
 // pageable destinations: copy out of the pinned ring with several host threads (a single memcpy stream tops out near
 // 10 GB/s and first-touch page faults of a fresh NumPy array are serial otherwise)
 int host_copy_threads() {
+    if (const char* e = getenv("PSTB_HOST_COPY_THREADS")) {          // experiments
+        const int v = atoi(e);
+        if (v >= 1 && v <= 256) return v;
+    }
     static int n = [] {
         unsigned hc = std::thread::hardware_concurrency();
         int v = hc ? (int)hc / 2 : 4;                    // measured: 8 of 16 cores 1.96 s for a fresh 40 GB result, 14 cores 2.7 s
@@ -165,6 +169,17 @@ int make_axis(const int64_t* h_idx, int64_t n, int64_t count, const char* name, 
 
 using namespace pstb;
 
+
+// Host -> device upload that is COMPLETE when it returns: cudaMemcpyAsync on one of the context's (non-blocking) streams followed by a
+// stream synchronize.  A blocking cudaMemcpy on the legacy default stream may return once a pageable source has been staged, before the
+// DMA lands, and non-blocking streams do not synchronise with the legacy stream (round-1 advisor finding).
+static int upload_sync(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return 0;
+    PSTB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    PSTB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
                               int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
                               int use_stats, double* h_stats, void* h_out, int dtype, int order) {
@@ -201,7 +216,7 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
     const bool any_stats = mode != PSTB_STD_NONE;
     if (any_stats) {
         if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
-        if (use_stats) PSTB_CUDA(cudaMemcpy(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice));
+        if (use_stats && upload_sync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), c.s[0])) return 1;
     }
     for (int k = 0; k < kSlots; ++k) {
         if (c.d_packed[k].ensure((size_t)chunk * ld) || c.d_out[k].ensure((size_t)chunk * col_bytes)) return 1;
@@ -230,6 +245,13 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
 
     int rc = 0;
     int64_t nchunks = (n_sid + chunk - 1) / chunk;
+    // a failure inside the pipelined loop leaves through the drain below (every slot finished, device synchronised): no async copy
+    // into the caller's buffers may still be in flight when the error is returned
+#define PSTB_CUDA_BREAK(x)                                                                       \
+    {                                                                                            \
+        cudaError_t e__ = (x);                                                                   \
+        if (e__ != cudaSuccess) { rc = pstb::fail("%s -> %s", #x, cudaGetErrorString(e__)); break; } \
+    }
     for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
         const int slot = (int)(ch % kSlots);
         const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
@@ -242,15 +264,15 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         if (contiguous && packed_pinned) {
             // one contiguous DMA over PCIe (rows of ceil(N/4) bytes make a slow 2-D copy), then re-pitch to ld on the device
             if (ld == rec) {
-                PSTB_CUDA(cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
+                PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
             } else {
-                if (c.d_tight[slot].ensure((size_t)chunk * rec)) return 1;
-                PSTB_CUDA(cudaMemcpyAsync(c.d_tight[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
-                PSTB_CUDA(cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns,
+                if (c.d_tight[slot].ensure((size_t)chunk * rec)) { rc = 1; break; }
+                PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_tight[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
+                PSTB_CUDA_BREAK(cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns,
                                             cudaMemcpyDeviceToDevice, st));
             }
         } else {
-            if (c.h_in[slot].ensure((size_t)chunk * ld)) return 1;
+            if (c.h_in[slot].ensure((size_t)chunk * ld)) { rc = 1; break; }
             char* stage = (char*)c.h_in[slot].p;
             parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) {
                 for (size_t k = lo; k < hi; ++k) {
@@ -258,7 +280,7 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
                     memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
                 }
             });
-            PSTB_CUDA(cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
+            PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
         }
         // ---- kernel ----
         pstb_axis sid_ax{nullptr, 0, 1, ns};
@@ -269,18 +291,19 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         // ---- output ----
         if (order == PSTB_ORDER_F) {
             void* dst = out_pinned ? (void*)((char*)h_out + (size_t)b0 * col_bytes) : c.h_out[slot].p;
-            PSTB_CUDA(cudaMemcpyAsync(dst, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
+            PSTB_CUDA_BREAK(cudaMemcpyAsync(dst, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
         } else if (out_pinned) {
-            PSTB_CUDA(cudaMemcpy2DAsync((char*)h_out + (size_t)b0 * es, (size_t)n_sid * es, c.d_out[slot].p, (size_t)ns * es,
+            PSTB_CUDA_BREAK(cudaMemcpy2DAsync((char*)h_out + (size_t)b0 * es, (size_t)n_sid * es, c.d_out[slot].p, (size_t)ns * es,
                                         (size_t)ns * es, (size_t)n_iid, cudaMemcpyDeviceToHost, st));
         } else {
-            PSTB_CUDA(cudaMemcpyAsync(c.h_out[slot].p, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
+            PSTB_CUDA_BREAK(cudaMemcpyAsync(c.h_out[slot].p, c.d_out[slot].p, (size_t)ns * col_bytes, cudaMemcpyDeviceToHost, st));
         }
-        PSTB_CUDA(cudaEventRecord(c.done[slot], st));
+        PSTB_CUDA_BREAK(cudaEventRecord(c.done[slot], st));
         pend[slot].b0 = b0;
         pend[slot].ns = ns;
         pend[slot].active = true;
     }
+#undef PSTB_CUDA_BREAK
     for (int k = 0; k < kSlots; ++k) {
         int r2 = finish(k);
         if (!rc) rc = r2;
@@ -306,7 +329,7 @@ extern "C" int pstb_standardize_host(void* h_val, int dtype, int order, int64_t 
     const size_t es = esize_of(dtype);
     if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
     if (c.d_work.ensure((size_t)pstb_standardize_work_bytes(n_sid))) return 1;
-    if (use_stats) PSTB_CUDA(cudaMemcpy(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    if (use_stats && upload_sync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), c.s[0])) return 1;
     const size_t col_bytes = (size_t)n_iid * es;
     if (order == PSTB_ORDER_C || col_bytes == 0) {
         // C order: statistics need whole columns, i.e. the whole matrix resident

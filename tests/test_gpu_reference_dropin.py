@@ -46,10 +46,10 @@ def ref():
     pr.PstReader._process_ndarray = staticmethod(_process_ndarray)
     ns = types.SimpleNamespace()
     from pysnptools.snpreader import Bed, SnpData
-    from pysnptools.standardizer import Unit, Beta, DiagKtoN
+    from pysnptools.standardizer import Unit, Beta, DiagKtoN, Identity
     from pysnptools.kernelreader import SnpKernel
     import pysnptools.util as pstutil
-    ns.Bed, ns.SnpData, ns.Unit, ns.Beta, ns.DiagKtoN, ns.SnpKernel, ns.util = Bed, SnpData, Unit, Beta, DiagKtoN, SnpKernel, pstutil
+    ns.Bed, ns.SnpData, ns.Unit, ns.Beta, ns.DiagKtoN, ns.SnpKernel, ns.util, ns.Identity = Bed, SnpData, Unit, Beta, DiagKtoN, SnpKernel, pstutil, Identity
     assert "baseline" in sys.modules["pysnptools"].__file__
     yield ns
     for p in added:
@@ -300,3 +300,113 @@ def test_reference_unit_test(ref, ref_examples, module, cls, name):
     problems = result.failures + result.errors
     assert not problems, problems[0][1]
     assert result.testsRun == 1
+
+
+# ---- patch_reference(): the reference's own SnpKernel(...).read() / read_kernel on the tensor cores ---------------------------------
+@pytest.fixture()
+def patched(ref):
+    from pysnptools_b200.compat import patch
+    patch.patch_reference(float64="tensor")
+    yield patch
+    patch.unpatch_reference()
+
+
+def test_patched_reference_read_kernel_runs_on_the_gpu(ref, patched, golden):
+    """SnpReader._read_kernel (snpreader.py:623-668) of the UNMODIFIED reference, rebound by patch_reference(): Bed / nested subsets /
+    Unit / Beta / trained / Identity go through pstb_snp_kernel_host (k_syrk2).  Values against the goldens the reference itself
+    produced (<= 1e-5 relative Frobenius, the north_star gate), statistics to 1e-9, and the launch counter proves where it ran."""
+    bed = ref.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    l0, s0 = patched.launches(), patched.stats()
+    for dtype in (np.float64, np.float32):
+        for order in ("A", "C", "F"):
+            K = bed.read_kernel(ref.Unit(), block_size=100, order=order, dtype=dtype)
+            assert K.val.dtype == dtype and (order == "A" or K.val.flags["C_CONTIGUOUS" if order == "C" else "F_CONTIGUOUS"])
+            assert rel_fro(K.val, golden["n300_unit_K"]) < 1e-5 and np.array_equal(K.val, K.val.T)
+            assert np.array_equal(K.iid, bed.iid)
+    assert patched.launches() > l0 and patched.stats()["fused"] == s0["fused"] + 6 and patched.stats()["reference"] == s0["reference"]
+    Kb = ref.SnpKernel(bed, ref.Beta(1, 25), block_size=333).read().val
+    assert rel_fro(Kb, golden["n300_beta_1_25_K"]) < 1e-5
+    toy = ref.Bed(os.path.join(DATA_DIR, "toydata.bed"), count_A1=False)
+    Kt = ref.SnpKernel(toy, ref.Unit(), block_size=2500).read().val
+    assert rel_fro(Kt, golden["toydata_unit_K_shipped"]) < 1e-5
+    kd = ref.SnpKernel(toy, ref.Unit()).read().standardize(ref.DiagKtoN())
+    assert abs(kd.val[0, 0] - float(golden["toydata_unit_K_diagKtoN_00"])) < 1e-5 and abs(np.trace(kd.val) - 500) < 1e-6
+    # _read_with_standardizing (snpkernel.py:104-132): the trained standardizer equals what Unit._merge_trained would build
+    kdata, trained, ktrained = ref.SnpKernel(bed[10:, :], ref.Unit(), block_size=200)._read_with_standardizing(to_kerneldata=True, return_trained=True)
+    assert type(trained).__name__ == "UnitTrained" and np.array_equal(trained.sid, bed.sid)
+    assert np.allclose(trained.stats, golden["n300_trained_unit_stats"], rtol=1e-9)
+    # nested subsets with negative steps, boolean masks and repeats resolve to one gathered call; trained statistics are applied
+    sub = bed[::-2, :][3:120, 5:900:3]
+    want = sub.read().standardize(ref.Unit()).val
+    want = want.dot(want.T)
+    got = sub.read_kernel(ref.Unit()).val
+    assert rel_fro(got, want) < 1e-5
+    test_part = bed[:10, :]
+    xt = test_part.read().standardize(trained).val
+    assert rel_fro(test_part.read_kernel(trained).val, xt.dot(xt.T)) < 1e-5
+    # Identity on data WITHOUT missing values == dosage dot product
+    raw = bed[:50, :200].read().val
+    assert rel_fro(bed[:50, :200].read_kernel(ref.Identity()).val, raw.dot(raw.T)) < 1e-5
+    # what the patch leaves alone: force_python_only (the reference's pure-Python route; answered here by its own code)
+    before = patched.stats()["reference"]
+    d = bed[:20, :30].read()
+    d.read_kernel(ref.Unit())                                           # in-memory SnpData with a standardizer -> reference loop -> GPU GEMM
+    assert patched.stats()["reference"] > before and patched.stats()["float"] > s0["float"]
+
+
+def test_patched_reference_distributed_bed_and_snpdata(ref, patched, golden):
+    from pysnptools.snpreader import DistributedBed
+    dbed = DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1"))
+    x = dbed.read().standardize(ref.Unit()).val
+    s0 = patched.stats()
+    K = dbed.read_kernel(ref.Unit(), block_size=30).val
+    assert patched.stats()["pieces"] == s0["pieces"] + 1
+    assert rel_fro(K, x.dot(x.T)) < 1e-5 and np.array_equal(K, K.T)
+    sub = dbed[::2, 10:90]
+    xs = sub.read().standardize(ref.Beta(1, 25)).val
+    assert rel_fro(sub.read_kernel(ref.Beta(1, 25)).val, xs.dot(xs.T)) < 1e-5
+    # SnpData._read_kernel (snpdata.py:190-214): val.dot(val.T) on the tensor cores, C and F order, float32 and float64
+    rng = np.random.default_rng(5)
+    for order in ("C", "F"):
+        for dtype in (np.float32, np.float64):
+            val = np.array(rng.standard_normal((130, 777)), dtype=dtype, order=order)
+            sd = ref.SnpData(iid=[["f", str(i)] for i in range(130)], sid=[str(j) for j in range(777)], val=val)
+            Kd = sd.read_kernel(ref.Identity(), dtype=dtype).val
+            assert Kd.dtype == dtype and rel_fro(Kd.astype(np.float64), val.astype(np.float64).dot(val.astype(np.float64).T)) < 1e-5
+    assert patched.stats()["float"] >= s0["float"] + 4
+
+
+# The reference's own kernel tests on the PATCHED reference.  Three of them compare two float64 kernels to 10 decimals
+# (kernelreader/test.py:48-50, :189; test.py:535-553): that is float64 arithmetic, which the tensor-core path (fp32 accumulation,
+# north_star gate 1e-5) cannot meet -- they are expected to fail in "tensor" mode and are listed as such, not hidden.
+TOLERANCE_BOUND = {"test_merge_std", "test_respect_inputs", "test_some_std"}
+PATCHED_TESTS = [t for t in REF_UNIT_TESTS if t[1] == "TestKernelReader"] + [("pysnptools.test", "TestPySnpTools", "test_some_std"),
+                                                                              ("pysnptools.test", "TestPySnpTools", "test_diagKtoN")]
+
+
+@pytest.mark.parametrize("module,cls,name", PATCHED_TESTS, ids=["patched-" + t[2] for t in PATCHED_TESTS])
+def test_reference_kernel_tests_on_patched_reference(ref, ref_examples, ref_main_tests, patched, module, cls, name):
+    import importlib
+    import unittest
+    mod = importlib.import_module(module)
+    case_cls = getattr(mod, cls)
+    if name not in unittest.defaultTestLoader.getTestCaseNames(case_cls):
+        pytest.skip("{0}.{1} has no {2} in this reference version".format(module, cls, name))
+    l0 = patched.launches()
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(mod.__file__))
+    try:
+        result = unittest.TestResult()
+        unittest.TestSuite([case_cls(name)]).run(result)
+    finally:
+        os.chdir(cwd)
+    problems = result.failures + result.errors
+    if name in TOLERANCE_BOUND:
+        assert problems and "Arrays are not almost equal to 10 decimals" in problems[0][1], (
+            "expected ONLY the 10-decimal float64 comparison to fail on the fp32-accumulating tensor-core path: " + (problems[0][1] if problems else "passed"))
+        assert patched.launches() > l0
+        pytest.xfail("compares float64 kernels to 10 decimals; the tensor-core path accumulates in fp32 (gate: 1e-5 relative Frobenius)")
+    assert not problems, problems[0][1]
+    assert result.testsRun == 1
+    if name in ("test_subset", "test_npz"):
+        assert patched.launches() > l0, "the kernel of this test should have run on the GPU"

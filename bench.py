@@ -111,6 +111,124 @@ def cpu_kernel_baseline(lib, n_iid, sample_sid, threads):
             "float64_value": f64, "float64_note": "the reference's default dtype (K float64), block of {0} SNPs, {1:.2f} s".format(max(64, sample_sid // 2), t64)}
 
 
+class limit_threads(object):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU checker / baseline legs get their share of the host cores back."""
+
+    def __init__(self, threads):
+        self.threads, self.limiter = threads, None
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self.limiter = threadpool_limits(limits=self.threads)
+        except Exception:
+            self.limiter = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.limiter is not None:
+            self.limiter.restore_original_limits()
+        return False
+
+
+def oracle_rows(lib, store, stats, n, block, spec, threads):
+    """The CPU oracle's standardized values of the 256 individuals of row block `block` for every SNP of this rank's store:
+    float64 [cnt, m_local] (C order).  256 aligned individuals are 64 contiguous bytes of every packed record."""
+    lo_b = block * 64
+    cnt = min(n, block * 256 + 256) - block * 256
+    sub = np.ascontiguousarray(store.tensor[:, lo_b:lo_b + (cnt + 3) // 4].contiguous().cpu().numpy())
+    m_local = sub.shape[0]
+    x = np.empty((cnt, m_local), dtype=np.float64)
+    p = ctypes.c_void_p
+    lib.pst_oracle_decode_f64(p(sub.ctypes.data), ctypes.c_int64(sub.shape[1]), ctypes.c_int64(cnt), ctypes.c_int64(m_local), None, ctypes.c_int64(cnt),
+                              None, ctypes.c_int64(m_local), 0, 1, p(x.ctypes.data), threads)
+    is_beta = spec[0] == "beta"
+    a, b = (float(spec[1]), float(spec[2])) if is_beta else (float("nan"), float("nan"))
+    lib.pst_oracle_standardize_f64(p(x.ctypes.data), ctypes.c_int64(cnt), ctypes.c_int64(m_local), 1, int(is_beta), ctypes.c_double(a), ctypes.c_double(b),
+                                   1, p(stats.ctypes.data), threads)
+    return x
+
+
+def sampled_tile_parity(torch, dist, world, rank, lib_o, store, stats_t, n, spec, fetch_tile, blocks, owner_of=None):
+    """K against the CPU oracle on sampled 256 x 256 tiles: every pair (I, J), I >= J, of the row blocks in `blocks` (diagonal tiles
+    included), over ALL SNPs of the kernel.  Every rank builds the float64 reference of its own SNP shard (oracle/c decode +
+    standardize with the statistics of the GPU run -- themselves checked against the oracle on the shard's first SNPs at full N --
+    then a NumPy float64 GEMM); the partial references are summed over the ranks.  fetch_tile(I, J) returns the GPU result tile as a
+    float64 array, or None when another rank holds it (K-tile sharding: owner_of(I, J) says which).
+    Returns per-tile relative Frobenius errors, a stratified estimate for the whole matrix, and the relative bias of the diagonal."""
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    stats = np.ascontiguousarray(stats_t.cpu().numpy())
+    m_local = stats.shape[0]
+    rec = (n + 3) // 4
+    head = min(64, m_local)
+    if head:
+        packed_head = np.ascontiguousarray(store.tensor[:head, :rec].contiguous().cpu().numpy())
+        full = np.empty((n, head), dtype=np.float64, order="F")
+        st_ref = np.empty((head, 2), dtype=np.float64)
+        p = ctypes.c_void_p
+        lib_o.pst_oracle_decode_f64(p(packed_head.ctypes.data), ctypes.c_int64(rec), ctypes.c_int64(n), ctypes.c_int64(head), None, ctypes.c_int64(n),
+                                    None, ctypes.c_int64(head), 0, 0, p(full.ctypes.data), threads)
+        is_beta = spec[0] == "beta"
+        a, b = (float(spec[1]), float(spec[2])) if is_beta else (float("nan"), float("nan"))
+        lib_o.pst_oracle_standardize_f64(p(full.ctypes.data), ctypes.c_int64(n), ctypes.c_int64(head), 0, int(is_beta), ctypes.c_double(a), ctypes.c_double(b),
+                                         0, p(st_ref.ctypes.data), threads)
+        stats_ok = bool(np.allclose(stats[:head], st_ref, rtol=1e-12, equal_nan=True))
+        del full
+    else:
+        stats_ok = True
+    pairs = [(I, J) for a_, I in enumerate(blocks) for J in blocks[: a_ + 1]]
+    pairs = [(max(I, J), min(I, J)) for I, J in pairs]
+    with limit_threads(threads):
+        rows = {b: oracle_rows(lib_o, store, stats, n, b, spec, threads) for b in blocks}
+        ref = np.zeros((len(pairs), 256, 256), dtype=np.float64)
+        for t, (I, J) in enumerate(pairs):
+            r = rows[I].dot(rows[J].T)
+            ref[t, : r.shape[0], : r.shape[1]] = r
+    del rows
+    if world > 1:
+        ref_t = torch.from_numpy(ref).cuda()
+        dist.all_reduce(ref_t)
+        ok_t = torch.tensor([1.0 if stats_ok else 0.0], device="cuda")
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        stats_ok = bool(ok_t.item() > 0.5)
+        ref = ref_t.cpu().numpy()
+        del ref_t
+    # per-tile errors where the tile lives; with K-tile sharding the partial sums are combined over the ranks
+    acc = np.zeros((len(pairs), 4), dtype=np.float64)                   # diff^2, ref^2, sum of relative diagonal error, diagonal count
+    for t, (I, J) in enumerate(pairs):
+        got = fetch_tile(I, J)
+        if got is None:
+            continue
+        ri, rj = min(n, I * 256 + 256) - I * 256, min(n, J * 256 + 256) - J * 256
+        d = got[:ri, :rj] - ref[t, :ri, :rj]
+        acc[t, 0], acc[t, 1] = float((d * d).sum()), float((ref[t, :ri, :rj] ** 2).sum())
+        if I == J:
+            dg = np.diagonal(ref[t, :ri, :ri])
+            acc[t, 2], acc[t, 3] = float((np.diagonal(d) / np.where(dg != 0, dg, 1.0)).sum()), ri
+    if world > 1 and owner_of is not None:
+        acc_t = torch.from_numpy(acc).cuda()
+        dist.all_reduce(acc_t)
+        acc = acc_t.cpu().numpy()
+    per_tile = np.sqrt(acc[:, 0] / np.maximum(acc[:, 1], 1e-300))
+    diag = np.array([I == J for I, J in pairs])
+    T = (n + 255) // 256
+    # whole-matrix estimate: T diagonal tiles + T (T - 1) off-diagonal ones (both triangles), each stratum scaled from its sample
+    def stratum(mask, population):
+        k = int(mask.sum())
+        return (acc[mask, 0].sum() * population / k, acc[mask, 1].sum() * population / k) if k else (0.0, 0.0)
+    d2a, r2a = stratum(diag, T)
+    d2b, r2b = stratum(~diag, T * (T - 1))
+    whole = float(np.sqrt((d2a + d2b) / max(r2a + r2b, 1e-300)))
+    return {"sampled_tiles": len(pairs), "row_blocks": [int(b) for b in blocks], "diagonal_tiles": int(diag.sum()),
+            "worst_rel_frobenius_vs_oracle": float(per_tile.max()),
+            "worst_rel_frobenius_diagonal_tile": float(per_tile[diag].max()) if diag.any() else None,
+            "worst_rel_frobenius_off_diagonal_tile": float(per_tile[~diag].max()) if (~diag).any() else None,
+            "rel_frobenius_whole_K_estimate": whole,
+            "diag_rel_bias": float(acc[diag, 2].sum() / max(1.0, acc[diag, 3].sum())) if diag.any() else None,
+            "stats_match_oracle_rtol_1e-12": stats_ok, "gate": 1e-5,
+            "oracle": "oracle/c decode + standardize (float64, the GPU run's statistics, checked on each shard's first 64 SNPs at full N) + NumPy float64 GEMM over ALL SNPs"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -227,8 +345,9 @@ def gen_store_device(dev, torch, n_iid, n_sid, seed, missing_rate=0.0):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from pysnptools_b200 import _lib, device as dev
+    from pysnptools_b200 import _lib, device as dev, parallel
     lib = _lib.lib
+    globals()["parallel"] = parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -265,7 +384,12 @@ def run_gpu(args):
         return float(t.item())
 
     if args.cfg5:
-        res = run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        res = run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks)
         if rank == 0:
             print(json.dumps(res))
         if world > 1:
@@ -362,14 +486,28 @@ def run_gpu(args):
     if args.e2e:
         e2e = run_e2e(args, torch, lib, _lib, store, stats, n_iid, n_sid, rec, world, rank, barrier, max_over_ranks)
     api_e2e = None
-    if args.api_e2e and rank == 0:
+    if args.api_e2e and rank == 0 and world == 1:
         api_e2e = run_api_e2e(torch, store, n_iid, n_sid, rec)
+    # ---- the other BASELINE configurations (single-GPU legs run at N = 1 only; cfg5 needs the memory of 8 GPUs) ----
+    c_order = gather = kernel_missing = cfg5 = None
+    if args.extra_legs and world == 1:
+        c_order = run_c_order_leg(args, torch, dev, _lib, peaks, store, out)
     del out, store, stats
     torch.cuda.empty_cache()
+    if args.extra_legs and world == 1:
+        gather = run_gather_leg(args, torch, dev, _lib, peaks)
     # ---- SnpKernel (cfg3) ----
     kernel = None
     if args.kernel:
         kernel = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler)
+        if args.extra_legs:
+            # the same kernel on data WITH missing genotypes (5 %, like cfg4) and Beta(1,25): round 1 fell back to the 3-term split here
+            kernel_missing = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler, n=args.kernel_n,
+                                                 m=args.kernel_missing_m, missing=0.05, spec=("unit",), label="cfg3 shape with missing data", with_e2e=False, with_cpu=False)
+            kernel_missing["beta"] = run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, None, n=args.kernel_n,
+                                                         m=args.kernel_missing_m, missing=0.05, spec=("beta", 1, 25), label="cfg3 shape with missing data", with_e2e=False, with_cpu=False)
+    if args.extra_legs and world >= 8:
+        cfg5 = run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks)
     if sampler:
         sampler.close()
 
@@ -389,6 +527,9 @@ def run_gpu(args):
             line["kernel"] = kernel
         if api_e2e is not None:
             line["e2e_python_api"] = api_e2e
+        for key, val in (("kernel_missing", kernel_missing), ("gather", gather), ("c_order", c_order), ("cfg5", cfg5)):
+            if val is not None:
+                line[key] = val
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -483,11 +624,26 @@ def run_api_e2e(torch, store, n_iid, n_sid, rec):
             "into_pinned_out": {"value": n_iid * n_sid / min(tp), "seconds": tp, "api": "the same call with out=pinned_empty(...)"}}
 
 
-def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler=None):
-    """cfg3: SnpKernel(Unit) on 50 000 x 500 000, SNP-sharded over the ranks, one NCCL all-reduce of K."""
-    n, m = (args.kernel_n, args.kernel_m)
+def pick_blocks(n, count, seed):
+    """`count` distinct 256-row blocks: the first, the last (ragged) one and a seeded random choice of the others."""
+    T = (n + 255) // 256
+    count = min(count, T)
+    rng = np.random.default_rng(seed)
+    chosen = {0, T - 1}
+    for b in rng.permutation(T):
+        if len(chosen) >= count:
+            break
+        chosen.add(int(b))
+    return sorted(chosen)
+
+
+def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks, sampler=None, n=None, m=None,
+                        missing=0.0, spec=("unit",), label="cfg3", with_e2e=True, with_cpu=True):
+    """SnpKernel on n x m (default cfg3: 50 000 x 500 000, Unit), SNP-sharded over the ranks, one NCCL all-reduce of K; the result is
+    compared with the CPU oracle on sampled 256 x 256 tiles (after the all-reduce at N > 1)."""
+    n, m = (n or args.kernel_n, m or args.kernel_m)
     m_lo, m_hi = rank * m // world, (rank + 1) * m // world
-    store = gen_store_device(dev, torch, n, m_hi - m_lo, seed=2000 + rank)
+    store = gen_store_device(dev, torch, n, m_hi - m_lo, seed=2000 + rank + (7000 if missing else 0), missing_rate=missing)
     K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
     chunk = args.kernel_chunk
     # N GPUs: the partial kernels live in compact lower-triangular tile storage, so the all-reduce moves the triangle only
@@ -495,16 +651,24 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     tiles = torch.zeros((len(dev.kernel_tile_coords(n)), 256, 256), dtype=torch.float32, device="cuda") if compact else None
 
     marks = []
-
-    low_term = dev.low_term_for(m, n)                             # SNP shards: the low-term mode follows the whole kernel's SNP count
+    low_term = dev.low_term_for(m, n, spec)                       # SNP shards: the low-term mode follows the whole kernel's SNP count
+    stats_box = [None]
 
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
+        if compact and not args.serial_allreduce:
+            # the NCCL all-reduce of finished tile bands runs on a side stream under the last SNP chunk's multiplication
+            _k, stats_box[0] = parallel.snp_kernel_sharded_overlapped(store, n, m, None, spec, chunk=chunk, tiles=tiles, K=K,
+                                                                      bands=args.allreduce_bands, reserve_sms=args.allreduce_sms)
+            for e in ev[1:]:
+                e.record()
+            marks.append(ev)
+            return
         if compact:
-            dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
+            _t, _c, stats_box[0] = dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term, standardizer=spec)
         else:
-            dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1), low_term=low_term)
+            _k, stats_box[0] = dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1), low_term=low_term, standardizer=spec)
         ev[1].record()
         if compact:
             dist.all_reduce(tiles)                                                   # sum of the partial triangles over NVLink
@@ -534,38 +698,62 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     tk1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     kclocks = sampler.window(tk0, tk1) if sampler else None
+    launches = int(_lib.lib.pstb_launch_count() - l0)
     breakdown = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
                  "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
                  "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
-                 "allreduce": ("compact lower-triangular tiles ({0:.2f} GB), expanded to the square matrix in the 'mirror' slot".format(tiles.numel() * 4 / 1e9)
+                 "allreduce": (("compact lower-triangular tiles ({0:.2f} GB) in {1} bands, all-reduced + expanded on a side stream while the last SNP chunk is multiplied "
+                                "({2} SMs left to NCCL); compute_ms is the whole overlapped step").format(tiles.numel() * 4 / 1e9, args.allreduce_bands, args.allreduce_sms)
+                               if (compact and not args.serial_allreduce) else
+                               "compact lower-triangular tiles ({0:.2f} GB), expanded to the square matrix in the 'mirror' slot".format(tiles.numel() * 4 / 1e9)
                                if compact else ("square matrix" if world > 1 else "none"))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
     diag = float(K.diagonal().double().mean().item())
-    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks, low_term) if args.e2e else None
+    # ---- parity of THIS result (every rank holds the all-reduced K) against the CPU oracle on sampled tiles ----
+    parity = None
+    if args.kernel_parity_blocks > 0:
+        blocks = pick_blocks(n, args.kernel_parity_blocks, seed=n + m)
+
+        def fetch(I, J):
+            if rank != 0:
+                return np.zeros((256, 256))
+            sub = K[I * 256:I * 256 + 256, J * 256:J * 256 + 256].double().cpu().numpy()
+            out = np.zeros((256, 256))
+            out[: sub.shape[0], : sub.shape[1]] = sub
+            return out
+        parity = sampled_tile_parity(torch, dist, world, rank, _oracle_lib(), store, stats_box[0], n, spec, fetch, blocks)
+        parity["symmetric"] = bool(torch.equal(K[:512, -512:], K[-512:, :512].t()))
+    e2e = run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_hi - m_lo, chunk, rank, world, barrier, max_over_ranks, low_term) if (args.e2e and with_e2e) else None
     cpu_baseline = None
-    if rank == 0 and world == 1 and args.kernel_cpu:
+    if rank == 0 and world == 1 and args.kernel_cpu and with_cpu:
         del K
         torch.cuda.empty_cache()
         cpu_baseline = cpu_kernel_baseline(_oracle_lib(), n, args.ref_kernel_sid, os.cpu_count() or 1)
         K = torch.zeros((1, 1), device="cuda")
     fp8lo = low_term == "fp8"
     t256 = (n + 255) // 256
-    tiles = t256 * (t256 + 1) // 2                                                 # lower-triangular 256 x 256 tiles per rank
-    # synthetic cfg3 has no missing genotypes: every chunk takes the 2-term exact-dosage GEMM (3 terms with PSTB_SYRK_3TERM=1)
+    ntiles = t256 * (t256 + 1) // 2                                                # lower-triangular 256 x 256 tiles per rank
+    # every chunk takes the 2-term exact-dosage GEMM, with or without missing genotypes (3 terms with PSTB_SYRK_3TERM=1)
     terms = 3 if os.environ.get("PSTB_SYRK_3TERM", "0") not in ("", "0") or os.environ.get("PSTB_SYRK_V1", "0") not in ("", "0") else 2
     # tensor-pipe work in fp16-equivalent terms: an fp8 (e4m3) MMA term costs half the cycles of an fp16 one
     pipe_terms = 1.5 if (terms == 2 and fp8lo) else float(terms)
-    executed = pipe_terms * 2.0 * 256 * 256 * tiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
+    executed = pipe_terms * 2.0 * 256 * 256 * ntiles * (((m_hi - m_lo) + 63) // 64 * 64) / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "e2e": e2e, "cpu_baseline": cpu_baseline, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
-            "config": {"workload": "cfg3: synthetic .bed {0} iids x {1} SNPs, SnpKernel(Unit), K fp32, SNP-sharded + NCCL allreduce".format(n, m),
-                       "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": ("exact fp16 dosage x fp16 high part of the weighted dosage + e4m3 x e4m3 low term on the fp8 pipe (1 fp16 + 1 fp8 MMA term per k-step = 1.5 fp16-equivalent terms)"
-                                 if (terms == 2 and fp8lo) else "exact fp16 dosage x fp16 hi/lo weights ({0} MMA terms per k-step)".format(terms))
-                                + "; 3-term hi/lo split when a chunk has missing data; lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2)",
-                       "low_term": "fp8" if fp8lo else "fp16"},
-            "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
-                         "note": "executed tensor-pipe work per rank in fp16-equivalent flops ({0} terms x lower-triangular tiles; an fp8 term counts half) / time; peak = MEASURED_PEAKS bf16_tflops_sustained".format(pipe_terms)},
-            "gpu_launches": int(_lib.lib.pstb_launch_count() - l0), "mean_diag_over_M": diag / m, "rank0_breakdown": breakdown, "clocks": kclocks}
+    burst = float(peaks.get("bf16_tflops", 1650.0))
+    std_name = "Unit" if spec[0] == "unit" else "Beta({0},{1})".format(spec[1], spec[2])
+    res = {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": tflops, "e2e": e2e, "cpu_baseline": cpu_baseline, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms, "steps": steps,
+           "scaling": "strong", "higher_is_better": True,
+           "config": {"workload": "{0}: synthetic .bed {1} iids x {2} SNPs, {3:.0f} % missing, SnpKernel({4}), K fp32, SNP-sharded + NCCL allreduce".format(label, n, m, 100 * missing, std_name),
+                      "chunk_snps": chunk or dev.default_kernel_chunk(n, m_hi - m_lo), "split": ("exact fp16 left plane (g - mu', missing -> mu - mu') x fp16 high part of the weighted centred value + e4m3 x e4m3 low term on the fp8 pipe (1 fp16 + 1 fp8 MMA term per k-step = 1.5 fp16-equivalent terms)"
+                                if (terms == 2 and fp8lo) else "exact fp16 left plane x fp16 hi/lo right plane ({0} MMA terms per k-step)".format(terms))
+                               + "; lower-triangular 256x256 tiles on CTA pairs (tcgen05 cta_group::2); K leaves through TMA bulk tensor store / reduce-add",
+                      "low_term": "fp8" if fp8lo else "fp16"},
+           "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak, "frac_of_burst_peak": executed / burst,
+                        "note": "executed tensor-pipe work per rank in fp16-equivalent flops ({0} terms x lower-triangular tiles; an fp8 term counts half) / time; peak = MEASURED_PEAKS bf16_tflops_sustained (a step lasts seconds under the power cap); burst peak {1:.0f}".format(pipe_terms, burst)},
+           "gpu_launches": launches, "mean_diag_over_M": diag / m, "parity": parity, "rank0_breakdown": breakdown, "clocks": kclocks}
+    del store, K, tiles
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local, chunk, rank, world, barrier, max_over_ranks, low_term="default"):
@@ -595,12 +783,39 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
     else:
         t_pk = torch.from_numpy(h_packed)
         d_tight = torch.empty((m_local, rec), dtype=torch.uint8, device="cuda")
+        # ONE host copy of K shared by the ranks (a file mapping; every rank page-locks and fills its own row band): the finished kernel
+        # leaves over all the PCIe links instead of rank 0's alone
+        shared = None
+        r0, r1 = rank * n // world, (rank + 1) * n // world
+        try:
+            base = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > n * n * 4 + (1 << 30) else None
+            ok_all = max_over_ranks(0.0 if base else 1.0) == 0.0
+            if ok_all:
+                path = os.path.join(base, "pstb_bench_K_{0}.bin".format(os.environ.get("MASTER_PORT", "0")))
+                if rank == 0:
+                    with open(path, "wb") as f:
+                        f.truncate(n * n * 4)
+                barrier()
+                mm = np.memmap(path, dtype=np.float32, mode="r+", shape=(n, n))
+                band = mm[r0:r1]
+                rcr = torch.cuda.cudart().cudaHostRegister(band.ctypes.data, band.nbytes, 0)
+                if max_over_ranks(0.0 if int(rcr) == 0 else 1.0) == 0.0:
+                    shared = (path, mm, band, torch.from_numpy(band))
+                elif int(rcr) == 0:
+                    torch.cuda.cudart().cudaHostUnregister(band.ctypes.data)
+        except Exception:
+            shared = None
+        if max_over_ranks(0.0 if shared is not None else 1.0) != 0.0:
+            shared = None
         t_K = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(h_K, ctypes.POINTER(ctypes.c_float)), shape=(n, n))) if rank == 0 else None
 
         def step():
             d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
             store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
-            if tiles is not None:
+            if tiles is not None and not args.serial_allreduce:
+                parallel.snp_kernel_sharded_overlapped(store, n, m, None, ("unit",), chunk=chunk, tiles=tiles, K=K, bands=args.allreduce_bands,
+                                                       reserve_sms=args.allreduce_sms)
+            elif tiles is not None:
                 dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
                 dist.all_reduce(tiles)
                 dev.kernel_from_tiles(tiles, n, K=K)
@@ -608,10 +823,14 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
                 dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False, low_term=low_term)
                 dist.all_reduce(K)
                 _lib.check(lib.pstb_mirror_lower(K.data_ptr(), n, n, stream))
-            if rank == 0:
+            if shared is not None:
+                shared[3].copy_(K[r0:r1], non_blocking=True)                        # D2H of this rank's row band of the finished kernel
+            elif rank == 0:
                 t_K.copy_(K, non_blocking=True)                                     # D2H of the finished kernel
             torch.cuda.synchronize()
-        api = "per rank: pinned packed shard -> HBM, pstb_snp_kernel, NCCL all-reduce, rank 0 copies float32 K to pinned host memory"
+        api = ("per rank: pinned packed shard -> HBM, SNP-sharded SnpKernel with the NCCL all-reduce overlapped, every rank copies its row band of the float32 K "
+               "into ONE shared page-locked host matrix" if shared is not None else
+               "per rank: pinned packed shard -> HBM, pstb_snp_kernel, NCCL all-reduce, rank 0 copies float32 K to pinned host memory")
     step()
     barrier()
     steps = max(1, min(args.steps, args.kernel_steps))
@@ -621,11 +840,33 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
     torch.cuda.synchronize()
     dt = max_over_ranks((time.perf_counter() - t0) / steps)
     ok = None
+    if world > 1:
+        barrier()
     if rank == 0:
-        hk = np.ctypeslib.as_array(ctypes.cast(h_K, ctypes.POINTER(ctypes.c_float)), shape=(n, n))
-        ok = bool(abs(float(np.mean(np.diagonal(hk).astype(np.float64))) / m - 1.0) < 1e-3 and np.array_equal(hk[:64, -64:], hk[-64:, :64].T))
+        hk = shared[1] if (world > 1 and shared is not None) else np.ctypeslib.as_array(ctypes.cast(h_K, ctypes.POINTER(ctypes.c_float)), shape=(n, n))
+        # the host copy against the device-resident K of the timed leg (itself checked against the oracle on sampled tiles):
+        # diagonal and off-diagonal 256 x 256 blocks to 2e-6 relative Frobenius (slice boundaries may regroup the fp32 sums), symmetry
+        T = (n + 255) // 256
+        worst = 0.0
+        for I, J in ((0, 0), (T - 1, T - 1), (T // 2, T // 3), (T - 1, 0), (T // 2, T // 2)):
+            a = hk[I * 256:I * 256 + 256, J * 256:J * 256 + 256].astype(np.float64)
+            b = K[I * 256:I * 256 + 256, J * 256:J * 256 + 256].double().cpu().numpy()
+            worst = max(worst, float(np.linalg.norm(a - b) / max(1e-300, np.linalg.norm(b))))
+        ok = {"worst_rel_frobenius_vs_device_K_on_5_blocks": worst, "within_2e-6": bool(worst <= 2e-6),
+              "symmetric_block": bool(np.array_equal(hk[:256, -256:], hk[-256:, :256].T))}
         del hk
         lib.pstb_host_free(h_K)
+    if world > 1 and shared is not None:
+        barrier()
+        torch.cuda.cudart().cudaHostUnregister(shared[2].ctypes.data)
+        path = shared[0]
+        shared = None
+        barrier()
+        if rank == 0:
+            try:
+                os.remove(path)
+            except OSError:
+                pass
     del h_packed
     lib.pstb_host_free(h_pk)
     lib.pstb_host_release()
@@ -633,7 +874,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
             "ms_per_step": dt * 1e3, "steps": steps, "api": api, "result_check": ok}
 
 
-def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks):
+def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks, peaks):
     """cfg5: streamed decode + standardize + K for N = 500 000 (K = 1 TB): K-tile sharding, packed store replicated, no collective."""
     n, m = args.cfg5_n, args.cfg5_m
     coords = dev.kernel_tile_coords(n, rank, world)
@@ -658,36 +899,127 @@ def run_cfg5(args, torch, dist, dev, _lib, rank, world, barrier, max_over_ranks)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    # parity on sampled tiles against the CPU oracle (statistics from the GPU run, themselves checked on a SNP sample)
-    from oracle import bed_oracle
-    rng = np.random.default_rng(rank)
-    worst = 0.0
-    packed_all = None
-    for t in rng.choice(len(coords), size=min(args.cfg5_tiles, len(coords)), replace=False):
-        I, J = int(coords[t][0]), int(coords[t][1])
-        rows = np.arange(I * 256, min(n, I * 256 + 256))
-        cols = np.arange(J * 256, min(n, J * 256 + 256))
-        if packed_all is None:
-            st = stats.cpu().numpy()
-            head = store.tensor[:64, :rec].cpu().numpy()
-            _sub, rst = bed_oracle.standardize(bed_oracle.decode(head, n))
-            assert np.allclose(st[:64], rst, rtol=1e-12, equal_nan=True)
-            packed_all = True
+    # parity on sampled tiles against the CPU oracle: >= 64 tiles in total (all pairs of `cfg5_blocks` row blocks), each compared on the
+    # rank that owns it; the float64 reference is built from SNP shards of the (replicated) store, one shard per rank, and summed
+    blocks = pick_blocks(n, args.cfg5_blocks, seed=n)
+    index_of = {(int(c[0]), int(c[1])): t for t, c in enumerate(coords)}
 
-        def tile_rows(block):                                   # 256 aligned individuals = 64 contiguous bytes of every record
-            lo_b, cnt = block * 64, min(n, block * 256 + 256) - block * 256
-            sub = store.tensor[:, lo_b:lo_b + (cnt + 3) // 4].contiguous().cpu().numpy()
-            x, _ = bed_oracle.standardize(bed_oracle.decode(sub, cnt), use_stats=True, stats=st)
-            return x
-        xr, xc = tile_rows(I), tile_rows(J)
-        ref = xr @ xc.T
-        got = tiles[t, : len(rows), : len(cols)].double().cpu().numpy()
-        worst = max(worst, float(np.linalg.norm(got - ref) / max(1e-300, np.linalg.norm(ref))))
-    worst = max_over_ranks(worst)
-    return {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": 2.0 * n * n * m / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms,
-            "config": {"workload": "cfg5: synthetic .bed {0} iids x {1} SNPs, streamed decode+standardize+K, K-tile sharded over {2} GPUs (no collective)".format(n, m, world),
-                       "tiles_per_rank": int(len(coords)), "tile_bytes_per_rank": need, "chunk_snps": chunk},
-            "parity": {"sampled_tiles_per_rank": int(min(args.cfg5_tiles, len(coords))), "worst_rel_frobenius_vs_oracle": worst}}
+    def fetch(I, J):
+        t = index_of.get((I, J))
+        return None if t is None else tiles[t].double().cpu().numpy()
+    lo, hi = rank * m // world, (rank + 1) * m // world
+    shard = dev.PackedStore(store.tensor[lo:hi], n, hi - lo)
+    parity = sampled_tile_parity(torch, dist, world, rank, _oracle_lib(), shard, stats[lo:hi], n, ("unit",), fetch, blocks, owner_of=True)
+    low_term = dev.low_term_for(m, n)
+    t256 = (n + 255) // 256
+    executed = (1.5 if low_term == "fp8" else 2.0) * 2.0 * 256 * 256 * (t256 * (t256 + 1) // 2) * ((m + 63) // 64 * 64) / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) * world
+    res = {"metric": "SnpKernel TFLOP/s (2*N^2*M)", "value": 2.0 * n * n * m / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "ms_per_step": ms,
+           "config": {"workload": "cfg5: synthetic .bed {0} iids x {1} SNPs, streamed decode+standardize+K, K-tile sharded over {2} GPUs (no collective)".format(n, m, world),
+                      "tiles_per_rank": int(len(coords)), "tile_bytes_per_rank": need, "chunk_snps": chunk, "low_term": low_term},
+           "roofline": {"bound": "tensor", "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak,
+                        "note": "executed fp16-equivalent tensor work of all ranks / time; peak = ranks x MEASURED_PEAKS bf16_tflops_sustained"},
+           "parity": parity}
+    del store, tiles, shard
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gather_leg(args, torch, dev, _lib, peaks):
+    """cfg4 (BASELINE configs[3]): 100 000 iids x 200 000 SNPs, 5 % missing, Beta(1,25), random unsorted iid / sid subsets
+    (rng = default_rng(1); permutation(N)[:N//2], permutation(M)[:M//2] -- SURVEY 8d), float32, F order.  One fused launch."""
+    lib = _lib.lib
+    n, m = args.cfg4_n, args.cfg4_m
+    rng = np.random.default_rng(1)
+    iid_idx, sid_idx = rng.permutation(n)[: n // 2], rng.permutation(m)[: m // 2]
+    store = gen_store_device(dev, torch, n, m, seed=4000, missing_rate=0.05)
+    I, S = dev.Selection(iid_idx, n, "cuda"), dev.Selection(sid_idx, m, "cuda")
+    out = torch.empty((S.n, I.n), dtype=torch.float32, device="cuda")
+    stats = torch.empty((S.n, 2), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n, m, I.axis(), S.axis(), 0, _lib.STD_BETA, 1.0, 25.0, 0,
+                                               stats.data_ptr(), out.data_ptr(), _lib.F32, _lib.ORDER_F, st))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    steps = max(3, min(args.steps, 10))
+    ts = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    rec = (n + 3) // 4
+    algo = S.n * rec + 4 * I.n * S.n + 16 * S.n
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # spot parity: the first 1 024 selected SNPs against the oracle (bit pattern of NaN handling + values to 1e-6 relative)
+    lib_o = _oracle_lib()
+    chk = min(1024, S.n)
+    threads = os.cpu_count() or 1
+    packed = np.ascontiguousarray(store.tensor[torch.as_tensor(sid_idx[:chk], device="cuda"), :rec].cpu().numpy())
+    ref = np.empty((I.n, chk), dtype=np.float64, order="F")
+    rst = np.empty((chk, 2), dtype=np.float64)
+    p = ctypes.c_void_p
+    ii64 = np.ascontiguousarray(iid_idx, dtype=np.int64)
+    lib_o.pst_oracle_decode_f64(p(packed.ctypes.data), ctypes.c_int64(rec), ctypes.c_int64(n), ctypes.c_int64(chk), p(ii64.ctypes.data), ctypes.c_int64(I.n),
+                                None, ctypes.c_int64(chk), 0, 0, p(ref.ctypes.data), threads)
+    lib_o.pst_oracle_standardize_f64(p(ref.ctypes.data), ctypes.c_int64(I.n), ctypes.c_int64(chk), 0, 1, ctypes.c_double(1.0), ctypes.c_double(25.0), 0,
+                                     p(rst.ctypes.data), threads)
+    got = out[:chk].t().double().cpu().numpy()
+    scale = max(1e-300, float(np.max(np.abs(ref))))
+    parity = {"checked_snps": chk, "max_abs_diff_over_max_abs": float(np.max(np.abs(got - ref)) / scale), "tolerance": 1e-6,
+              "stats_max_rel_diff": float(np.max(np.abs(stats[:chk].cpu().numpy() - rst) / np.maximum(1e-300, np.abs(rst))))}
+    res = {"metric": "genotypes/s decoded+standardized", "value": I.n * S.n / (ms * 1e-3), "unit": "genotypes/s", "ms_per_step": ms, "steps": steps,
+           "config": {"workload": "cfg4: synthetic .bed {0} iids x {1} SNPs, 5 % missing, Beta(1,25), random unsorted {2} x {3} subset (default_rng(1) permutations), float32, F order".format(n, m, I.n, S.n)},
+           "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_bytes_per_launch": algo, "kernel": "k_read_f_gather4<float> (byte-interleaved gather of four records + masked-popcount statistics)"},
+           "parity_spot_check": parity}
+    del store, out, stats
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_c_order_leg(args, torch, dev, _lib, peaks, store, ref_out_f):
+    """cfg2 with order='C' (sid fastest: the layout the reference's kernel loop asks for, snpreader.py:640): k_stats_dense + k_emit_c_wide."""
+    lib = _lib.lib
+    n, m = store.iid_count, args.c_order_m
+    out = torch.empty((n, m), dtype=torch.float32, device="cuda")
+    stats = torch.empty((m, 2), dtype=torch.float64, device="cuda")
+    full = _lib.Axis(None, 0, 1, n), _lib.Axis(None, 0, 1, m)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        _lib.check(lib.pstb_decode_standardize(store.tensor.data_ptr(), store.ld, n, store.sid_count, full[0], full[1], 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
+                                               stats.data_ptr(), out.data_ptr(), _lib.F32, _lib.ORDER_C, st))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(max(3, min(args.steps, 10))):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    rec = (n + 3) // 4
+    algo = 2 * m * rec + 4 * n * m + 16 * m                      # the packed records are read twice: statistics pass + emit pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    same = bool(torch.equal(out[:, :4096], ref_out_f[:4096].t())) if ref_out_f is not None else None
+    res = {"metric": "genotypes/s decoded+standardized", "value": n * m / (ms * 1e-3), "unit": "genotypes/s", "ms_per_step": ms,
+           "config": {"workload": "cfg2 shape in C order: {0} iids x {1} SNPs, decode + Unit, float32".format(n, m)},
+           "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_bytes_per_launch": algo, "kernel": "k_stats_dense + k_emit_c_wide<float>"},
+           "bit_identical_to_F_order_result_on_4096_snps": same}
+    del out, stats
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -704,8 +1036,14 @@ def main():
     ap.add_argument("--cfg5", action="store_true", help="run only the cfg5 leg: K-tile sharded SnpKernel (500 000 x 100 000 across the ranks)")
     ap.add_argument("--cfg5-n", type=int, default=500_000)
     ap.add_argument("--cfg5-m", type=int, default=100_000)
-    ap.add_argument("--cfg5-tiles", type=int, default=8, help="tiles per rank compared with the CPU oracle")
-    ap.add_argument("--api-e2e", action="store_true", help="also time Bed(file).read(dtype=float32, standardizer=Unit()) -> NumPy through the Python layer")
+    ap.add_argument("--cfg5-blocks", type=int, default=11, help="row blocks whose pairwise tiles (66 for 11) are compared with the CPU oracle")
+    ap.add_argument("--cfg4-n", type=int, default=100_000)
+    ap.add_argument("--cfg4-m", type=int, default=200_000)
+    ap.add_argument("--c-order-m", type=int, default=CFG2["n_sid"])
+    ap.add_argument("--kernel-missing-m", type=int, default=100_032, help="SNPs of the missing-data SnpKernel leg (cfg3 individuals)")
+    ap.add_argument("--kernel-parity-blocks", type=int, default=11, help="row blocks whose pairwise 256x256 tiles (66 for 11) of K are compared with the CPU oracle; 0 = off")
+    ap.add_argument("--no-extra-legs", dest="extra_legs", action="store_false", help="skip the cfg4 / C-order / missing-data / cfg5 legs")
+    ap.add_argument("--no-api-e2e", dest="api_e2e", action="store_false", help="skip Bed(file).read(dtype=float32, standardizer=Unit()) -> NumPy through the Python layer")
     ap.add_argument("--only-kernel", action="store_true", help="experiments: run only the cfg3 SnpKernel leg and print its object")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--kernel-n", type=int, default=CFG3["n_iid"])
@@ -713,6 +1051,9 @@ def main():
     ap.add_argument("--kernel-steps", type=int, default=2)
     ap.add_argument("--kernel-chunk", type=int, default=None)
     ap.add_argument("--square-allreduce", action="store_true", help="A/B: all-reduce the square K instead of the compact lower triangle")
+    ap.add_argument("--serial-allreduce", action="store_true", help="A/B: all-reduce the compact triangle after the whole multiplication (round 1) instead of overlapping it")
+    ap.add_argument("--allreduce-bands", type=int, default=8)
+    ap.add_argument("--allreduce-sms", type=int, default=16, help="SMs the last chunk's SYRK leaves to the overlapped NCCL all-reduce")
     ap.add_argument("--no-kernel-cpu", dest="kernel_cpu", action="store_false", help="skip the CPU SnpKernel sample (NumPy BLAS) of the kernel leg")
     ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")
     args = ap.parse_args()

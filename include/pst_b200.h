@@ -145,6 +145,19 @@ int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_t iid_count
  * entries of other ranks' tiles are left untouched).  The SNP-sharded multi-GPU path accumulates into compact tiles
  * (rank 0 of world 1 = the whole lower triangle), all-reduces them -- half the bytes of the square matrix -- and expands. */
 int pstb_kernel_from_tiles(const float* d_tiles, int64_t n_iid, int rank, int world, float* d_K, void* stream);
+/* Bands of a compact-tile kernel, for overlapping the NCCL reduction of the SNP-sharded multi-GPU path with its last SNP chunk
+ * ("overlappable by reducing finished tile-rows early"): pstb_snp_kernel_tiles_band multiplies ONE chunk of SNPs
+ * (sid.n <= chunk) for tiles [tile_begin, tile_end) of `rank`'s list only, leaving `reserve_sms` SMs idle for a concurrent collective.
+ * flags bit 0 = first band of the chunk: statistics and operand planes are built into d_work; later bands (flags = 0) reuse them.
+ * low_term must be PSTB_LOW_TERM_FP16 or _FP8.  pstb_kernel_from_tiles_range expands tiles [tile_begin, tile_end) into the square K. */
+int pstb_snp_kernel_tiles_band(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                               pstb_axis iid, pstb_axis sid, int count_a1,
+                               int mode, double a, double b, int use_stats, double* d_stats,
+                               float* d_tiles, int rank, int world, int accumulate,
+                               void* d_work, int64_t work_bytes, int64_t chunk, int low_term,
+                               int64_t tile_begin, int64_t tile_end, int flags, int reserve_sms, void* stream);
+int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid, int rank, int world, int64_t tile_begin, int64_t tile_end,
+                                 float* d_K, void* stream);
 /* Train x test kernel (what FaST-LMM builds from SnpKernel + the *Trained standardizers: unittrained.py:47-70,
  * betatrained.py:47-63 applied to a second iid set, then train.val.dot(test.val.T)):
  *   d_out [n_r, n_c] float32, C order (ld = n_c):  out[i, k] (+)= sum_j x_ij y_kj
@@ -164,6 +177,23 @@ int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, int64_t iid_c
  * val.dot(val.T) of SnpData._read_kernel (snpdata.py:203-206).  Same fp16 hi/lo tensor-core path and workspace. */
 int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
                       int mirror, void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* ---- K3 in float64 -----------------------------------------------------------------------------
+ * The reference computes a kernel in the dtype the caller asks for: val.dot(val.T) (snpdata.py:203-206) is a DGEMM for the default
+ * dtype=float64, and its unit tests compare float64 kernels to 10 decimals (kernelreader/test.py:48-50, :189; test.py:535-553).
+ * These entry points are that contract on the GPU: the same fused decode + exact-count statistics + standardize, into a float64
+ * panel, followed by an fp64-FMA SYRK on the CUDA cores (two-level summation: one register partial per SNP chunk, then K += it).
+ * ~1e-13 relative to the reference's float64 path; ~100 x its CPU rate (B200 has full-rate fp64).  d_K is float64 [n_iid, n_iid].
+ * pstb_kernel_f64_workspace_bytes: one float64 panel of `chunk` SNPs.  `chunk` need not be a multiple of 64 here. */
+int64_t pstb_kernel_f64_workspace_bytes(int64_t n_iid, int64_t chunk);
+int pstb_snp_kernel_f64(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,
+                        pstb_axis iid, pstb_axis sid, int count_a1,
+                        int mode, double a, double b, int use_stats, double* d_stats,
+                        double* d_K, int accumulate, int mirror,
+                        void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+/* K = V V^T in float64 for a float64 matrix V [n_iid, n_sid] (C or F order) already in HBM. */
+int pstb_float_kernel_f64(const double* d_val, int order, int64_t n_iid, int64_t n_sid, double* d_K, int accumulate, int mirror,
+                          void* stream);
+int pstb_mirror_lower_f64(double* d_K, int64_t n, int64_t ldk, void* stream);
 /* Test/bench hook for the tensor-core stage alone: K_lower (+)= (hi+lo)(hi+lo)^T minus lo*lo^T, on
  * fp16 planes [n_pad, k_pad] (row-major, k_pad % 64 == 0, n_pad % 128 == 0). */
 int pstb_syrk_planes(const void* d_hi, const void* d_lo, int64_t n, int64_t n_pad, int64_t k_pad,
@@ -189,6 +219,11 @@ int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid
                          const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
                          int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
                          void* h_K, int dtype, int64_t chunk, int low_term);
+/* the same loop in float64 arithmetic (pstb_snp_kernel_f64): h_K is float64 [n_iid, n_iid]; chunk a multiple of 64. */
+int pstb_snp_kernel_host_f64(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count,
+                             const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
+                             int count_a1, int mode, double a, double b, int use_stats, double* h_stats,
+                             double* h_K, int64_t chunk);
 /* standardize_f32/f64 equivalent on a host array (H2D, K2f, D2H). */
 int pstb_standardize_host(void* h_val, int dtype, int order, int64_t n_iid, int64_t n_sid,
                           int mode, double a, double b, int apply_in_place, int use_stats, double* h_stats);

@@ -9,12 +9,12 @@ Same names as the reference for this path::
 """
 from . import _lib
 from .kernelreader import KernelData, SnpKernel
-from .snpreader import Bed, SnpData, SnpReader
+from .snpreader import Bed, SnpData, SnpReader, set_kernel_float64
 from .distributedbed import DistributedBed
 from .snpmemmap import SnpMemMap
 from .standardizer import Beta, BetaTrained, DiagKtoN, Identity, Standardizer, Unit, UnitTrained
 from . import kernelreader, kernelstandardizer, snpreader, standardizer, util  # noqa: F401  (the reference's sub-package names)
 
 __all__ = ["Bed", "DistributedBed", "SnpMemMap", "SnpData", "SnpReader", "Unit", "Beta", "UnitTrained", "BetaTrained", "Identity", "DiagKtoN", "Standardizer",
-           "SnpKernel", "KernelData"]
+           "SnpKernel", "KernelData", "set_kernel_float64"]
 __version__ = "0.1.0"

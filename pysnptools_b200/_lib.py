@@ -55,6 +55,10 @@ def _load():
         "pstb_kernel_tile_coords": (c_int, [c_int64, c_int, c_int, c_void_p]),
         "pstb_snp_kernel_tiles": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
                                           c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+        "pstb_snp_kernel_tiles_band": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
+                                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_int,
+                                               c_void_p]),
+        "pstb_kernel_from_tiles_range": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p]),
         "pstb_set_syrk_low_term": (c_int, [c_int]),
         "pstb_kernel_from_tiles": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
         "pstb_cross_kernel_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
@@ -62,6 +66,13 @@ def _load():
                                           c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int,
                                           c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
         "pstb_float_kernel": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+        "pstb_kernel_f64_workspace_bytes": (c_int64, [c_int64, c_int64]),
+        "pstb_snp_kernel_f64": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
+                                        c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64, c_void_p]),
+        "pstb_float_kernel_f64": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p]),
+        "pstb_mirror_lower_f64": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+        "pstb_snp_kernel_host_f64": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double,
+                                             c_double, c_int, c_void_p, c_void_p, c_int64]),
         "pstb_syrk_planes": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p]),
         "pstb_mirror_lower": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
         "pstb_convert_kernel": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p]),

@@ -441,9 +441,9 @@ extern "C" int pstb_subset_host(const void* h_in, int dtype_in, int order_in, in
 // The packed records cross PCIe in slices of a few SYRK chunks on a copy stream while the previous slice is being multiplied
 // (2 bits per genotype: 6.25 GB for 50 000 x 500 000, hidden behind seconds of tensor-core work); K is accumulated on the
 // device and only the finished matrix travels back, converted to the requested dtype band by band.
-extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
-                                    int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
-                                    int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk, int low_term) {
+static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
+                                int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
+                                int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk, int low_term, bool exact) {
     if (iid_count < 0 || sid_count < 0) return fail("negative iid_count / sid_count");
     if (!h_iid_idx) n_iid = iid_count;
     if (!h_sid_idx) n_sid = sid_count;
@@ -451,6 +451,7 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
     if (iid_count > 0xfffffff0LL) return fail("iid_count too large");
     if (dtype != PSTB_F32 && dtype != PSTB_F64) return fail("kernel dtype must be float32 or float64");
     if (chunk < 64 || chunk % 64) return fail("chunk must be a positive multiple of 64");
+    if (exact && dtype != PSTB_F64) return fail("the float64 kernel path returns float64");
     for (int64_t k = 0; h_sid_idx && k < n_sid; ++k)
         if (h_sid_idx[k] < 0 || h_sid_idx[k] >= sid_count)
             return fail("sid index %lld out of range [0, %lld)", (long long)h_sid_idx[k], (long long)sid_count);
@@ -470,7 +471,7 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
     };
 
     const int64_t rec = (iid_count + 3) / 4, ld = pstb_packed_ld(iid_count);
-    const size_t es = esize_of(dtype), kbytes32 = (size_t)n_iid * n_iid * sizeof(float);
+    const size_t es = esize_of(dtype), kbytes32 = (size_t)n_iid * n_iid * (exact ? sizeof(double) : sizeof(float));   // device K: fp64 on the exact path
     int64_t slice = (int64_t)(((size_t)384 << 20) / (size_t)(ld > 0 ? ld : 1)) / chunk * chunk;      // ~384 MB of records per slice
     if (const char* e = getenv("PSTB_KERNEL_SLICE_SNPS")) {                                          // tests: force several slices
         const int64_t v = atoll(e);
@@ -478,7 +479,7 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
     }
     if (slice < chunk) slice = chunk;
     if (slice > n_sid) slice = (n_sid + chunk - 1) / chunk * chunk;
-    const int64_t work_bytes = pstb_kernel_workspace_bytes(n_iid, chunk);
+    const int64_t work_bytes = exact ? pstb_kernel_f64_workspace_bytes(n_iid, chunk) : pstb_kernel_workspace_bytes(n_iid, chunk);
     // the device K and the workspace stay cached in the thread's context between calls (cudaFree of a 10 GB buffer was measured
     // at up to 0.9 s); pstb_host_release() returns them
     Buf& d_K = c.d_K;
@@ -539,16 +540,20 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
             break;
         }
         pstb_axis sid_ax{nullptr, 0, 1, ns};
-        rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
-                              (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, low_term, comp,
-                              (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
+        if (exact)
+            rc = snp_kernel_f64_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                                      (double*)c.d_stats.p + 2 * b0, (double*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp);
+        else
+            rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                                  (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, low_term, comp,
+                                  (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
         if (rc) break;
         if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
         used_pending[slot] = true;
     }
     if (rc) return cleanup(rc);
     mark("slices enqueued");
-    if (pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
+    if (exact ? pstb_mirror_lower_f64((double*)d_K.p, n_iid, n_iid, comp) : pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
     // ---- K back to the host: row bands, converted on the device, D2H overlapped with the next band's conversion ----
     const bool out_pinned = is_pinned(h_K);
     const size_t row_bytes = (size_t)n_iid * es;
@@ -575,7 +580,9 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
         cudaStream_t st = c.s[slot];
         const float* src = (const float*)d_K.p + (size_t)r0 * n_iid;
         const void* from = src;
-        if (dtype == PSTB_F64) {
+        if (exact) {
+            from = (const double*)d_K.p + (size_t)r0 * n_iid;           // already float64: straight D2H
+        } else if (dtype == PSTB_F64) {
             if (c.d_out[slot].ensure((size_t)band * row_bytes)) { rc = 1; break; }
             if ((rc = convert_range(src, (long long)nr * n_iid, c.d_out[slot].p, dtype, 1.0, st))) break;
             from = c.d_out[slot].p;
@@ -605,6 +612,21 @@ extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, 
     rc = cleanup(rc);
     mark("buffers released");
     return rc;
+}
+
+extern "C" int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
+                                    int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
+                                    int use_stats, double* h_stats, void* h_K, int dtype, int64_t chunk, int low_term) {
+    return snp_kernel_host_impl(h_packed, iid_count, sid_count, h_iid_idx, n_iid, h_sid_idx, n_sid, count_a1, mode, a, b, use_stats, h_stats, h_K,
+                                dtype, chunk, low_term, false);
+}
+
+// the same loop in float64 arithmetic (syrk_f64.cu): what a dtype=float64 request of the reference means (snpdata.py:203-206 is a DGEMM then)
+extern "C" int pstb_snp_kernel_host_f64(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count, const int64_t* h_iid_idx,
+                                        int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid, int count_a1, int mode, double a, double b,
+                                        int use_stats, double* h_stats, double* h_K, int64_t chunk) {
+    return snp_kernel_host_impl(h_packed, iid_count, sid_count, h_iid_idx, n_iid, h_sid_idx, n_sid, count_a1, mode, a, b, use_stats, h_stats, h_K,
+                                PSTB_F64, chunk, PSTB_LOW_TERM_DEFAULT, true);
 }
 
 // free every device / pinned buffer the host-buffer entry points keep cached for the calling thread

@@ -119,6 +119,11 @@ int snp_kernel_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int
                      int count_a1, int mode, double a, double b, int use_stats, double* d_stats, float* d_K, int accumulate,
                      void* d_work, int64_t work_bytes, int64_t chunk, int low_term, void* stream, int phase, int64_t total_sid);
 
+// one slice of a streamed float64 kernel (syrk_f64.cu): decode + standardize into a float64 panel, fp64 FMA SYRK, no mirror
+int snp_kernel_f64_slice(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid, pstb_axis sid,
+                         int count_a1, int mode, double a, double b, int use_stats, double* d_stats, double* d_K, int accumulate,
+                         void* d_work, int64_t work_bytes, int64_t chunk, void* stream);
+
 }  // namespace pstb
 
 #define PSTB_CUDA(x)                                                                   \

@@ -1105,7 +1105,8 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad, long long k_pad, float* K, long long ldk,
                 int accumulate, const Scalars* sc, float out_scale, cudaStream_t st, int rank = 0, int world = 1, int compact = 0,
-                const __half* p2 = nullptr, const int2** tiles_out = nullptr, int* ntiles_out = nullptr, int fp8lo = 0) {
+                const __half* p2 = nullptr, const int2** tiles_out = nullptr, int* ntiles_out = nullptr, int fp8lo = 0,
+                long long tile_begin = 0, long long tile_end = -1, int reserve_sms = 0) {
     if (n_pad % ROW_PAD || k_pad % BK || n_pad < n) return fail("planes must be padded to %d rows / %d columns", ROW_PAD, BK);
     if ((reinterpret_cast<uintptr_t>(hi) & 127u) || (reinterpret_cast<uintptr_t>(lo) & 127u)) return fail("planes must be 128-byte aligned");
     CUtensorMap map_hi, map_lo, map_p2, map_h8;
@@ -1124,6 +1125,13 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     const int2* d_tiles = nullptr;
     int ntiles = 0;
     if (get_tiles(n, version, rank, world, st, &d_tiles, &ntiles)) return 1;
+    if (tile_end >= 0) {
+        // a band of the (compact) tile list: tiles [tile_begin, tile_end) of this rank, stored at their usual place
+        if (!compact || tile_begin < 0 || tile_end > ntiles || tile_begin > tile_end) return fail("bad tile range [%lld, %lld) of %d", tile_begin, tile_end, ntiles);
+        d_tiles += tile_begin;
+        K += tile_begin * (long long)(v2::TM * v2::TN);
+        ntiles = (int)(tile_end - tile_begin);
+    }
     if (tiles_out) *tiles_out = d_tiles;
     if (ntiles_out) *ntiles_out = ntiles;
     SyrkParams p{};
@@ -1156,6 +1164,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     if (version == 2) {
         int clusters = sm_count_cached() / 2;
         if (kn.clusters > 0 && kn.clusters < clusters) clusters = kn.clusters;
+        if (reserve_sms > 0) clusters = clusters - (reserve_sms + 1) / 2 > 8 ? clusters - (reserve_sms + 1) / 2 : 8;   // leave SMs to a concurrent collective
         if (clusters > ntiles) clusters = ntiles;
         v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, map_out, p);   // __cluster_dims__(2,1,1)
         PSTB_AFTER_LAUNCH("k_syrk2");
@@ -1330,7 +1339,12 @@ static int resolve_fp8lo(int low_term, int64_t snps, int64_t n_iid, int mode) {
 static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
                            pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
                            float* d_K, int accumulate, int mirror, void* d_work, int64_t work_bytes, int64_t chunk, int low_term,
-                           void* stream, int rank, int world, int compact, int phase = 3, int64_t total_sid = -1) {
+                           void* stream, int rank, int world, int compact, int phase = 3, int64_t total_sid = -1,
+                           long long tile_begin = 0, long long tile_end = -1, int band_flags = 1, int reserve_sms = 0) {
+    // banded mode (tile_end >= 0; pstb_snp_kernel_tiles_band): ONE chunk of SNPs, tiles [tile_begin, tile_end) only.  band_flags bit 0:
+    // build the operand planes (first band of the chunk); without it the planes a previous band call left in d_work are reused.
+    const bool banded = tile_end >= 0;
+    if (banded && sid.n > chunk) return fail("a band call multiplies one chunk of SNPs (%lld > %lld)", (long long)sid.n, (long long)chunk);
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
     if (iid.n < 0 || sid.n < 0) return fail("negative selection length");
@@ -1369,12 +1383,19 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
                             (getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0);
     // (a streamed call passes the SNP count of the whole kernel in total_sid)
     const int fp8lo = force_slow ? 0 : resolve_fp8lo(low_term, total_sid >= 0 ? total_sid : sid.n, iid.n, mode);
-    if (phase & 1) PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
+    const bool build_planes = !banded || (band_flags & 1);
+    if ((phase & 1) && build_planes) PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     const int2* d_tiles = nullptr;
     int ntiles = 0;
     for (long long c0 = 0; c0 < sid.n; c0 += chunk) {
         const long long ns = (c0 + chunk <= sid.n) ? chunk : sid.n - c0;
         const long long k_pad = round_up(ns, BK);
+        if (!build_planes) {                               // later band of the same chunk: planes, scalars and u are in the workspace
+            int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, accumulate ? 1 : 0, sc, 1.0f, st, rank, world, compact, p2, &d_tiles, &ntiles, fp8lo,
+                                 tile_begin, tile_end, reserve_sms);
+            if (rc) return rc;
+            continue;
+        }
         pstb_axis sub = sid;
         sub.n = ns;
         if (sid.idx) sub.idx = sid.idx + c0; else sub.start = sid.start + c0 * sid.step;
@@ -1415,13 +1436,14 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
         PSTB_AFTER_LAUNCH("k_planes");
         int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact, p2,
-                             &d_tiles, &ntiles, pp.fp8lo);
+                             &d_tiles, &ntiles, pp.fp8lo, tile_begin, tile_end, reserve_sms);
         if (rc) return rc;
     }
     if (!force_slow && (phase & 2)) {
         if (compact) {
             if (ntiles > 0) {
-                k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(d_K, d_tiles, n, u);
+                // (banded: d_tiles / ntiles are the band's, so is the tile storage)
+                k_apply_rank1_tiles<<<(unsigned)ntiles, 256, 0, st>>>(banded ? d_K + tile_begin * 65536LL : d_K, d_tiles, n, u);
                 PSTB_AFTER_LAUNCH("k_apply_rank1_tiles");
             }
         } else {
@@ -1472,6 +1494,39 @@ extern "C" int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_
     if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
     return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_tiles, accumulate,
                            0, d_work, work_bytes, chunk, low_term, stream, rank, world, 1);
+}
+
+// One band of a compact-tile kernel: tiles [tile_begin, tile_end) of `rank`'s list for ONE chunk of SNPs (sid.n <= chunk).  The
+// SNP-sharded multi-GPU path runs its last chunk band by band so that the NCCL all-reduce of finished bands overlaps the
+// multiplication of the later ones (`reserve_sms` SMs are left to the collective).  flags bit 0: first band of the chunk (statistics +
+// operand planes are built into d_work); later bands reuse them, so the calls of one chunk must not be interleaved with other
+// kernel calls on the same workspace.  The rank-one part of the chunk is added to every band's tiles.
+extern "C" int pstb_snp_kernel_tiles_band(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count, pstb_axis iid,
+                                          pstb_axis sid, int count_a1, int mode, double a, double b, int use_stats, double* d_stats,
+                                          float* d_tiles, int rank, int world, int accumulate, void* d_work, int64_t work_bytes,
+                                          int64_t chunk, int low_term, int64_t tile_begin, int64_t tile_end, int flags, int reserve_sms,
+                                          void* stream) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+    if (tile_begin < 0 || tile_end < tile_begin) return fail("bad tile range");
+    if (low_term != PSTB_LOW_TERM_FP16 && low_term != PSTB_LOW_TERM_FP8) return fail("a band call needs an explicit low_term (FP16 / FP8): every band of a chunk must use the same planes");
+    return snp_kernel_impl(d_packed, ld, iid_count, sid_count, iid, sid, count_a1, mode, a, b, use_stats, d_stats, d_tiles, accumulate,
+                           0, d_work, work_bytes, chunk, low_term, stream, rank, world, 1, 3, -1, tile_begin, tile_end, flags, reserve_sms);
+}
+
+// tiles [tile_begin, tile_end) of `rank`'s compact list -> their places in the full symmetric K (the other entries are untouched)
+extern "C" int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid, int rank, int world, int64_t tile_begin, int64_t tile_end,
+                                            float* d_K, void* stream) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
+    if (n_iid <= 0 || tile_end <= tile_begin) return 0;
+    if (!d_tiles || !d_K) return fail("NULL pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int2* coords = nullptr;
+    int ntiles = 0;
+    if (get_tiles(n_iid, 2, rank, world, st, &coords, &ntiles)) return 1;
+    if (tile_begin < 0 || tile_end > ntiles) return fail("bad tile range [%lld, %lld) of %d", (long long)tile_begin, (long long)tile_end, ntiles);
+    k_untile<<<dim3((unsigned)(tile_end - tile_begin), 64), 256, 0, st>>>(d_tiles + tile_begin * 65536LL, coords + tile_begin, n_iid, d_K, n_iid);
+    PSTB_AFTER_LAUNCH("k_untile");
+    return 0;
 }
 
 extern "C" int pstb_float_kernel(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_sid, float* d_K, int accumulate,
@@ -1555,7 +1610,10 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
     Scalars* sc = reinterpret_cast<Scalars*>(p2 + n_pad * k_cap);
     double* u = reinterpret_cast<double*>(sc + 1);                                        // rank-one vector v of the column side
     const bool force_slow = getenv("PSTB_SYRK_3TERM") && atoi(getenv("PSTB_SYRK_3TERM")) != 0;
-    const int fp8lo = force_slow ? 0 : resolve_fp8lo(low_term, sid_r.n, nr > nc ? nr : nc, mode);
+    // AUTO means fp16 here: a train x test product has no diagonal, so its Frobenius norm lacks the mass that makes the e4m3 rounding of
+    // the low term small in relative terms (measured 1.1e-5 on the rare-variant fixture all_chr.maf0.001.N300, 290 x 10); FP8 on request
+    int lt = (low_term == PSTB_LOW_TERM_FP16 || low_term == PSTB_LOW_TERM_FP8 || low_term == PSTB_LOW_TERM_AUTO) ? low_term : g_low_term.load();
+    const int fp8lo = (!force_slow && lt == PSTB_LOW_TERM_FP8) ? 1 : 0;
     PSTB_CUDA(cudaMemsetAsync(u, 0, (size_t)(n_pad + 2) * sizeof(double), st));
     for (long long c0 = 0; c0 < sid_r.n; c0 += chunk) {
         const long long ns = (c0 + chunk <= sid_r.n) ? chunk : sid_r.n - c0;

@@ -388,6 +388,57 @@ def float_kernel(val, chunk=None, K=None, accumulate=False, mirror=True):
     return K
 
 
+def snp_kernel_f64(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
+                   K=None, accumulate=False, mirror=True):
+    """``K = sum_j x_j x_j^T`` in float64 arithmetic (``pstb_snp_kernel_f64``: fused decode + standardize into a float64 panel, fp64-FMA
+    SYRK): what a ``dtype=float64`` kernel of the reference means (snpdata.py:203-206 is a DGEMM).  float64 CUDA tensor [n, n]."""
+    _lib.require_gpu()
+    dev = store.device
+    isel = iid_sel if isinstance(iid_sel, Selection) else Selection(iid_sel, store.iid_count, dev)
+    ssel = sid_sel if isinstance(sid_sel, Selection) else Selection(sid_sel, store.sid_count, dev)
+    mode, a, b = _mode_args(standardizer)
+    n = isel.n
+    with torch.cuda.device(dev):
+        if K is None:
+            K = torch.zeros((n, n), dtype=torch.float64, device=dev)
+            accumulate = False
+        assert K.dtype == torch.float64 and K.is_contiguous() and tuple(K.shape) == (n, n)
+        use_stats = 0
+        if stats is not None:
+            d_stats = torch.as_tensor(stats, dtype=torch.float64, device=dev).contiguous()
+            use_stats = 1
+        else:
+            d_stats = torch.empty((ssel.n, 2), dtype=torch.float64, device=dev)
+        if chunk is None:
+            chunk = max(64, min(4096, (256 << 20) // max(1, 8 * n) // 64 * 64))        # a float64 panel of ~256 MB
+        wbytes = int(lib.pstb_kernel_f64_workspace_bytes(n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        check(lib.pstb_snp_kernel_f64(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
+                                      int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), K.data_ptr(),
+                                      int(bool(accumulate)), int(bool(mirror)), work.data_ptr(), wbytes, chunk, _stream()))
+    return K, d_stats
+
+
+def float_kernel_f64(val, K=None, accumulate=False, mirror=True):
+    """``K = V V^T`` of a float64 CUDA tensor [n_iid, n_sid] (C- or F-contiguous) in float64 arithmetic (``pstb_float_kernel_f64``)."""
+    _lib.require_gpu()
+    assert val.dtype == torch.float64, "the float64 kernel path takes float64 values"
+    n, m = val.shape
+    if val.is_contiguous():
+        order = _lib.ORDER_C
+    elif val.t().is_contiguous():
+        order = _lib.ORDER_F
+    else:
+        val, order = val.contiguous(), _lib.ORDER_C
+    dev = val.device
+    with torch.cuda.device(dev):
+        if K is None:
+            K = torch.zeros((n, n), dtype=torch.float64, device=dev)
+            accumulate = False
+        check(lib.pstb_float_kernel_f64(val.data_ptr(), order, n, m, K.data_ptr(), int(bool(accumulate)), int(bool(mirror)), _stream()))
+    return K
+
+
 def default_kernel_chunk(n_iid, n_sid):
     """SNPs per operand-plane chunk, a multiple of 64.
 

@@ -60,6 +60,71 @@ def snp_kernel_sharded(store_shard, partial_kernel_fn, n_iid, group=None, mirror
     return K, stats
 
 
+def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardizer_spec=("unit",), count_A1=False, chunk=None,
+                                  bands=8, reserve_sms=16, tiles=None, K=None):
+    """SNP-sharded SnpKernel with the NCCL reduction OVERLAPPED: this rank's partial K accumulates in compact
+    lower-triangular tiles; the LAST chunk of SNPs is multiplied band by band (``pstb_snp_kernel_tiles_band``) and, as soon as a band
+    of tiles is final, it is all-reduced on a side stream and expanded into the square K while the later bands still multiply
+    (``reserve_sms`` SMs are left to the collective).  Only the last band's reduction (1 / bands of the triangle) stays exposed.
+    Returns ``(K, stats_local)``: float32 CUDA tensor [n, n] (both triangles) and this rank's float64 statistics [m_local, 2]."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib, device
+    lib, check = _lib.lib, _lib.check
+    dev = store.device
+    n, m_local = int(n_iid), store.sid_count
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    chunk = int(chunk or device.default_kernel_chunk(n, m_local))
+    low_term = device.low_term_for(total_sid, n, standardizer_spec)
+    coords = device.kernel_tile_coords(n)
+    ntiles = len(coords)
+    with torch.cuda.device(dev):
+        if tiles is None:
+            tiles = torch.empty((ntiles, 256, 256), dtype=torch.float32, device=dev)
+        if K is None:
+            K = torch.empty((n, n), dtype=torch.float32, device=dev)
+        stats = torch.empty((m_local, 2), dtype=torch.float64, device=dev)
+        if m_local == 0:
+            tiles.zero_()
+        head = ((m_local - 1) // chunk) * chunk if m_local > 0 else 0
+        if head > 0:
+            _t, _c, st_head = device.snp_kernel_tiles(store, None, slice(0, head), count_A1=count_A1, standardizer=standardizer_spec, chunk=chunk,
+                                                      tiles=tiles, accumulate=False, low_term=low_term)
+            stats[:head] = st_head
+        bands = max(1, min(int(bands), ntiles))
+        edges = [ntiles * b // bands for b in range(bands + 1)]
+        main = torch.cuda.current_stream()
+        comm = torch.cuda.Stream(device=dev)
+        comm.wait_stream(main)
+        mode, a, b = device._mode_args(standardizer_spec)
+        wbytes = int(lib.pstb_kernel_workspace_bytes(n, chunk))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        iid_ax = _lib.Axis(None, 0, 1, n)
+        sid_ax = _lib.Axis(None, head, 1, m_local - head)
+        tail_stats = stats[head:] if m_local > head else stats
+        for bnd in range(bands):
+            t0, t1 = edges[bnd], edges[bnd + 1]
+            if t1 <= t0:
+                continue
+            if m_local > head:
+                check(lib.pstb_snp_kernel_tiles_band(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, iid_ax, sid_ax, int(bool(count_A1)),
+                                                     mode, a, b, 0, tail_stats.data_ptr(), tiles.data_ptr(), 0, 1, int(head > 0), work.data_ptr(), wbytes, chunk,
+                                                     device._LOW_TERM[low_term], t0, t1, 1 if bnd == 0 else 0, int(reserve_sms) if world > 1 else 0,
+                                                     main.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                if world > 1:
+                    dist.all_reduce(tiles[t0:t1], op=dist.ReduceOp.SUM, group=group)
+                check(lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), n, 0, 1, t0, t1, K.data_ptr(), comm.cuda_stream))
+        main.wait_stream(comm)
+        tiles.record_stream(comm)
+        K.record_stream(comm)
+        work.record_stream(main)
+    return K, stats
+
+
 def distributed_bed_partial_kernel(dbed, rank, world, standardizer_spec=("unit",), chunk=None):
     """This rank's share of ``K`` for a :class:`DistributedBed`: the lower triangle accumulated over the pieces
     ``assign_pieces`` gives it (each piece file is read by one rank only).  Returns ``(K_r, stats_r, sid_positions_r)``:
@@ -109,13 +174,9 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     if world == 1:
         K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=True)
     else:
-        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix.
-        # The low-term mode "auto" looks at one call's SNP count; this kernel's is the global one.
-        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
-                                                        low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec))
-        allreduce_sum_(tiles, group)
-        K = device.kernel_from_tiles(tiles, bed.iid_count)
-        del tiles
+        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix, band by band
+        # under the multiplication of the last SNP chunk (the low-term mode follows the SNP count of the whole kernel)
+        K, stats = snp_kernel_sharded_overlapped(store, bed.iid_count, bed.sid_count, group, standardizer_spec, bed.count_A1, chunk)
         counts = [shard_range(bed.sid_count, r, world)[1] - shard_range(bed.sid_count, r, world)[0] for r in range(world)]
         stats = allgather_rows(stats, counts, group)
     return K, stats

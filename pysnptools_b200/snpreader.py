@@ -220,15 +220,19 @@ class SnpReader(object):
             # Identity: x = dosage, missing -> 0 (the reference would propagate NaN; documented difference)
             spec, stats = ("unit",), np.tile(np.array([[0.0, 1.0]]), (len(sid_labels), 1))
         chunk = _kernel_chunk(block_size, self.iid_count, self.sid_count)
+        exact = dtype == np.float64 and _KERNEL_FLOAT64[0] == "exact"
         if not to_device and getattr(root, "_device_store", True) is None and dtype in (np.float32, np.float64):
             # file -> host K in one call: the packed records are streamed to the GPU while earlier ones are multiplied
-            val, st = root._kernel_host(iid_idx, sid_idx, spec, stats, dtype, chunk)
+            val, st = root._kernel_host(iid_idx, sid_idx, spec, stats, dtype, chunk, exact=exact)
             if order == "F":
                 val = val.T
             return (val, standardizer._make_trained(sid_labels, st.astype(dtype))) if return_trained else val
         store, ssel_local = root._store_for(sid_idx)
-        K32, d_stats = device.snp_kernel(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats, chunk=chunk)
-        out = device.convert_kernel(K32, dtype)
+        if exact:
+            out, d_stats = device.snp_kernel_f64(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats)
+        else:
+            K32, d_stats = device.snp_kernel(store, iid_idx, ssel_local, count_A1=root.count_A1, standardizer=spec, stats=stats, chunk=chunk)
+            out = device.convert_kernel(K32, dtype)
         val = out if to_device else _symmetric_to_host(out, order)
         if return_trained:
             st = d_stats.cpu().numpy().astype(dtype if dtype in (np.float32, np.float64) else np.float64)
@@ -240,6 +244,22 @@ class SnpReader(object):
 
     def __repr__(self):
         return "{0}()".format(self.__class__.__name__)
+
+
+_KERNEL_FLOAT64 = ["tensor"]
+
+
+def set_kernel_float64(mode):
+    """What a ``dtype=float64`` kernel request computes with: ``"tensor"`` (default) -- the tcgen05 path (fp32 accumulation, <= 1e-5
+    relative Frobenius error, the north_star gate) converted to float64; ``"exact"`` -- float64 arithmetic on the GPU
+    (``pstb_snp_kernel_f64`` / ``pstb_float_kernel_f64``), which is what the reference's ``val.dot(val.T)`` is for float64 values
+    (snpdata.py:203-206) and what its 10-decimal unit tests need.  ``dtype=float32`` requests always use the tensor cores.
+    Returns the previous mode."""
+    if mode not in ("tensor", "exact"):
+        raise ValueError("mode must be 'tensor' or 'exact'")
+    prev = _KERNEL_FLOAT64[0]
+    _KERNEL_FLOAT64[0] = mode
+    return prev
 
 
 def _kernel_chunk(block_size, n_iid, n_sid):
@@ -420,7 +440,7 @@ class Bed(SnpReader):
     def _can_fuse(self):
         return True
 
-    def _kernel_host(self, iid_idx, sid_idx, spec, stats_in, dtype, chunk):
+    def _kernel_host(self, iid_idx, sid_idx, spec, stats_in, dtype, chunk, exact=False):
         """``pstb_snp_kernel_host``: memory-mapped file bytes -> K as a NumPy array (C order, symmetric) + float64 statistics."""
         packed = self._packed_host()
         n, m = self.iid_count, self.sid_count
@@ -437,9 +457,12 @@ class Bed(SnpReader):
         a, b = (float(spec[1]), float(spec[2])) if spec[0] == "beta" else (float("nan"), float("nan"))
         if ni:
             _lib.require_gpu()
-            _lib.check(_lib.lib.pstb_snp_kernel_host(packed.ctypes.data if m else None, n, m, ii.ctypes.data if ii is not None else None, ni,
-                                                     si.ctypes.data if si is not None else None, ns, int(bool(self.count_A1)), mode, a, b,
-                                                     use_stats, stats.ctypes.data, K.ctypes.data, _DT_CODE[np.dtype(dtype)], int(chunk), _lib.LOW_TERM_DEFAULT))
+            args = (packed.ctypes.data if m else None, n, m, ii.ctypes.data if ii is not None else None, ni,
+                    si.ctypes.data if si is not None else None, ns, int(bool(self.count_A1)), mode, a, b, use_stats, stats.ctypes.data, K.ctypes.data)
+            if exact:
+                _lib.check(_lib.lib.pstb_snp_kernel_host_f64(*args, int(chunk)))
+            else:
+                _lib.check(_lib.lib.pstb_snp_kernel_host(*args, _DT_CODE[np.dtype(dtype)], int(chunk), _lib.LOW_TERM_DEFAULT))
         return K, stats
 
     # --- read (bed.py:318-345 -> bed_reader read_f32/f64/i8) ---
@@ -644,8 +667,11 @@ class SnpData(SnpReader):
             data = SnpData(self.iid, self.sid, self.val.clone() if _is_tensor(self.val) else np.array(self.val, order="A"), pos=self.pos)
             data, trained = data.standardize(standardizer, return_trained=True, num_threads=num_threads)
         v = data.val if _is_tensor(data.val) else torch.from_numpy(np.ascontiguousarray(data.val)).cuda()
-        K32 = device.float_kernel(v)
-        out = device.convert_kernel(K32, dtype)
+        if dtype == np.float64 and _KERNEL_FLOAT64[0] == "exact":
+            out = device.float_kernel_f64(v.double())
+        else:
+            K32 = device.float_kernel(v)
+            out = device.convert_kernel(K32, dtype)
         val = out if to_device else _symmetric_to_host(out, order)
         return (val, trained) if return_trained else val
 

@@ -27,8 +27,8 @@ def rand_store(n, m, missing=False):
         t = t & ~(lo & ~hi)            # code 01 -> 00
     return dev.PackedStore(t, n, m)
 
-def run(tag, n, m, dtype, order, std, isel=None, ssel=None, missing=False):
-    store = rand_store(n, m, missing)
+def run(tag, n, m, dtype, order, std, isel=None, ssel=None, missing=False, store=None):
+    store = store or rand_store(n, m, missing)
     I = dev.Selection(isel, n, "cuda"); S = dev.Selection(ssel, m, "cuda")
     es = np.dtype(dtype).itemsize
     code, base, view = dev._alloc_out(I.n, S.n, dtype, order, "cuda")
@@ -41,7 +41,7 @@ def run(tag, n, m, dtype, order, std, isel=None, ssel=None, missing=False):
     algo = S.n * ((n + 3) // 4) + es * I.n * S.n + (16 * S.n if std else 0)
     print("%-34s n=%d m=%d out=%dx%d %s %s: %.3f ms  %.3e genotypes/s  %.0f GB/s algorithmic = %.1f%% of %.0f"
           % (tag, n, m, I.n, S.n, np.dtype(dtype).name, order, ms, I.n * S.n / ms * 1e3, algo / ms / 1e6, 100 * algo / ms / 1e6 / PEAK, PEAK), flush=True)
-    del store, base, view
+    del base, view
 
 import signal; signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 which = sys.argv[1:] or ["cfg2", "cfg4", "variants"]
@@ -53,6 +53,19 @@ if "peaks" in which:
     del a, b
 if "cfg2" in which:
     run("cfg2 decode+Unit", 10000, 1000000, np.float32, "F", ("unit",))
+if "cfg4real" in which:
+    # the same selection on a store with the genotype distribution of SURVEY 8d (p ~ U(.05,.5), Binomial(2,p), 5 % missing) instead of random bytes
+    import bench
+    rng = np.random.default_rng(1)
+    N, M = 100000, 200000
+    ii, si = rng.permutation(N)[: N // 2], rng.permutation(M)[: M // 2]
+    real = bench.gen_store_device(dev, torch, N, M, seed=4000, missing_rate=0.05)
+    run("cfg4 real genotypes, Beta", N, M, np.float32, "F", ("beta", 1, 25), ii, si, store=real)
+    run("cfg4 real genotypes, Unit", N, M, np.float32, "F", ("unit",), ii, si, store=real)
+    run("cfg4 real genotypes, decode only", N, M, np.float32, "F", None, ii, si, store=real)
+    run("cfg4 real, sorted iid subset", N, M, np.float32, "F", ("beta", 1, 25), np.sort(ii), si, store=real)
+    run("cfg4 random bytes, Beta", N, M, np.float32, "F", ("beta", 1, 25), ii, si, missing=True)
+    run("cfg4 random bytes, Unit", N, M, np.float32, "F", ("unit",), ii, si, missing=True)
 if "cfg4" in which:
     rng = np.random.default_rng(1)
     N, M = 100000, 200000

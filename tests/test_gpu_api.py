@@ -386,3 +386,33 @@ def test_read_into_out_and_pinned_buffers(golden):
     del buf, d, d2
     import gc
     gc.collect()
+
+
+def test_kernel_float64_exact_switch(golden):
+    """set_kernel_float64("exact"): dtype=float64 kernels in float64 arithmetic on the GPU (file path, device-store path, in-memory values);
+    float32 requests keep the tensor cores; the default ("tensor") is restored afterwards."""
+    import pysnptools_b200 as p
+    bed = p.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    want = golden["n300_unit_K"]
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert p.set_kernel_float64("exact") == "tensor"
+    try:
+        K = bed.read_kernel(p.Unit(), block_size=100).val                         # host path: pstb_snp_kernel_host_f64
+        assert K.dtype == np.float64 and rel(K, want) < 1e-12
+        sub = bed[::2, 5:900]
+        x = sub.read().standardize(p.Unit()).val
+        assert rel(sub.read_kernel(p.Unit()).val, x.dot(x.T)) < 1e-12
+        sub.read(dtype=np.float32)                                                # puts the packed store on the device
+        bed._store_for(None)
+        assert rel(bed.read_kernel(p.Unit()).val, want) < 1e-12                   # device-store path: pstb_snp_kernel_f64
+        data = bed.read()
+        assert rel(data.read_kernel(p.Unit()).val, want) < 1e-12                  # in-memory values: pstb_float_kernel_f64
+        K32 = bed.read_kernel(p.Unit(), dtype=np.float32).val
+        assert K32.dtype == np.float32 and 1e-9 < rel(K32.astype(np.float64), want) < 1e-5
+    finally:
+        assert p.set_kernel_float64("tensor") == "exact"
+    assert 1e-9 < rel(bed.read_kernel(p.Unit()).val, want) < 1e-5
+    with pytest.raises(ValueError):
+        p.set_kernel_float64("fp8")

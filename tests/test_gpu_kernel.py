@@ -2,6 +2,8 @@
 
 Gate (north_star): relative Frobenius error <= 1e-5.  The fp16 hi/lo split lands near 1e-7.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -355,3 +357,82 @@ def test_low_term_is_per_call_under_threads(oracle, dev):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not bad, bad
+
+
+def test_float64_kernel_path(oracle, dev):
+    """K3 in float64 (syrk_f64.cu): the dtype=float64 contract of the reference (val.dot(val.T) is a DGEMM then, snpdata.py:203-206; its
+    tests compare float64 kernels to 10 decimals).  Fused decode + standardize into a float64 panel + fp64-FMA SYRK: ~1e-14 relative to the
+    float64 oracle, for missing data, Beta, gathered axes, trained statistics, ragged chunks, accumulation over SNP halves; plus the
+    float-matrix and host-buffer entry points."""
+    import ctypes
+    import torch
+    from pysnptools_b200 import _lib
+    n, m = 700, 1500
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.05, seed=21)
+    packed[7, :] = 0x55                                                   # an all-missing SNP and an SNC one
+    packed[8, :] = 0xFF
+    store = dev.PackedStore.from_host(packed, n)
+    for std, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        ref, rst = oracle.read_kernel(packed, n, **args)
+        for chunk in (None, 100, 64):
+            K, st = dev.snp_kernel_f64(store, standardizer=std, chunk=chunk)
+            Kc = K.cpu().numpy()
+            assert K.dtype == torch.float64 and np.array_equal(Kc, Kc.T) and not np.isnan(Kc).any()
+            assert rel_fro(Kc, ref) < 1e-13, (std, chunk, rel_fro(Kc, ref))
+            assert np.max(np.abs(Kc - ref)) < 1e-10 * max(1.0, np.max(np.abs(ref)) / 1e3)      # the reference's "10 decimals" at these magnitudes
+        np.testing.assert_allclose(st.cpu().numpy(), rst, rtol=1e-12, equal_nan=True)
+    rng = np.random.default_rng(2)
+    ii, si = rng.permutation(n)[:333], rng.permutation(m)[:1000]
+    ref, rst = oracle.read_kernel(packed, n, iid_index=ii, sid_index=si, count_A1=True)
+    K, st = dev.snp_kernel_f64(store, ii, si, count_A1=True, chunk=256)
+    assert rel_fro(K.cpu().numpy(), ref) < 1e-13
+    K2, _ = dev.snp_kernel_f64(store, ii, si, count_A1=True, stats=st, chunk=256)              # trained statistics
+    assert rel_fro(K2.cpu().numpy(), ref) < 1e-13
+    Ka, _ = dev.snp_kernel_f64(store, ii, si[:500], count_A1=True, chunk=128, mirror=False)
+    Ka, _ = dev.snp_kernel_f64(store, ii, si[500:], count_A1=True, chunk=128, K=Ka, accumulate=True)
+    assert rel_fro(Ka.cpu().numpy(), ref) < 1e-13
+    # float matrices, C and F order
+    v = rng.standard_normal((130, 777))
+    want = v.dot(v.T)
+    for arr in (np.ascontiguousarray(v), np.asfortranarray(v)):
+        t = torch.from_numpy(arr).cuda() if arr.flags["C_CONTIGUOUS"] else torch.from_numpy(arr.T).cuda().t()
+        Kf = dev.float_kernel_f64(t).cpu().numpy()
+        assert rel_fro(Kf, want) < 1e-14 and np.array_equal(Kf, Kf.T)
+    # host-buffer entry point, several slices
+    lib, check = _lib.lib, _lib.check
+    os.environ["PSTB_KERNEL_SLICE_SNPS"] = "512"
+    try:
+        ref, rst = oracle.read_kernel(packed, n)
+        Kh = np.empty((n, n))
+        sth = np.empty((m, 2))
+        check(lib.pstb_snp_kernel_host_f64(packed.ctypes.data, n, m, None, n, None, m, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
+                                           sth.ctypes.data, Kh.ctypes.data, 128))
+        assert rel_fro(Kh, ref) < 1e-13 and np.array_equal(Kh, Kh.T)
+        np.testing.assert_allclose(sth, rst, rtol=1e-12, equal_nan=True)
+    finally:
+        del os.environ["PSTB_KERNEL_SLICE_SNPS"]
+    _lib.lib.pstb_host_release()
+
+
+@pytest.mark.parametrize("n,m,chunk,bands", [(700, 1000, 256, 4), (1300, 200, 256, 3), (515, 512, 256, 8), (300, 0, 64, 2)])
+def test_banded_last_chunk_matches_plain_kernel(n, m, chunk, bands, oracle, dev):
+    """The overlapped multi-GPU reduction multiplies the last SNP chunk band by band (pstb_snp_kernel_tiles_band) and expands finished
+    bands on a side stream (pstb_kernel_from_tiles_range).  On one GPU (no collective) the result must equal the plain kernel: same
+    planes, same tiles, only the rank-one part is added per call."""
+    import torch
+    from pysnptools_b200 import parallel
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + m) if m else np.zeros((0, (n + 3) // 4), dtype=np.uint8)
+    store = dev.PackedStore.from_host(packed, n)
+    for std in (("unit",), ("beta", 1, 25)):
+        K, st = parallel.snp_kernel_sharded_overlapped(store, n, m, None, std, chunk=chunk, bands=bands)
+        torch.cuda.synchronize()
+        Kp, stp = dev.snp_kernel(store, standardizer=std, chunk=chunk, low_term=dev.low_term_for(m, n, std))
+        Kc, Kpc = K.double().cpu().numpy(), Kp.double().cpu().numpy()
+        assert np.array_equal(Kc, Kc.T)
+        if m:
+            assert rel_fro(Kc, Kpc) < 3e-7, rel_fro(Kc, Kpc)
+            assert np.array_equal(st.cpu().numpy(), stp.cpu().numpy())
+            ref, _ = oracle.read_kernel(packed, n, **({} if std[0] == "unit" else dict(is_beta=True, a=1, b=25)))
+            assert rel_fro(Kc, ref) < K_TOL
+        else:
+            assert not Kc.any()

@@ -410,3 +410,50 @@ def test_reference_kernel_tests_on_patched_reference(ref, ref_examples, ref_main
     assert result.testsRun == 1
     if name in ("test_subset", "test_npz"):
         assert patched.launches() > l0, "the kernel of this test should have run on the GPU"
+
+
+@pytest.fixture()
+def patched_exact(ref):
+    from pysnptools_b200.compat import patch
+    patch.patch_reference(float64="exact")
+    yield patch
+    patch.unpatch_reference()
+
+
+@pytest.mark.parametrize("module,cls,name", PATCHED_TESTS, ids=["exact-" + t[2] for t in PATCHED_TESTS])
+def test_reference_kernel_tests_on_patched_reference_float64_exact(ref, ref_examples, ref_main_tests, patched_exact, module, cls, name):
+    """patch_reference(float64="exact"): a dtype=float64 kernel request runs the library's float64 path (syrk_f64.cu), a float32 one the
+    tensor cores.  EVERY kernel test of the reference passes then, the 10-decimal comparisons included, with the GPU doing the work."""
+    import importlib
+    import unittest
+    mod = importlib.import_module(module)
+    case_cls = getattr(mod, cls)
+    if name not in unittest.defaultTestLoader.getTestCaseNames(case_cls):
+        pytest.skip("{0}.{1} has no {2} in this reference version".format(module, cls, name))
+    l0 = patched_exact.launches()
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(mod.__file__))
+    try:
+        result = unittest.TestResult()
+        unittest.TestSuite([case_cls(name)]).run(result)
+    finally:
+        os.chdir(cwd)
+    problems = result.failures + result.errors
+    assert not problems, problems[0][1]
+    assert result.testsRun == 1
+    if name in ("test_subset", "test_npz", "test_merge_std", "test_respect_inputs", "test_some_std"):
+        assert patched_exact.launches() > l0, "the kernel of this test should have run on the GPU"
+
+
+def test_patched_reference_float64_exact_matches_goldens_to_1e12(ref, patched_exact, golden):
+    bed = ref.Bed(os.path.join(DATA_DIR, "n300.bed"), count_A1=False)
+    K = bed.read_kernel(ref.Unit(), block_size=100).val
+    assert K.dtype == np.float64 and rel_fro(K, golden["n300_unit_K"]) < 1e-12
+    assert abs(K[0, 0] - 901.421836) < 1e-6                                    # doctest scalar snpreader.py:308-313
+    Kb = ref.SnpKernel(bed, ref.Beta(1, 25), block_size=333).read().val
+    assert rel_fro(Kb, golden["n300_beta_1_25_K"]) < 1e-12
+    toy = ref.Bed(os.path.join(DATA_DIR, "toydata.bed"), count_A1=False)
+    Kt = ref.SnpKernel(toy, ref.Unit(), block_size=2500).read().val
+    assert rel_fro(Kt, golden["toydata_unit_K_shipped"]) < 1e-12 and np.max(np.abs(Kt - golden["toydata_unit_K_shipped"])) < 1e-9
+    K32 = bed.read_kernel(ref.Unit(), dtype=np.float32).val                   # float32 requests stay on the tensor cores
+    assert K32.dtype == np.float32 and 1e-9 < rel_fro(K32.astype(np.float64), golden["n300_unit_K"]) < 1e-5

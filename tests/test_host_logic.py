@@ -477,3 +477,35 @@ def test_fusion_is_a_reader_capability():
     with pytest.raises(ValueError):
         data.read(out=ro)
     assert np.array_equal(data.val, data.read(standardizer=None).val)       # the source is never standardized in place by read()
+
+
+def test_bench_sampled_tile_parity_checker(oracle):
+    """bench.py's K checker (sampled 256 x 256 tiles against the oracle, stratified whole-matrix estimate) on a small case without a GPU:
+    an exact K scores ~1e-16, a K with a known relative perturbation scores that perturbation, Beta and ragged last blocks included."""
+    import types
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    n, m = 700, 320
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.05, seed=4)
+    store = types.SimpleNamespace(tensor=torch.from_numpy(packed.copy()), iid_count=n, sid_count=m)
+    for spec, args in ((("unit",), {}), (("beta", 1, 25), dict(is_beta=True, a=1, b=25))):
+        K, stats = oracle.read_kernel(packed, n, **args)
+        blocks = bench.pick_blocks(n, 3, seed=1)
+        assert blocks == [0, 1, 2]                                        # T = 3 row blocks, the last one ragged (188 rows)
+
+        def fetch(I, J, K=K):
+            out = np.zeros((256, 256))
+            sub = K[I * 256:I * 256 + 256, J * 256:J * 256 + 256]
+            out[: sub.shape[0], : sub.shape[1]] = sub
+            return out
+        res = bench.sampled_tile_parity(torch, None, 1, 0, bench._oracle_lib(), store, torch.from_numpy(stats), n, spec, fetch, blocks)
+        assert res["sampled_tiles"] == 6 and res["diagonal_tiles"] == 3 and res["stats_match_oracle_rtol_1e-12"]
+        assert res["worst_rel_frobenius_vs_oracle"] < 1e-12 and res["rel_frobenius_whole_K_estimate"] < 1e-12
+        res = bench.sampled_tile_parity(torch, None, 1, 0, bench._oracle_lib(), store, torch.from_numpy(stats), n, spec,
+                                        lambda I, J: fetch(I, J) * (1 + 3e-6), blocks)
+        assert abs(res["worst_rel_frobenius_vs_oracle"] - 3e-6) < 1e-9 and abs(res["rel_frobenius_whole_K_estimate"] - 3e-6) < 1e-9
+        assert abs(res["diag_rel_bias"] - 3e-6) < 1e-9
+        wrong = stats.copy()
+        wrong[0, 0] += 1e-6
+        assert not bench.sampled_tile_parity(torch, None, 1, 0, bench._oracle_lib(), store, torch.from_numpy(wrong), n, spec, fetch, blocks)["stats_match_oracle_rtol_1e-12"]

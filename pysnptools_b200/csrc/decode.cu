@@ -44,6 +44,7 @@ struct ReadParams {
     long long seg_len;      // outputs per segment (multiple of 16) when direct
     int vec_ok;             // output columns: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = neither
     unsigned int* miss_flag;    // optional: set to 1 when any selected genotype of any processed SNP is missing (K3 picks its GEMM by it)
+    int l2_prefetch;            // staged gather: prefetch the records two batches ahead into L2
     const uint32_t* sel_mask;   // gather: 2 bits per individual (0b01 = selected), built once per call; word [mask_words] = "index vector has repeats"
     long long mask_words;
 };
@@ -682,6 +683,26 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
     }
 }
 
+// The selection mask below is a stream-ordered allocation (cudaMallocAsync: safe for concurrent callers on different streams).  The
+// default memory pool hands its memory back to the driver at every synchronisation unless told otherwise, which made every gathered
+// read pay a driver allocation on the HOST side -- 0.1 to several ms between the caller's events: cfg4 measured anywhere from 4.3 to
+// 11.8 ms per call for the same 4.3 ms kernel.  Keep up to 64 MiB in the pool of each device this library allocates from.
+static void keep_pool_memory(cudaStream_t) {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t cur = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < (64ull << 20)) {
+            uint64_t keep = 64ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    cudaGetLastError();
+    done_for = dev;
+}
+
 // Selection mask for the statistics of gathered reads: bit 2*(i%16) of word i/16 is set when individual i is selected.
 // Per-SNP dosage counts over the selected individuals then are masked popcounts over the raw record -- a coalesced
 // sweep instead of a second random gather.  A repeated index (the counts would need multiplicities) raises the flag in
@@ -745,12 +766,23 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
         for (int s = 0; s < 4; ++s)
             bulk_g2s(raw0 + (size_t)s * p.raw_stride, p.packed + clampll(p.sid.at(bb + min(s, nn - 1)), p.sid_count) * p.ld, p.copy_bytes, &stage_bar);
     };
+    // ... and the batch after the staged one into L2 (no shared memory needed), by four lanes of another warp: the staging copy then is an
+    // L2 hit instead of a DRAM read that has to find its way through the write flood within ONE batch time.  Without it the kernel's time
+    // depended on where the buffers happened to lie in HBM: 4.3 ms in one process, 5.6 - 11.8 ms in the next (cfg4, same data).
+    auto prefetch_l2 = [&](long long batch) {
+        if (!p.l2_prefetch || batch >= nbatch || tid < 32 || tid >= 36) return;
+        const long long j = (batch << 2) + (tid - 32);
+        if (j >= p.sid.n) return;
+        const uint8_t* src = p.packed + clampll(p.sid.at(j), p.sid_count) * p.ld;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(p.copy_bytes) : "memory");
+    };
     if (kStaged) {
         if (tid == 0) {
             mbar_init(&stage_bar, 1);
             fence_mbar_init();
             if ((long long)blockIdx.x < nbatch) issue(blockIdx.x);
         }
+        prefetch_l2((long long)blockIdx.x + gridDim.x);
         __syncthreads();
     }
     uint32_t iter = 0;
@@ -832,6 +864,7 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
         }
         __syncthreads();
         if (kStaged && tid == 0 && batch + gridDim.x < nbatch) issue(batch + gridDim.x);   // staging area is free again
+        if (kStaged) prefetch_l2(batch + 2 * (long long)gridDim.x);
         // ---- pass 1: dosage counts of the 4 SNPs over the selected individuals ----
         if (p.mode != PSTB_STD_NONE) {
             if (!p.use_stats && !mask_count) {
@@ -1284,6 +1317,9 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
             const unsigned staged_bytes = inter_bytes + 4u * rec16;
             const bool staged = p.bulk_ok && staged_bytes <= max_smem && !getenv("PSTB_GATHER_NOSTAGE");
             if (staged) {
+                // optional (PSTB_GATHER_L2PF=1): measured 74-79 % of the HBM peak with it, 79-80 % without on cfg4
+                p.l2_prefetch = (getenv("PSTB_GATHER_L2PF") && atoi(getenv("PSTB_GATHER_L2PF")) != 0) ? 1 : 0;
+                keep_pool_memory(st);
                 uint32_t* d_mask = nullptr;
                 if (p.mode != PSTB_STD_NONE && !p.use_stats) {
                     p.mask_words = (p.iid_count + 15) / 16;

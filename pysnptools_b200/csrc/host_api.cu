@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "pstb_common.cuh"
@@ -97,8 +100,10 @@ bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-// pageable destinations: copy out of the pinned ring with several host threads (a single memcpy stream tops out near
-// 10 GB/s and first-touch page faults of a fresh NumPy array are serial otherwise)
+// pageable destinations: copy out of the pinned ring with several host threads (a single memcpy stream tops out near 10 GB/s and
+// first-touch page faults of a fresh NumPy array are serial otherwise).  Measured on a 16-core B200 host (scripts/probe_pagefault.py):
+// a fresh array fills at 35 GB/s with 8 threads and 51 GB/s with 16 (107 GB/s once its pages exist), so the default is all cores but
+// two (the caller's thread keeps enqueueing GPU work, the CUDA driver has threads of its own), at most 16.
 int host_copy_threads() {
     if (const char* e = getenv("PSTB_HOST_COPY_THREADS")) {          // experiments
         const int v = atoi(e);
@@ -106,26 +111,96 @@ int host_copy_threads() {
     }
     static int n = [] {
         unsigned hc = std::thread::hardware_concurrency();
-        int v = hc ? (int)hc / 2 : 4;                    // measured: 8 of 16 cores 1.96 s for a fresh 40 GB result, 14 cores 2.7 s
-        return v < 1 ? 1 : (v > 16 ? 16 : v);
+        int v = hc ? (int)hc - 2 : 4;
+        return v < 2 ? 2 : (v > 16 ? 16 : v);
     }();
     return n;
 }
 
+// A persistent pool of copy threads per calling thread.  Round 1 spawned fresh std::threads for every 64 MiB chunk; their creation is
+// serial in the caller (~0.1 ms each), so 8 threads delivered 28 GB/s inside the pipeline against 77 GB/s for the same memcpy alone.
+class CopyPool {
+  public:
+    ~CopyPool() { stop(); }
+    template <typename F>
+    void run(size_t count, size_t min_per_thread, F&& body) {
+        int nt = host_copy_threads();
+        if (count < 2 * min_per_thread) nt = 1;
+        if ((size_t)nt > count / (min_per_thread ? min_per_thread : 1)) nt = (int)(count / (min_per_thread ? min_per_thread : 1));
+        if (nt <= 1) { body((size_t)0, count); return; }
+        ensure(nt - 1);
+        const size_t per = (count + nt - 1) / nt;
+        std::function<void(size_t, size_t)> fn = std::ref(body);
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            job_ = &fn;
+            count_ = count;
+            per_ = per;
+            active_ = nt - 1;
+            pending_ = nt - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        body((size_t)0, per < count ? per : count);                 // the caller takes the first range
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+  private:
+    void ensure(int workers) {
+        while ((int)th_.size() < workers) {
+            const int id = (int)th_.size();
+            th_.emplace_back([this, id] { loop(id); });
+        }
+    }
+    void loop(int id) {
+        long long seen = 0;
+        for (;;) {
+            std::function<void(size_t, size_t)>* job = nullptr;
+            size_t lo = 0, hi = 0;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (id >= active_) continue;                        // this job uses fewer workers
+                job = job_;
+                lo = (size_t)(id + 1) * per_;
+                hi = lo + per_ < count_ ? lo + per_ : count_;
+            }
+            if (job && lo < hi) (*job)(lo, hi);
+            std::unique_lock<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    void stop() {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::function<void(size_t, size_t)>* job_ = nullptr;
+    size_t count_ = 0, per_ = 0;
+    int active_ = 0, pending_ = 0;
+    long long generation_ = 0;
+    bool stop_ = false;
+};
+
+CopyPool& copy_pool() {
+    static thread_local CopyPool pool;
+    return pool;
+}
+
 template <typename F>
 void parallel_ranges(size_t count, size_t min_per_thread, F&& body) {
-    int nt = host_copy_threads();
-    if (count < 2 * min_per_thread) nt = 1;
-    if ((size_t)nt > count / min_per_thread) nt = (int)(count / min_per_thread);
-    if (nt <= 1) { body((size_t)0, count); return; }
-    std::vector<std::thread> th;
-    const size_t per = (count + nt - 1) / nt;
-    for (int t = 1; t < nt; ++t) {
-        const size_t lo = (size_t)t * per, hi = lo + per < count ? lo + per : count;
-        if (lo < hi) th.emplace_back([&body, lo, hi] { body(lo, hi); });
-    }
-    body((size_t)0, per < count ? per : count);
-    for (auto& x : th) x.join();
+    copy_pool().run(count, min_per_thread, body);
 }
 
 size_t esize_of(int dtype) { return dtype == PSTB_F64 ? 8 : (dtype == PSTB_F32 ? 4 : 1); }
@@ -224,11 +299,19 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
     }
 
     struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kSlots];
+    const bool trace = getenv("PSTB_HOST_TRACE") != nullptr;
+    double t_wait = 0.0, t_copy = 0.0, t_enq = 0.0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return 0;
+        const auto tw = now();
         PSTB_CUDA(cudaEventSynchronize(c.done[slot]));
+        t_wait += ms_since(tw);
         pend[slot].active = false;
         if (out_pinned) return 0;
+        const auto tc = now();
+        struct CopyTimer { double& acc; std::chrono::steady_clock::time_point t0; ~CopyTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } copy_timer{t_copy, tc};
         const int64_t b0 = pend[slot].b0, ns = pend[slot].ns;
         const char* src = (const char*)c.h_out[slot].p;
         if (order == PSTB_ORDER_F) {
@@ -256,6 +339,8 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         const int slot = (int)(ch % kSlots);
         const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
         if ((rc = finish(slot))) break;
+        const auto te = now();
+        struct EnqTimer { double& acc; std::chrono::steady_clock::time_point t0; ~EnqTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } enq_timer{t_enq, te};
         cudaStream_t st = c.s[slot];
         // ---- input records ----
         bool contiguous = true;
@@ -308,6 +393,9 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         int r2 = finish(k);
         if (!rc) rc = r2;
     }
+    if (trace)
+        fprintf(stderr, "[pstb_read_host] %lld chunks of %lld SNPs, %d copy threads: event wait %.1f ms, host copy %.1f ms, enqueue %.1f ms\n",
+                (long long)nchunks, (long long)chunk, host_copy_threads(), t_wait, t_copy, t_enq);
     if (rc) {
         cudaDeviceSynchronize();
         return rc;

@@ -336,7 +336,8 @@ struct SyrkParams {
     int accumulate;
     const Scalars* sc;      // NULL -> out_scale is used as is
     float out_scale;
-    int run_kb_fast;        // k-blocks per TMEM run on the 2-term path
+    int run_kb_fast;        // k-blocks per TMEM run on the 2-term path (tiles on the diagonal)
+    int run_kb_off;         // ... for tiles off the diagonal: their sums have no sign, so the truncating accumulator has no bias to limit
     int compact;            // K is tile storage [ntiles][256][256] (K-tile sharding: this rank's tiles only), 2-CTA kernel only
     // rectangular (train x test) product on stacked planes, 2-CTA kernel only: plane rows [0, row0) hold the column operand,
     // rows [row0, row0 + n) the row operand; tiles are (I, J) with 256 I >= row0 > 256 J; output row = plane row - row0,
@@ -614,9 +615,14 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    // k-blocks per TMEM run: the same number of truncating accumulates (48) per run in both paths unless overridden
-    const int run_kb = fast ? p.run_kb_fast : RUN_KB;
-    const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
+    // k-blocks per TMEM run.  The tensor core truncates on every accumulate, which biases long POSITIVE sums -- the diagonal of K -- so
+    // tiles on the diagonal drain their accumulator every few k-blocks (the same number of truncating accumulates per run in both
+    // paths).  Off the diagonal the partial sums change sign at random and the truncation has no preferred direction: those tiles
+    // (99 % of them) run much longer between drains -- every drain costs the tensor pipe ~500 idle cycles (measured: 3 / 6 / 12 / 24
+    // k-blocks per run = 1339 / 1500 / 1503 / 1570 TFLOP/s on the cfg3 shape).
+    const int run_kb_diag = fast ? p.run_kb_fast : RUN_KB;
+    const int run_kb_offd = (fast && p.run_kb_off > run_kb_diag) ? p.run_kb_off : run_kb_diag;
+    auto run_kb_of = [&](const int2& tile) { return (tile.x == tile.y) ? run_kb_diag : run_kb_offd; };
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
@@ -661,6 +667,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         if (leader && lane == 0) {
             uint32_t stage = 0, phase = 0, run = 0;
             for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+                const int run_kb = run_kb_of(p.tiles[t]);
+                const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
                 for (int r = 0; r < num_runs; ++r, ++run) {
                     const uint32_t acc = run & 1u;
                     mbar_wait(&bar_tempty[acc], ((run >> 1) & 1u) ^ 1u);
@@ -723,6 +731,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         uint32_t run = 0;
         for (int t = cluster_id; t < p.ntiles; t += nclusters) {
             const int2 tile = p.tiles[t];
+            const int run_kb = run_kb_of(tile);
+            const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
             float sum[128];
 #pragma unroll
             for (int q = 0; q < 128; ++q) sum[q] = 0.0f;
@@ -961,7 +971,8 @@ __global__ void __launch_bounds__(256) k_split_planes(const T* val, long long si
 // ---- host helpers --------------------------------------------------------------------------------------------
 // Tuning knobs, read from the environment on every launch (kernel experiments; the defaults are the shipped configuration).
 struct Knobs {
-    int run_kb_fast;   // PSTB_RUN_KB_FAST: k-blocks per TMEM run on the 2-term path (default 6)
+    int run_kb_fast;   // PSTB_RUN_KB_FAST: k-blocks per TMEM run on the 2-term path, diagonal tiles (default 6)
+    int run_kb_off;    // PSTB_RUN_KB_OFF: ... off-diagonal tiles (default 1024 = one run per chunk)
     int tma_out;       // PSTB_SYRK_TMA_OUT: 1 = K leaves through staging tiles + TMA bulk tensor store / reduce-add (default), 0 = per-thread path
     int red_add;       // PSTB_SYRK_RED: per-thread path: 1 = red.global.add.v4.f32 (default), 0 = load + add + store
     int dbg;           // PSTB_SYRK_DBG: timing experiments only (results are wrong): 2 = no K write, 4 = no operand loads
@@ -973,6 +984,8 @@ Knobs knobs() {
     Knobs k;
     k.run_kb_fast = geti("PSTB_RUN_KB_FAST", 6);
     if (k.run_kb_fast < 1 || k.run_kb_fast > 64) k.run_kb_fast = 6;
+    k.run_kb_off = geti("PSTB_RUN_KB_OFF", 1024);
+    if (k.run_kb_off < 1) k.run_kb_off = 1024;
     k.tma_out = geti("PSTB_SYRK_TMA_OUT", 1) != 0 ? 1 : 0;
     k.red_add = geti("PSTB_SYRK_RED", 1) != 0 ? 1 : 0;
     k.dbg = geti("PSTB_SYRK_DBG", 0);
@@ -1150,6 +1163,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
     p.fp8lo = fp8lo;
     const Knobs kn = knobs();
     p.run_kb_fast = kn.run_kb_fast;
+    p.run_kb_off = kn.run_kb_off;
     p.red_add = kn.red_add;
     p.dbg = kn.dbg;
     CUtensorMap map_out;
@@ -1248,6 +1262,7 @@ int launch_cross(const __half* hi, const __half* lo, const __half* p2, int fp8lo
     p.compact = 0;
     p.fp8lo = fp8lo;
     p.run_kb_fast = kn.run_kb_fast;
+    p.run_kb_off = 0;               // a train x test product may pair an individual with itself (positive sums anywhere): short runs for every tile
     p.red_add = kn.red_add;
     p.dbg = kn.dbg;
     CUtensorMap map_out;

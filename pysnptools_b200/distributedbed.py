@@ -116,16 +116,31 @@ class DistributedBed(SnpReader):
         storage = str(storage)
         os.makedirs(storage, exist_ok=True)
         chrom = snpreader.pos[:, 0]
+        for c in sorted(set(chrom.tolist()), key=lambda x: (x != x, x)):
+            # distributedbed.py:167-169: every chromosome must be an integer (a NaN chromosome would be dropped silently otherwise)
+            assert c == c and c == int(c), "DistributedBed.write expects all chromosomes to be integers (not '{0}')".format(c)
         names = []
-        for c in sorted(set(chrom[~np.isnan(chrom)])):
+        for c in sorted(set(chrom)):
             idx = np.nonzero(chrom == c)[0]
             for p in range(piece_per_chrom_count):
                 lo, hi = len(idx) * p // piece_per_chrom_count, len(idx) * (p + 1) // piece_per_chrom_count
-                if hi <= lo:
+                if hi <= lo and piece_per_chrom_count > len(idx):
                     continue
                 name = "chrom{0}.piece{1}of{2}.bed".format(int(c), p, piece_per_chrom_count)
-                if not os.path.exists(os.path.join(storage, name)):       # pieces already present are skipped, as the reference does
-                    Bed.write(os.path.join(storage, name), snpreader[:, idx[lo:hi]].read(dtype=np.float64), count_A1=True)
+                trio = [os.path.join(storage, name[:-3] + ext) for ext in ("bim", "fam", "bed")]
+                present = [os.path.exists(f) for f in trio]
+                if sum(present) < 3:                # a piece is skipped only when all three files exist; leftovers of a partial write are removed
+                    for f, there in zip(trio, present):
+                        if there:
+                            os.remove(f)
+                    Bed.write(trio[-1], snpreader[:, idx[lo:hi]].read(dtype=np.float64), count_A1=True)
                 names.append(name)
-        np.savez(os.path.join(storage, "reader_name_list.npz"), reader_name_list=np.array(names))
-        return DistributedBed(storage)
+        np.savez(os.path.join(storage, "reader_name_list.npz"), reader_name_list=np.array(names, dtype="S"))
+        # metadata.npz: the cache file the reference's DistributedBed opens unconditionally (its _MergeSIDs cache, snpreader/_mergesids.py:9-23:
+        # row / row_property / col / col_property of the merged reader + the SNP count of every piece), so a directory written here reads there
+        out = DistributedBed(storage)
+        out._run_once()
+        np.savez(os.path.join(storage, "metadata.npz"), _row=np.array(out._row, dtype="S"), _row_property=np.empty((len(out._row), 0)),
+                 _col=np.array(out._col, dtype="S"), _col_property=out._col_property,
+                 sid_count_list=np.array([p.sid_count for p in out._pieces], dtype=np.int32))     # snpreader/_mergesids.py:9-23
+        return out

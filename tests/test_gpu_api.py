@@ -296,6 +296,16 @@ def test_distributed_bed(golden, tmp_path):
     back = DistributedBed.write(str(tmp_path / "dist"), _bed("dbx"), piece_per_chrom_count=2)
     assert back.sid_count == 100 and np.array_equal(back.read().val, want, equal_nan=True)
     assert np.array_equal(back.sid, d.sid)
+    buf = np.empty((100, 100), order="F")
+    assert d.read(out=buf).val is buf and np.array_equal(buf, want, equal_nan=True)          # out= on a reader without a fused path
+    assert os.path.exists(str(tmp_path / "dist" / "metadata.npz"))
+    os.remove(str(tmp_path / "dist" / "chrom1.piece0of2.fam"))                                # a partial piece is rewritten, a complete one skipped
+    DistributedBed.write(str(tmp_path / "dist"), _bed("dbx"), piece_per_chrom_count=2)
+    assert os.path.exists(str(tmp_path / "dist" / "chrom1.piece0of2.fam"))
+    bad = _bed("dbx").read()
+    bad.pos[3, 0] = np.nan
+    with pytest.raises(AssertionError, match="integers"):
+        DistributedBed.write(str(tmp_path / "bad"), bad)
 
 
 def test_distributed_bed_pieces_as_rank_shards(golden):

@@ -457,3 +457,90 @@ def test_patched_reference_float64_exact_matches_goldens_to_1e12(ref, patched_ex
     assert rel_fro(Kt, golden["toydata_unit_K_shipped"]) < 1e-12 and np.max(np.abs(Kt - golden["toydata_unit_K_shipped"])) < 1e-9
     K32 = bed.read_kernel(ref.Unit(), dtype=np.float32).val                   # float32 requests stay on the tensor cores
     assert K32.dtype == np.float32 and 1e-9 < rel_fro(K32.astype(np.float64), golden["n300_unit_K"]) < 1e-5
+
+
+def test_reference_nan_cnc_cases_bed_factory(ref, ref_examples, ref_main_tests):
+    """pysnptools/test.py:1201-1358 NaNCNCTestCases, the Bed factory (144 of the 576 generated cases; the others read hdf5 / dat files,
+    other formats): reversed / halved iid and sid index lists x Unit / Beta(1,25) x float64 / float32 x C / F x native / python.  Each case
+    reads through the shim (GPU), plants a NaN and an SNC column, standardizes (GPU; `force_python_only=True` cases run the reference's
+    own python twin) and is compared with the reference's python-twin result at rtol 1e-12 (float64) / 1e-4 (float32)."""
+    import unittest
+    main = ref_main_tests
+    from pysnptools.snpreader import Bed
+    from pysnptools_b200 import _lib
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(main.__file__))
+    l0 = _lib.lib.pstb_launch_count()
+    ran = native = 0
+    try:
+        for case in main.NaNCNCTestCases.factory_iterator():
+            if not isinstance(case.snpreader, Bed):
+                continue
+            result = unittest.TestResult()
+            case.run(result)
+            problems = result.failures + result.errors
+            assert not problems, str(case) + "\n" + problems[0][1]
+            ran += 1
+            native += 0 if case.force_python_only else 1
+    finally:
+        os.chdir(cwd)
+    assert ran == 144 and native == 72
+    assert _lib.lib.pstb_launch_count() > l0 + 72                               # the native half ran on the GPU
+
+
+def test_reference_respect_read_inputs_in_scope_readers(ref, ref_examples, ref_main_tests, tmp_path):
+    """The body of pysnptools/test.py:912-1005 (test_respect_read_inputs) over the readers of this path -- Bed, a Bed subset, _MergeSIDs /
+    _MergeIIDs of Bed reads, DistributedBed, in-memory SnpData (the other entries of the reference's list are hdf5 / dat / ped / npz /
+    SnpGen files, other formats): every order x dtype x force_python_only x view_ok returns the requested dtype and memory order, a
+    non-view read never aliases the source, and every reader survives a pickle round trip (the open_bed handle of the shim included)."""
+    import pickle
+    from pysnptools.snpreader import Bed, DistributedBed, _MergeIIDs, _MergeSIDs
+    toy = os.path.join(ref_examples, "toydata.5chrom.bed")
+    readers = [
+        Bed(toy, count_A1=True),
+        Bed(toy, count_A1=True)[::2, ::2],
+        _MergeSIDs([Bed(toy, count_A1=True)[:, :5].read(), Bed(toy, count_A1=True)[:, 5:].read()]),
+        DistributedBed(os.path.join(DATA_DIR, "distributed_bed_test1")),
+        Bed(toy, count_A1=True).read(),
+        _MergeIIDs([Bed(toy, count_A1=True)[:5, :].read(), Bed(toy, count_A1=True)[5:, :].read()]),
+    ]
+    for snpreader in readers:
+        for order in ["F", "C", "A"]:
+            for dtype in [np.float32, np.float64]:
+                for force_python_only in [True, False]:
+                    for view_ok in [True, False]:
+                        val = snpreader.read(order=order, dtype=dtype, force_python_only=force_python_only, view_ok=view_ok).val
+                        has_right_order = order == "A" or (order == "C" and val.flags["C_CONTIGUOUS"]) or (order == "F" and val.flags["F_CONTIGUOUS"])
+                        if hasattr(snpreader, "val") and not view_ok:
+                            assert snpreader.val is not val
+                        if not force_python_only:
+                            assert val.dtype == dtype and has_right_order, (str(snpreader), order, dtype, view_ok)
+        if isinstance(snpreader, DistributedBed) or hasattr(snpreader, "val") or hasattr(snpreader, "reader_list"):
+            # not picklable in this reference version, shim or not: DistributedBed pieces keep generator-based context managers after a
+            # read (distributedbed.py:236-268) and every SnpData carries its array MODULE (`self._xp`, snpdata.py:86)
+            continue
+        with open(tmp_path / "respect.p", "wb") as f:
+            pickle.dump(snpreader, f)
+        with open(tmp_path / "respect.p", "rb") as f:
+            snpreader_p = pickle.load(f)
+        val_p = snpreader_p.read(order=order, dtype=dtype, force_python_only=force_python_only, view_ok=view_ok).val
+        assert np.allclose(val, val_p, equal_nan=True)
+    import cloudpickle                                                          # test.py:993-1003 uses pickle; cluster runners use cloudpickle
+    bed = Bed(toy, count_A1=True)
+    bed.read()                                                                  # the handle is open now
+    again = cloudpickle.loads(cloudpickle.dumps(bed))
+    assert np.array_equal(again[:7, :9].read().val, bed[:7, :9].read().val, equal_nan=True)
+
+
+def test_distributed_bed_written_here_opens_in_the_reference(ref, golden, tmp_path):
+    """Interop of the shard format: a DistributedBed directory written by this package (pieces + reader_name_list.npz +
+    metadata.npz, the reference's _MergeSIDs cache, snpreader/_mergesids.py:9-23) is read by the reference's own DistributedBed."""
+    import pysnptools_b200 as p
+    from pysnptools.snpreader import DistributedBed as RefDistributedBed
+    src = p.Bed(os.path.join(DATA_DIR, "dbx.bed"), count_A1=False)
+    p.DistributedBed.write(str(tmp_path / "d"), src, piece_per_chrom_count=2)
+    r = RefDistributedBed(str(tmp_path / "d"))
+    want = i8_to_float(golden["dbx_decode_i8"])
+    assert r.iid_count == 100 and r.sid_count == 100
+    assert np.array_equal(r.read().val, want, equal_nan=True)
+    assert list(r.sid) == list(src.sid) and np.array_equal(r.iid, src.iid) and np.allclose(r.pos, src.pos, equal_nan=True)

@@ -615,11 +615,12 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    // k-blocks per TMEM run.  The tensor core truncates on every accumulate, which biases long POSITIVE sums -- the diagonal of K -- so
-    // tiles on the diagonal drain their accumulator every few k-blocks (the same number of truncating accumulates per run in both
-    // paths).  Off the diagonal the partial sums change sign at random and the truncation has no preferred direction: those tiles
-    // (99 % of them) run much longer between drains -- every drain costs the tensor pipe ~500 idle cycles (measured: 3 / 6 / 12 / 24
-    // k-blocks per run = 1339 / 1500 / 1503 / 1570 TFLOP/s on the cfg3 shape).
+    // k-blocks per TMEM run.  The tensor core truncates (rounds toward zero) on every accumulate: every partial sum loses magnitude,
+    // ~2.3e-7 of it per k-block of the run (fitted on cfg3: 6 / 63 k-blocks per run -> 5.3e-6 / 1.5e-5 worst off-diagonal tile, fp8 low
+    // term).  On the diagonal of K -- long positive sums that carry most of the Frobenius norm -- that is a bias, so diagonal tiles drain
+    // their accumulator every 6 k-blocks.  Every drain idles the tensor pipe for ~500 cycles (6 / 12 / 24 / 63 k-blocks per run =
+    // 1485 / 1532 / 1561 / 1624 TFLOP/s on the cfg3 shape), so off-diagonal tiles (99 % of them) run 12 k-blocks: +3 % for ~2.8e-6 of
+    // shrink on entries whose error budget is dominated by the fp8 low term (5e-6).  One run per chunk would be +9 % but 1.5e-5.
     const int run_kb_diag = fast ? p.run_kb_fast : RUN_KB;
     const int run_kb_offd = (fast && p.run_kb_off > run_kb_diag) ? p.run_kb_off : run_kb_diag;
     auto run_kb_of = [&](const int2& tile) { return (tile.x == tile.y) ? run_kb_diag : run_kb_offd; };
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(256) k_split_planes(const T* val, long long si
 // Tuning knobs, read from the environment on every launch (kernel experiments; the defaults are the shipped configuration).
 struct Knobs {
     int run_kb_fast;   // PSTB_RUN_KB_FAST: k-blocks per TMEM run on the 2-term path, diagonal tiles (default 6)
-    int run_kb_off;    // PSTB_RUN_KB_OFF: ... off-diagonal tiles (default 1024 = one run per chunk)
+    int run_kb_off;    // PSTB_RUN_KB_OFF: ... off-diagonal tiles (default 12)
     int tma_out;       // PSTB_SYRK_TMA_OUT: 1 = K leaves through staging tiles + TMA bulk tensor store / reduce-add (default), 0 = per-thread path
     int red_add;       // PSTB_SYRK_RED: per-thread path: 1 = red.global.add.v4.f32 (default), 0 = load + add + store
     int dbg;           // PSTB_SYRK_DBG: timing experiments only (results are wrong): 2 = no K write, 4 = no operand loads
@@ -984,8 +985,8 @@ Knobs knobs() {
     Knobs k;
     k.run_kb_fast = geti("PSTB_RUN_KB_FAST", 6);
     if (k.run_kb_fast < 1 || k.run_kb_fast > 64) k.run_kb_fast = 6;
-    k.run_kb_off = geti("PSTB_RUN_KB_OFF", 1024);
-    if (k.run_kb_off < 1) k.run_kb_off = 1024;
+    k.run_kb_off = geti("PSTB_RUN_KB_OFF", 12);
+    if (k.run_kb_off < 1) k.run_kb_off = 12;
     k.tma_out = geti("PSTB_SYRK_TMA_OUT", 1) != 0 ? 1 : 0;
     k.red_add = geti("PSTB_SYRK_RED", 1) != 0 ? 1 : 0;
     k.dbg = geti("PSTB_SYRK_DBG", 0);

@@ -657,10 +657,10 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        if compact and not args.serial_allreduce:
+        if compact and args.overlap_allreduce:
             # the NCCL all-reduce of finished tile bands runs on a side stream under the last SNP chunk's multiplication
             _k, stats_box[0] = parallel.snp_kernel_sharded_overlapped(store, n, m, None, spec, chunk=chunk, tiles=tiles, K=K,
-                                                                      bands=args.allreduce_bands, reserve_sms=args.allreduce_sms)
+                                                                      bands=args.allreduce_bands, reserve_sms=args.allreduce_sms, tail_chunks=args.allreduce_tail_chunks)
             for e in ev[1:]:
                 e.record()
             marks.append(ev)
@@ -671,9 +671,10 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
             _k, stats_box[0] = dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1), low_term=low_term, standardizer=spec)
         ev[1].record()
         if compact:
-            dist.all_reduce(tiles)                                                   # sum of the partial triangles over NVLink
+            # ONE reduction of the compact triangle over NVLink, issued in slices so that the expansion of a reduced slice into the
+            # square K runs while the next slice is still being reduced
+            parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices)
             ev[2].record()
-            dev.kernel_from_tiles(tiles, n, K=K)                                     # -> full symmetric K
         elif world > 1:
             dist.all_reduce(K)
             ev[2].record()
@@ -702,10 +703,10 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     breakdown = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
                  "allreduce_ms_incl_wait_for_slowest_rank": float(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
                  "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
-                 "allreduce": (("compact lower-triangular tiles ({0:.2f} GB) in {1} bands, all-reduced + expanded on a side stream while the last SNP chunk is multiplied "
-                                "({2} SMs left to NCCL); compute_ms is the whole overlapped step").format(tiles.numel() * 4 / 1e9, args.allreduce_bands, args.allreduce_sms)
-                               if (compact and not args.serial_allreduce) else
-                               "compact lower-triangular tiles ({0:.2f} GB), expanded to the square matrix in the 'mirror' slot".format(tiles.numel() * 4 / 1e9)
+                 "allreduce": (("compact lower-triangular tiles ({0:.2f} GB) in {1} bands, all-reduced + expanded on a side stream while the last SNP chunks are multiplied "
+                                "({2} SMs left to NCCL; the last {3} chunks are multiplied band-major); compute_ms is the whole overlapped step").format(tiles.numel() * 4 / 1e9, args.allreduce_bands, args.allreduce_sms, args.allreduce_tail_chunks)
+                               if (compact and args.overlap_allreduce) else
+                               "compact lower-triangular tiles ({0:.2f} GB) in {1} slices, each expanded to the square matrix while the next is reduced (expansion of the last one in the 'mirror' slot)".format(tiles.numel() * 4 / 1e9, args.allreduce_slices)
                                if compact else ("square matrix" if world > 1 else "none"))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
     diag = float(K.diagonal().double().mean().item())
@@ -812,13 +813,12 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
         def step():
             d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
             store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
-            if tiles is not None and not args.serial_allreduce:
+            if tiles is not None and args.overlap_allreduce:
                 parallel.snp_kernel_sharded_overlapped(store, n, m, None, ("unit",), chunk=chunk, tiles=tiles, K=K, bands=args.allreduce_bands,
-                                                       reserve_sms=args.allreduce_sms)
+                                                       reserve_sms=args.allreduce_sms, tail_chunks=args.allreduce_tail_chunks)
             elif tiles is not None:
                 dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
-                dist.all_reduce(tiles)
-                dev.kernel_from_tiles(tiles, n, K=K)
+                parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices)
             else:
                 dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False, low_term=low_term)
                 dist.all_reduce(K)
@@ -828,7 +828,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
             elif rank == 0:
                 t_K.copy_(K, non_blocking=True)                                     # D2H of the finished kernel
             torch.cuda.synchronize()
-        api = ("per rank: pinned packed shard -> HBM, SNP-sharded SnpKernel with the NCCL all-reduce overlapped, every rank copies its row band of the float32 K "
+        api = ("per rank: pinned packed shard -> HBM, SNP-sharded SnpKernel, NCCL all-reduce of the compact triangle, every rank copies its row band of the float32 K "
                "into ONE shared page-locked host matrix" if shared is not None else
                "per rank: pinned packed shard -> HBM, pstb_snp_kernel, NCCL all-reduce, rank 0 copies float32 K to pinned host memory")
     step()
@@ -1051,9 +1051,11 @@ def main():
     ap.add_argument("--kernel-steps", type=int, default=2)
     ap.add_argument("--kernel-chunk", type=int, default=None)
     ap.add_argument("--square-allreduce", action="store_true", help="A/B: all-reduce the square K instead of the compact lower triangle")
-    ap.add_argument("--serial-allreduce", action="store_true", help="A/B: all-reduce the compact triangle after the whole multiplication (round 1) instead of overlapping it")
+    ap.add_argument("--overlap-allreduce", action="store_true", help="A/B: multiply the last SNP chunks band-major and all-reduce finished bands on a side stream (measured slower: DESIGN.md section 6)")
+    ap.add_argument("--allreduce-slices", type=int, default=4, help="slices of the compact triangle's all-reduce; a reduced slice is expanded while the next is in flight")
     ap.add_argument("--allreduce-bands", type=int, default=8)
-    ap.add_argument("--allreduce-sms", type=int, default=16, help="SMs the last chunk's SYRK leaves to the overlapped NCCL all-reduce")
+    ap.add_argument("--allreduce-sms", type=int, default=8, help="SMs the tail chunks' SYRK leaves to the overlapped NCCL all-reduce")
+    ap.add_argument("--allreduce-tail-chunks", type=int, default=4, help="SNP chunks multiplied band-major at the end, under which the all-reduce runs")
     ap.add_argument("--no-kernel-cpu", dest="kernel_cpu", action="store_false", help="skip the CPU SnpKernel sample (NumPy BLAS) of the kernel leg")
     ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")
     args = ap.parse_args()

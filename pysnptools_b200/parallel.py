@@ -35,6 +35,32 @@ def allreduce_sum_(tensor, group=None):
     return tensor
 
 
+def allreduce_tiles_and_expand(tiles, n_iid, K, group=None, slices=4):
+    """Sum the compact lower-triangular tiles ``[count, 256, 256]`` over the ranks and expand them into the square ``K``: ONE logical
+    reduction issued in ``slices`` asynchronous NCCL calls, so that ``pstb_kernel_from_tiles_range`` of a reduced slice runs while the
+    next slice is still on the wire (the expansion moves 3 x the bytes of the reduction through HBM: 6 of 24 ms at 8 GPUs when serial)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    count = int(tiles.shape[0])
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    slices = max(1, min(int(slices), count)) if count else 1
+    edges = [count * s // slices for s in range(slices + 1)]
+    works = []
+    for s in range(slices):
+        t0, t1 = edges[s], edges[s + 1]
+        works.append(dist.all_reduce(tiles[t0:t1], op=dist.ReduceOp.SUM, group=group, async_op=True) if (multi and t1 > t0) else None)
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in range(slices):
+        t0, t1 = edges[s], edges[s + 1]
+        if t1 <= t0:
+            continue
+        if works[s] is not None:
+            works[s].wait()                         # the current stream waits for this slice only
+        _lib.check(_lib.lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), int(n_iid), 0, 1, t0, t1, K.data_ptr(), stream))
+    return K
+
+
 def allgather_rows(local, counts, group=None):
     """Concatenate per-rank row blocks (e.g. per-SNP statistics [m_r, 2]) in rank order."""
     import torch
@@ -61,12 +87,15 @@ def snp_kernel_sharded(store_shard, partial_kernel_fn, n_iid, group=None, mirror
 
 
 def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardizer_spec=("unit",), count_A1=False, chunk=None,
-                                  bands=8, reserve_sms=16, tiles=None, K=None):
+                                  bands=8, reserve_sms=8, tail_chunks=4, tiles=None, K=None):
     """SNP-sharded SnpKernel with the NCCL reduction OVERLAPPED: this rank's partial K accumulates in compact
-    lower-triangular tiles; the LAST chunk of SNPs is multiplied band by band (``pstb_snp_kernel_tiles_band``) and, as soon as a band
-    of tiles is final, it is all-reduced on a side stream and expanded into the square K while the later bands still multiply
-    (``reserve_sms`` SMs are left to the collective).  Only the last band's reduction (1 / bands of the triangle) stays exposed.
-    Returns ``(K, stats_local)``: float32 CUDA tensor [n, n] (both triangles) and this rank's float64 statistics [m_local, 2]."""
+    lower-triangular tiles.  K is final only after the last SNP chunk, so the last ``tail_chunks`` chunks are multiplied BAND-major
+    instead of chunk-major (``pstb_snp_kernel_tiles_band``: their operand planes are built once, into one workspace each, then every
+    band of tiles takes all of them in turn): as soon as a band is final it is all-reduced on a side stream and expanded into the
+    square K while the later bands still multiply (``reserve_sms`` SMs are left to the collective).  Only the last band's reduction
+    (1 / bands of the triangle) stays exposed.  Returns ``(K, stats_local)``: float32 CUDA tensor [n, n] (both triangles) and this
+    rank's float64 statistics [m_local, 2]."""
+    import os
     import torch
     import torch.distributed as dist
     from . import _lib, device
@@ -78,6 +107,7 @@ def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardi
     low_term = device.low_term_for(total_sid, n, standardizer_spec)
     coords = device.kernel_tile_coords(n)
     ntiles = len(coords)
+    trace = os.environ.get("PSTB_OVERLAP_TRACE") and (not dist.is_initialized() or dist.get_rank(group) == 0)
     with torch.cuda.device(dev):
         if tiles is None:
             tiles = torch.empty((ntiles, 256, 256), dtype=torch.float32, device=dev)
@@ -86,42 +116,65 @@ def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardi
         stats = torch.empty((m_local, 2), dtype=torch.float64, device=dev)
         if m_local == 0:
             tiles.zero_()
-        head = ((m_local - 1) // chunk) * chunk if m_local > 0 else 0
+        nchunks = (m_local + chunk - 1) // chunk
+        ntail = max(1, min(int(tail_chunks), nchunks)) if nchunks else 0
+        head = (nchunks - ntail) * chunk if nchunks else 0
+        main = torch.cuda.current_stream()
+        t_ev = [torch.cuda.Event(enable_timing=True)] if trace else None
+        if trace:
+            t_ev[0].record(main)
         if head > 0:
             _t, _c, st_head = device.snp_kernel_tiles(store, None, slice(0, head), count_A1=count_A1, standardizer=standardizer_spec, chunk=chunk,
                                                       tiles=tiles, accumulate=False, low_term=low_term)
             stats[:head] = st_head
         bands = max(1, min(int(bands), ntiles))
         edges = [ntiles * b // bands for b in range(bands + 1)]
-        main = torch.cuda.current_stream()
-        comm = torch.cuda.Stream(device=dev)
+        # high priority: when SMs free up at the end of a band, the collective's CTAs are placed before the next SYRK launch's, so the
+        # persistent CTA pairs (statically assigned tiles) never find their SMs taken half-way through a launch
+        comm = torch.cuda.Stream(device=dev, priority=-1)
         comm.wait_stream(main)
         mode, a, b = device._mode_args(standardizer_spec)
         wbytes = int(lib.pstb_kernel_workspace_bytes(n, chunk))
-        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        works = [torch.empty(wbytes, dtype=torch.uint8, device=dev) for _ in range(ntail)]
         iid_ax = _lib.Axis(None, 0, 1, n)
-        sid_ax = _lib.Axis(None, head, 1, m_local - head)
-        tail_stats = stats[head:] if m_local > head else stats
+        ranges = [(head + c * chunk, min(m_local, head + (c + 1) * chunk)) for c in range(ntail)]
+        reserve = int(reserve_sms) if world > 1 else 0
+
+        def band_call(c, t0, t1, flags):
+            lo, hi = ranges[c]
+            check(lib.pstb_snp_kernel_tiles_band(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, iid_ax,
+                                                 _lib.Axis(None, lo, 1, hi - lo), int(bool(count_A1)), mode, a, b, 0, stats[lo:hi].data_ptr(),
+                                                 tiles.data_ptr(), 0, 1, int(head > 0 or c > 0), works[c].data_ptr(), wbytes, chunk,
+                                                 device._LOW_TERM[low_term], t0, t1, flags, reserve, main.cuda_stream))
+        for c in range(ntail):
+            band_call(c, 0, 0, 1)                                   # statistics + operand planes of the tail chunks, no tiles yet
+        marks = []
         for bnd in range(bands):
             t0, t1 = edges[bnd], edges[bnd + 1]
             if t1 <= t0:
                 continue
-            if m_local > head:
-                check(lib.pstb_snp_kernel_tiles_band(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, iid_ax, sid_ax, int(bool(count_A1)),
-                                                     mode, a, b, 0, tail_stats.data_ptr(), tiles.data_ptr(), 0, 1, int(head > 0), work.data_ptr(), wbytes, chunk,
-                                                     device._LOW_TERM[low_term], t0, t1, 1 if bnd == 0 else 0, int(reserve_sms) if world > 1 else 0,
-                                                     main.cuda_stream))
-            ev = torch.cuda.Event()
+            for c in range(ntail):
+                band_call(c, t0, t1, 0)
+            ev = torch.cuda.Event(enable_timing=bool(trace))
             ev.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
                 if world > 1:
                     dist.all_reduce(tiles[t0:t1], op=dist.ReduceOp.SUM, group=group)
                 check(lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), n, 0, 1, t0, t1, K.data_ptr(), comm.cuda_stream))
+                if trace:
+                    e2 = torch.cuda.Event(enable_timing=True)
+                    e2.record(comm)
+                    marks.append((ev, e2))
         main.wait_stream(comm)
         tiles.record_stream(comm)
         K.record_stream(comm)
-        work.record_stream(main)
+        for w in works:
+            w.record_stream(main)
+        if trace:
+            torch.cuda.synchronize()
+            print("[overlap] head %d SNPs, %d tail chunks, %d bands, %d SMs reserved; ms since start: " % (head, ntail, bands, reserve)
+                  + "  ".join("band%d compute %.1f reduced %.1f" % (i, t_ev[0].elapsed_time(a_), t_ev[0].elapsed_time(b_)) for i, (a_, b_) in enumerate(marks)), flush=True)
     return K, stats
 
 
@@ -174,9 +227,14 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     if world == 1:
         K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=True)
     else:
-        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix, band by band
-        # under the multiplication of the last SNP chunk (the low-term mode follows the SNP count of the whole kernel)
-        K, stats = snp_kernel_sharded_overlapped(store, bed.iid_count, bed.sid_count, group, standardizer_spec, bed.count_A1, chunk)
+        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix (the low-term
+        # mode follows the SNP count of the whole kernel); reduced slices are expanded while the next ones are in flight
+        import torch
+        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
+                                                        low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec))
+        K = torch.empty((bed.iid_count, bed.iid_count), dtype=torch.float32, device=tiles.device)
+        allreduce_tiles_and_expand(tiles, bed.iid_count, K, group)
+        del tiles
         counts = [shard_range(bed.sid_count, r, world)[1] - shard_range(bed.sid_count, r, world)[0] for r in range(world)]
         stats = allgather_rows(stats, counts, group)
     return K, stats

@@ -416,15 +416,15 @@ def test_float64_kernel_path(oracle, dev):
 
 @pytest.mark.parametrize("n,m,chunk,bands", [(700, 1000, 256, 4), (1300, 200, 256, 3), (515, 512, 256, 8), (300, 0, 64, 2)])
 def test_banded_last_chunk_matches_plain_kernel(n, m, chunk, bands, oracle, dev):
-    """The overlapped multi-GPU reduction multiplies the last SNP chunk band by band (pstb_snp_kernel_tiles_band) and expands finished
-    bands on a side stream (pstb_kernel_from_tiles_range).  On one GPU (no collective) the result must equal the plain kernel: same
-    planes, same tiles, only the rank-one part is added per call."""
+    """The overlapped multi-GPU reduction multiplies the last SNP chunks band-major (pstb_snp_kernel_tiles_band: planes of 1-3 tail chunks
+    built once, every band of tiles takes them in turn) and expands finished bands on a side stream (pstb_kernel_from_tiles_range).  On one
+    GPU (no collective) the result must equal the plain kernel: same planes, same tiles, only the rank-one part is added per call."""
     import torch
     from pysnptools_b200 import parallel
     packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + m) if m else np.zeros((0, (n + 3) // 4), dtype=np.uint8)
     store = dev.PackedStore.from_host(packed, n)
-    for std in (("unit",), ("beta", 1, 25)):
-        K, st = parallel.snp_kernel_sharded_overlapped(store, n, m, None, std, chunk=chunk, bands=bands)
+    for std, tail in ((("unit",), 1), (("unit",), 3), (("beta", 1, 25), 2)):
+        K, st = parallel.snp_kernel_sharded_overlapped(store, n, m, None, std, chunk=chunk, bands=bands, tail_chunks=tail)
         torch.cuda.synchronize()
         Kp, stp = dev.snp_kernel(store, standardizer=std, chunk=chunk, low_term=dev.low_term_for(m, n, std))
         Kc, Kpc = K.double().cpu().numpy(), Kp.double().cpu().numpy()

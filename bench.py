@@ -665,15 +665,18 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                 e.record()
             marks.append(ev)
             return
+        u_box = [None]
         if compact:
-            _t, _c, stats_box[0] = dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term, standardizer=spec)
+            # the rank-one vector of the exact-dosage path is deferred: all-reduced with the tiles (n doubles) and added during the expansion
+            _t, _c, stats_box[0], u_box[0] = dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term, standardizer=spec,
+                                                                 defer_rank1=True)
         else:
             _k, stats_box[0] = dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=(world == 1), low_term=low_term, standardizer=spec)
         ev[1].record()
         if compact:
             # ONE reduction of the compact triangle over NVLink, issued in slices so that the expansion of a reduced slice into the
             # square K runs while the next slice is still being reduced
-            parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices)
+            parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices, u=u_box[0])
             ev[2].record()
         elif world > 1:
             dist.all_reduce(K)
@@ -817,8 +820,8 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
                 parallel.snp_kernel_sharded_overlapped(store, n, m, None, ("unit",), chunk=chunk, tiles=tiles, K=K, bands=args.allreduce_bands,
                                                        reserve_sms=args.allreduce_sms, tail_chunks=args.allreduce_tail_chunks)
             elif tiles is not None:
-                dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term)
-                parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices)
+                _t, _c, _s, u_e = dev.snp_kernel_tiles(store, chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term, defer_rank1=True)
+                parallel.allreduce_tiles_and_expand(tiles, n, K, slices=args.allreduce_slices, u=u_e)
             else:
                 dev.snp_kernel(store, K=K, accumulate=False, chunk=chunk, mirror=False, low_term=low_term)
                 dist.all_reduce(K)

@@ -157,7 +157,12 @@ int pstb_snp_kernel_tiles_band(const uint8_t* d_packed, int64_t ld, int64_t iid_
                                void* d_work, int64_t work_bytes, int64_t chunk, int low_term,
                                int64_t tile_begin, int64_t tile_end, int flags, int reserve_sms, void* stream);
 int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid, int rank, int world, int64_t tile_begin, int64_t tile_end,
-                                 float* d_K, void* stream);
+                                 float* d_K, const double* d_u, void* stream);
+/* Deferred rank-one part (multi-GPU): with bit 1 of `accumulate` (pstb_snp_kernel_tiles) or of `flags` (pstb_snp_kernel_tiles_band) set,
+ * the call leaves the float64 vector v [n_iid] of the exact-dosage path (K_ik = sum_j L_ij B_kj + v_k) in its workspace instead of adding
+ * it to the tiles; pstb_kernel_workspace_rank1 returns its address.  The caller sums the vectors of its calls, all-reduces the total
+ * with the tiles (n_iid doubles) and passes it as d_u to pstb_kernel_from_tiles_range, which adds it while expanding (NULL: nothing). */
+double* pstb_kernel_workspace_rank1(void* d_work, int64_t n_iid, int64_t chunk);
 /* Train x test kernel (what FaST-LMM builds from SnpKernel + the *Trained standardizers: unittrained.py:47-70,
  * betatrained.py:47-63 applied to a second iid set, then train.val.dot(test.val.T)):
  *   d_out [n_r, n_c] float32, C order (ld = n_c):  out[i, k] (+)= sum_j x_ij y_kj

@@ -58,7 +58,8 @@ def _load():
         "pstb_snp_kernel_tiles_band": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double, c_int,
                                                c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_int,
                                                c_void_p]),
-        "pstb_kernel_from_tiles_range": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+        "pstb_kernel_from_tiles_range": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+        "pstb_kernel_workspace_rank1": (c_void_p, [c_void_p, c_int64, c_int64]),
         "pstb_set_syrk_low_term": (c_int, [c_int]),
         "pstb_kernel_from_tiles": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
         "pstb_cross_kernel_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),

@@ -344,6 +344,7 @@ struct SyrkParams {
     // n_cols columns.  Symmetric product: row0 = 0, n_cols = n.
     long long row0, n_cols;
     int fp8lo;              // 2-term path with the low term on the fp8 pipe: map_p2 / map_h8 are byte (e4m3) planes
+    int* counter;           // dynamic tile feed: zeroed device counter of this launch (NULL: static round-robin tile lists)
     int tma_out;            // K leaves through 32 x 32 staging tiles and TMA bulk tensor stores / reduce-adds (map_out)
     int red_add;            // accumulate with red.global.add.v4.f32 (no read round trip in the epilogue) instead of load + add + store
     int dbg;                // timing experiments only (PSTB_SYRK_DBG): bit 1 = no K write at all, bit 2 = no operand loads
@@ -575,17 +576,84 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_addr, uint32_t
         : "memory");
 }
 
+constexpr int SCHED_SLOTS = 4;
+__device__ __forceinline__ void st_shared_remote(uint32_t local_addr, uint32_t cta, uint32_t value) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}" ::"r"(local_addr),
+        "r"(cta), "r"(value)
+        : "memory");
+}
+// wait with cluster-scope acquire: the data the barrier guards may have been written by the peer CTA (distributed shared memory)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const unsigned long long t0 = global_ns();
+    for (uint32_t spin = 1;; ++spin) {
+        if (mbar_try_wait_cluster(bar, parity)) return;
+        if ((spin & 1023u) == 0 && global_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SYRK_THREADS, 1)
 k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_p2,
         const __grid_constant__ CUtensorMap map_h8, const __grid_constant__ CUtensorMap map_out, const SyrkParams p) {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar_full[STAGES2 + 1], bar_empty[STAGES2 + 1], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_sfull[SCHED_SLOTS], bar_sempty[SCHED_SLOTS];
+    __shared__ int sched_tile[SCHED_SLOTS];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    // ---- tile feed ---------------------------------------------------------------------------------------------------------------
+    // Static (p.counter == NULL): CTA pair c takes tiles c, c + pairs, ... .  Dynamic: the leader's producer thread draws the next tile
+    // index from a global counter and publishes it to every role of both CTAs through a small ring (value + full / empty mbarriers;
+    // the peer's copy is written through distributed shared memory).  A pair that gets its SMs late -- a collective or another kernel
+    // holds them when the launch starts -- then simply draws fewer tiles; with the static lists it would still owe its whole share and
+    // the launch would end that much later (measured on 2 GPUs: an all-reduce next to the static kernel cost more than it hid).
+    const bool dynamic = p.counter != nullptr;
+    auto feed_next = [&](uint32_t& it) -> int {                        // every role but the scheduler; all lanes of a warp may call it
+        if (!dynamic) {
+            const long long t = (long long)cluster_id + (long long)it * nclusters;
+            ++it;
+            return t < p.ntiles ? (int)t : -1;
+        }
+        const uint32_t slot = it % SCHED_SLOTS, ph = (it / SCHED_SLOTS) & 1u;
+        mbar_wait_cluster(&bar_sfull[slot], ph);
+        const int t = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
+        __syncwarp(__activemask());                                    // whole epilogue warps or a single elected lane
+        if (lane == 0) {                                               // the slot may be reused once every role has read it
+            if (leader) mbar_arrive(&bar_sempty[slot]); else mbar_arrive_remote(smem_u32(&bar_sempty[slot]), 0u);
+        }
+        ++it;
+        return t < p.ntiles ? t : -1;
+    };
+    auto sched_next = [&](uint32_t& it) -> int {                       // leader CTA, warp 0, lane 0 only
+        if (!dynamic) return feed_next(it);
+        const uint32_t slot = it % SCHED_SLOTS, ph = (it / SCHED_SLOTS) & 1u;
+        mbar_wait(&bar_sempty[slot], ph ^ 1u);
+        const int t = atomicAdd(p.counter, 1);
+        sched_tile[slot] = t;
+        st_shared_remote(smem_u32(&sched_tile[slot]), 1u, (uint32_t)t);
+        mbar_arrive(&bar_sfull[slot]);
+        mbar_arrive_remote(smem_u32(&bar_sfull[slot]), 1u);
+        ++it;
+        return t < p.ntiles ? t : -1;
+    };
     const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
 
     if (warp == 0 && lane == 0) {
@@ -605,6 +673,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES2 + 1; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 16); }
+        // tile feed: one arrival publishes a slot; 18 readers free it (leader: MMA thread + 8 epilogue warps; peer: producer + 8 epilogue warps)
+        for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&bar_sfull[q], 1); mbar_init(&bar_sempty[q], 18); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -628,8 +698,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+            uint32_t stage = 0, phase = 0, feed = 0;
+            for (int t = leader ? sched_next(feed) : feed_next(feed); t >= 0; t = leader ? sched_next(feed) : feed_next(feed)) {
                 const int2 tile = p.tiles[t];
                 const int row_a = tile.x * TM + (int)rank * 128, row_b = tile.y * TN + (int)rank * 128;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -666,8 +736,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
     } else if (warp == 1) {
         // ===== MMA issuer (one thread of the leader CTA) =====
         if (leader && lane == 0) {
-            uint32_t stage = 0, phase = 0, run = 0;
-            for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+            uint32_t stage = 0, phase = 0, run = 0, feed = 0;
+            for (int t = feed_next(feed); t >= 0; t = feed_next(feed)) {
                 const int run_kb = run_kb_of(p.tiles[t]);
                 const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
                 for (int r = 0; r < num_runs; ++r, ++run) {
@@ -729,8 +799,8 @@ k_syrk2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUte
         if (fast) scale *= exp2f(-(float)scale_exponent(p.sc->absmax_w_bits));            // only the right operand is scaled
         else if (p.sc) scale *= exp2f(-2.0f * (float)scale_exponent(p.sc->absmax_bits));
         const bool vec = (p.ldk % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
-        uint32_t run = 0;
-        for (int t = cluster_id; t < p.ntiles; t += nclusters) {
+        uint32_t run = 0, feed = 0;
+        for (int t = feed_next(feed); t >= 0; t = feed_next(feed)) {
             const int2 tile = p.tiles[t];
             const int run_kb = run_kb_of(tile);
             const int num_runs = (p.num_kb + run_kb - 1) / run_kb;
@@ -900,7 +970,9 @@ __global__ void __launch_bounds__(256) k_mirror(float* K, long long n, long long
 // compact tile storage [ntiles][256][256] (lower-triangular tiles of `coords`) -> full K, both triangles.  One CTA per 32 x 32
 // sub-block: a coalesced copy into the lower triangle and, through shared memory, its transpose into the upper one.  Of a
 // diagonal tile only the lower half is used, so K comes out exactly symmetric.
-__global__ void __launch_bounds__(256) k_untile(const float* tiles, const int2* coords, long long n, float* K, long long ldk) {
+// u (optional): the rank-one part of the exact-dosage path, K_ik += u_k, added on the way (deferred from the SYRK calls so that the
+// multi-GPU path all-reduces it as one small vector instead of sweeping the triangle once more per call)
+__global__ void __launch_bounds__(256) k_untile(const float* tiles, const int2* coords, long long n, float* K, long long ldk, const double* u) {
     __shared__ float sub[32][33];
     const int2 t = coords[blockIdx.x];
     const int sr = blockIdx.y >> 3, sc = blockIdx.y & 7;
@@ -908,9 +980,10 @@ __global__ void __launch_bounds__(256) k_untile(const float* tiles, const int2* 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* src = tiles + (long long)blockIdx.x * 65536 + (long long)(sr * 32) * 256 + sc * 32;
     const long long i0 = (long long)t.x * 256 + sr * 32, k0 = (long long)t.y * 256 + sc * 32;
+    const double uk = (u && k0 + tx < n) ? u[k0 + tx] : 0.0;
     for (int r = ty; r < 32; r += 8) {
         const long long i = i0 + r, k = k0 + tx;
-        const float v = src[r * 256 + tx];
+        const float v = u ? (float)((double)src[r * 256 + tx] + uk) : src[r * 256 + tx];
         sub[r][tx] = v;
         if (i < n && k < n && k <= i) K[i * ldk + k] = v;
     }
@@ -978,6 +1051,7 @@ struct Knobs {
     int red_add;       // PSTB_SYRK_RED: per-thread path: 1 = red.global.add.v4.f32 (default), 0 = load + add + store
     int dbg;           // PSTB_SYRK_DBG: timing experiments only (results are wrong): 2 = no K write, 4 = no operand loads
     int clusters;      // PSTB_SYRK_CLUSTERS: CTA pairs to launch (default: SM count / 2)
+    int dynamic;       // PSTB_SYRK_DYN: 1 = dynamic tile feed (default), 0 = static round-robin tile lists
     int group;         // PSTB_SYRK_GROUP: tiles per side of a rasterisation super-block (default 8 = 2048 x 2048)
 };
 Knobs knobs() {
@@ -991,6 +1065,7 @@ Knobs knobs() {
     k.red_add = geti("PSTB_SYRK_RED", 1) != 0 ? 1 : 0;
     k.dbg = geti("PSTB_SYRK_DBG", 0);
     k.clusters = geti("PSTB_SYRK_CLUSTERS", 0);
+    k.dynamic = geti("PSTB_SYRK_DYN", 1) != 0 ? 1 : 0;
     k.group = geti("PSTB_SYRK_GROUP", 8);
     if (k.group < 1 || k.group > 64) k.group = 8;
     return k;
@@ -1068,6 +1143,25 @@ void build_tiles(long long n, std::vector<int2>& out) {
             for (int I = gi; I < gi + GROUP_I && I < ti; ++I)
                 for (int J = gj; J < gj + GROUP_J && J < tj; ++J)
                     if ((long long)J * BN <= (long long)I * BM + BM - 1) out.push_back(make_int2(I, J));
+}
+
+// zeroed launch counter for the dynamic tile feed: a small per-thread, per-device ring, cleared in stream order before every launch
+int next_counter(cudaStream_t st, int** out) {
+    constexpr int kRing = 256;
+    static thread_local int* d_ring = nullptr;
+    static thread_local int ring_dev = -1;
+    static thread_local unsigned seq = 0;
+    int dev = 0;
+    PSTB_CUDA(cudaGetDevice(&dev));
+    if (!d_ring || ring_dev != dev) {
+        d_ring = nullptr;                                   // (a ring of another device is left to that device's teardown)
+        PSTB_CUDA(cudaMalloc(&d_ring, kRing * sizeof(int)));
+        ring_dev = dev;
+    }
+    int* c = d_ring + (seq++ % kRing);
+    PSTB_CUDA(cudaMemsetAsync(c, 0, sizeof(int), st));
+    *out = c;
+    return 0;
 }
 
 struct TileCache {
@@ -1181,6 +1275,7 @@ int launch_syrk(const __half* hi, const __half* lo, long long n, long long n_pad
         if (kn.clusters > 0 && kn.clusters < clusters) clusters = kn.clusters;
         if (reserve_sms > 0) clusters = clusters - (reserve_sms + 1) / 2 > 8 ? clusters - (reserve_sms + 1) / 2 : 8;   // leave SMs to a concurrent collective
         if (clusters > ntiles) clusters = ntiles;
+        if (kn.dynamic && next_counter(st, &p.counter)) return 1;
         v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, map_out, p);   // __cluster_dims__(2,1,1)
         PSTB_AFTER_LAUNCH("k_syrk2");
         return 0;
@@ -1274,6 +1369,7 @@ int launch_cross(const __half* hi, const __half* lo, const __half* p2, int fp8lo
     if (ntiles < 1) return 0;
     int clusters = sm_count_cached() / 2;
     if (clusters > ntiles) clusters = ntiles;
+    if (kn.dynamic && next_counter(st, &p.counter)) return 1;
     v2::k_syrk2<<<2 * clusters, SYRK_THREADS, v2::SYRK2_SMEM, st>>>(map_hi, map_lo, map_p2, map_h8, map_out, p);
     PSTB_AFTER_LAUNCH("k_syrk2");
     return 0;
@@ -1360,6 +1456,10 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
     // banded mode (tile_end >= 0; pstb_snp_kernel_tiles_band): ONE chunk of SNPs, tiles [tile_begin, tile_end) only.  band_flags bit 0:
     // build the operand planes (first band of the chunk); without it the planes a previous band call left in d_work are reused.
     const bool banded = tile_end >= 0;
+    // compact storage only: leave the rank-one vector v in the workspace (pstb_kernel_workspace_rank1) instead of adding it to the tiles;
+    // the caller sums / all-reduces the vectors and hands the total to pstb_kernel_from_tiles_range
+    const bool defer_rank1 = compact && (((accumulate & 2) != 0) || (banded && (band_flags & 2)));
+    accumulate &= 1;
     if (banded && sid.n > chunk) return fail("a band call multiplies one chunk of SNPs (%lld > %lld)", (long long)sid.n, (long long)chunk);
     if (mode != PSTB_STD_UNIT && mode != PSTB_STD_BETA) return fail("kernel needs PSTB_STD_UNIT or PSTB_STD_BETA");
     if (mode == PSTB_STD_BETA && !(a > 0.0 && b > 0.0)) return fail("Beta parameters must be positive");
@@ -1455,7 +1555,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
                              &d_tiles, &ntiles, pp.fp8lo, tile_begin, tile_end, reserve_sms);
         if (rc) return rc;
     }
-    if (!force_slow && (phase & 2)) {
+    if (!force_slow && (phase & 2) && !defer_rank1) {
         if (compact) {
             if (ntiles > 0) {
                 // (banded: d_tiles / ntiles are the band's, so is the tile storage)
@@ -1530,8 +1630,17 @@ extern "C" int pstb_snp_kernel_tiles_band(const uint8_t* d_packed, int64_t ld, i
 }
 
 // tiles [tile_begin, tile_end) of `rank`'s compact list -> their places in the full symmetric K (the other entries are untouched)
+// the rank-one vector v [n_iid] (float64) a kernel call with the "defer" flag left in its workspace
+extern "C" double* pstb_kernel_workspace_rank1(void* d_work, int64_t n_iid, int64_t chunk) {
+    if (!d_work || n_iid < 1 || chunk < BK) return nullptr;
+    const long long n_pad = round_up(n_iid, ROW_PAD), k_cap = round_up(chunk, BK);
+    char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_work) + 1023) & ~(uintptr_t)1023);
+    __half* p2_end = reinterpret_cast<__half*>(w) + 3 * n_pad * k_cap;
+    return reinterpret_cast<double*>(reinterpret_cast<Scalars*>(p2_end) + 1);
+}
+
 extern "C" int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid, int rank, int world, int64_t tile_begin, int64_t tile_end,
-                                            float* d_K, void* stream) {
+                                            float* d_K, const double* d_u, void* stream) {
     if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world");
     if (n_iid <= 0 || tile_end <= tile_begin) return 0;
     if (!d_tiles || !d_K) return fail("NULL pointer");
@@ -1540,7 +1649,7 @@ extern "C" int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid,
     int ntiles = 0;
     if (get_tiles(n_iid, 2, rank, world, st, &coords, &ntiles)) return 1;
     if (tile_begin < 0 || tile_end > ntiles) return fail("bad tile range [%lld, %lld) of %d", (long long)tile_begin, (long long)tile_end, ntiles);
-    k_untile<<<dim3((unsigned)(tile_end - tile_begin), 64), 256, 0, st>>>(d_tiles + tile_begin * 65536LL, coords + tile_begin, n_iid, d_K, n_iid);
+    k_untile<<<dim3((unsigned)(tile_end - tile_begin), 64), 256, 0, st>>>(d_tiles + tile_begin * 65536LL, coords + tile_begin, n_iid, d_K, n_iid, d_u);
     PSTB_AFTER_LAUNCH("k_untile");
     return 0;
 }
@@ -1703,7 +1812,7 @@ extern "C" int pstb_kernel_from_tiles(const float* d_tiles, int64_t n_iid, int r
     int ntiles = 0;
     if (get_tiles(n_iid, 2, rank, world, st, &coords, &ntiles)) return 1;
     if (ntiles < 1) return 0;
-    k_untile<<<dim3((unsigned)ntiles, 64), 256, 0, st>>>(d_tiles, coords, n_iid, d_K, n_iid);
+    k_untile<<<dim3((unsigned)ntiles, 64), 256, 0, st>>>(d_tiles, coords, n_iid, d_K, n_iid, nullptr);
     PSTB_AFTER_LAUNCH("k_untile");
     return 0;
 }

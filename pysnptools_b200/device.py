@@ -295,7 +295,7 @@ def kernel_tile_coords(n_iid, rank=0, world=1):
 
 
 def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standardizer=("unit",), stats=None, chunk=None,
-                     rank=0, world=1, tiles=None, accumulate=False, low_term="default"):
+                     rank=0, world=1, tiles=None, accumulate=False, low_term="default", defer_rank1=False):
     """K-tile sharded kinship: this rank's 256 x 256 tiles of ``K = X X^T`` over ALL selected SNPs (cfg5; no collective).
 
     Returns ``(tiles, coords, stats)``: float32 CUDA tensor [count, 256, 256], the (I, J) of each tile, per-SNP statistics.
@@ -324,8 +324,21 @@ def snp_kernel_tiles(store, iid_sel=None, sid_sel=None, count_A1=False, standard
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         check(lib.pstb_snp_kernel_tiles(store.tensor.data_ptr(), store.ld, store.iid_count, store.sid_count, isel.axis(), ssel.axis(),
                                         int(bool(count_A1)), mode, a, b, use_stats, d_stats.data_ptr(), tiles.data_ptr(), rank, world,
-                                        int(bool(accumulate)), work.data_ptr(), wbytes, chunk, _LOW_TERM[low_term], _stream()))
+                                        int(bool(accumulate)) | (2 if defer_rank1 else 0), work.data_ptr(), wbytes, chunk, _LOW_TERM[low_term], _stream()))
+        if defer_rank1:
+            # the rank-one vector v of the exact-dosage path stays in the workspace: hand a copy to the caller (multi-GPU: all-reduced with the tiles)
+            u = workspace_rank1(work, n, chunk).clone() if (n and ssel.n) else torch.zeros(n, dtype=torch.float64, device=dev)
+            return tiles, coords, d_stats, u
     return tiles, coords, d_stats
+
+
+def workspace_rank1(work, n_iid, chunk):
+    """float64 view [n_iid] of the rank-one vector inside a kernel workspace (``pstb_kernel_workspace_rank1``)."""
+    ptr = lib.pstb_kernel_workspace_rank1(work.data_ptr(), int(n_iid), int(chunk))
+    if not ptr:
+        raise _lib.PstB200Error("no rank-one vector in this workspace")
+    off = int(ptr) - int(work.data_ptr())
+    return work[off:off + 8 * int(n_iid)].view(torch.float64)
 
 
 def set_syrk_low_term(mode):

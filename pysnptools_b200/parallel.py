@@ -35,10 +35,12 @@ def allreduce_sum_(tensor, group=None):
     return tensor
 
 
-def allreduce_tiles_and_expand(tiles, n_iid, K, group=None, slices=4):
+def allreduce_tiles_and_expand(tiles, n_iid, K, group=None, slices=4, u=None):
     """Sum the compact lower-triangular tiles ``[count, 256, 256]`` over the ranks and expand them into the square ``K``: ONE logical
     reduction issued in ``slices`` asynchronous NCCL calls, so that ``pstb_kernel_from_tiles_range`` of a reduced slice runs while the
-    next slice is still on the wire (the expansion moves 3 x the bytes of the reduction through HBM: 6 of 24 ms at 8 GPUs when serial)."""
+    next slice is still on the wire (the expansion moves 3 x the bytes of the reduction through HBM: 6 of 24 ms at 8 GPUs when serial).
+    ``u``: this rank's deferred rank-one vector (float64 [n]); it is all-reduced as well and added during the expansion, which saves
+    every rank a read-modify-write sweep over its 5 GB of tiles."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -47,17 +49,21 @@ def allreduce_tiles_and_expand(tiles, n_iid, K, group=None, slices=4):
     slices = max(1, min(int(slices), count)) if count else 1
     edges = [count * s // slices for s in range(slices + 1)]
     works = []
+    u_work = dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group, async_op=True) if (multi and u is not None) else None
     for s in range(slices):
         t0, t1 = edges[s], edges[s + 1]
         works.append(dist.all_reduce(tiles[t0:t1], op=dist.ReduceOp.SUM, group=group, async_op=True) if (multi and t1 > t0) else None)
     stream = torch.cuda.current_stream().cuda_stream
+    if u_work is not None:
+        u_work.wait()
     for s in range(slices):
         t0, t1 = edges[s], edges[s + 1]
         if t1 <= t0:
             continue
         if works[s] is not None:
             works[s].wait()                         # the current stream waits for this slice only
-        _lib.check(_lib.lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), int(n_iid), 0, 1, t0, t1, K.data_ptr(), stream))
+        _lib.check(_lib.lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), int(n_iid), 0, 1, t0, t1, K.data_ptr(),
+                                                         u.data_ptr() if u is not None else None, stream))
     return K
 
 
@@ -123,10 +129,12 @@ def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardi
         t_ev = [torch.cuda.Event(enable_timing=True)] if trace else None
         if trace:
             t_ev[0].record(main)
+        u_total = torch.zeros(n, dtype=torch.float64, device=dev)        # deferred rank-one vectors of all calls (added during the expansion)
         if head > 0:
-            _t, _c, st_head = device.snp_kernel_tiles(store, None, slice(0, head), count_A1=count_A1, standardizer=standardizer_spec, chunk=chunk,
-                                                      tiles=tiles, accumulate=False, low_term=low_term)
+            _t, _c, st_head, u_head = device.snp_kernel_tiles(store, None, slice(0, head), count_A1=count_A1, standardizer=standardizer_spec,
+                                                              chunk=chunk, tiles=tiles, accumulate=False, low_term=low_term, defer_rank1=True)
             stats[:head] = st_head
+            u_total += u_head
         bands = max(1, min(int(bands), ntiles))
         edges = [ntiles * b // bands for b in range(bands + 1)]
         # high priority: when SMs free up at the end of a band, the collective's CTAs are placed before the next SYRK launch's, so the
@@ -147,21 +155,26 @@ def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardi
                                                  tiles.data_ptr(), 0, 1, int(head > 0 or c > 0), works[c].data_ptr(), wbytes, chunk,
                                                  device._LOW_TERM[low_term], t0, t1, flags, reserve, main.cuda_stream))
         for c in range(ntail):
-            band_call(c, 0, 0, 1)                                   # statistics + operand planes of the tail chunks, no tiles yet
+            band_call(c, 0, 0, 1 | 2)                               # statistics + operand planes of the tail chunks, no tiles yet
+            u_total += device.workspace_rank1(works[c], n, chunk)
+        with torch.cuda.stream(comm):
+            comm.wait_stream(main)
+            if world > 1:
+                dist.all_reduce(u_total, op=dist.ReduceOp.SUM, group=group)
         marks = []
         for bnd in range(bands):
             t0, t1 = edges[bnd], edges[bnd + 1]
             if t1 <= t0:
                 continue
             for c in range(ntail):
-                band_call(c, t0, t1, 0)
+                band_call(c, t0, t1, 2)
             ev = torch.cuda.Event(enable_timing=bool(trace))
             ev.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev)
                 if world > 1:
                     dist.all_reduce(tiles[t0:t1], op=dist.ReduceOp.SUM, group=group)
-                check(lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), n, 0, 1, t0, t1, K.data_ptr(), comm.cuda_stream))
+                check(lib.pstb_kernel_from_tiles_range(tiles.data_ptr(), n, 0, 1, t0, t1, K.data_ptr(), u_total.data_ptr(), comm.cuda_stream))
                 if trace:
                     e2 = torch.cuda.Event(enable_timing=True)
                     e2.record(comm)
@@ -169,6 +182,7 @@ def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardi
         main.wait_stream(comm)
         tiles.record_stream(comm)
         K.record_stream(comm)
+        u_total.record_stream(comm)
         for w in works:
             w.record_stream(main)
         if trace:
@@ -230,10 +244,11 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
         # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix (the low-term
         # mode follows the SNP count of the whole kernel); reduced slices are expanded while the next ones are in flight
         import torch
-        tiles, _coords, stats = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
-                                                        low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec))
+        tiles, _coords, stats, u = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
+                                                           low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec),
+                                                           defer_rank1=True)
         K = torch.empty((bed.iid_count, bed.iid_count), dtype=torch.float32, device=tiles.device)
-        allreduce_tiles_and_expand(tiles, bed.iid_count, K, group)
+        allreduce_tiles_and_expand(tiles, bed.iid_count, K, group, u=u)
         del tiles
         counts = [shard_range(bed.sid_count, r, world)[1] - shard_range(bed.sid_count, r, world)[0] for r in range(world)]
         stats = allgather_rows(stats, counts, group)

@@ -16,7 +16,7 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 8 * 4032
 missing = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 store = bench.gen_store_device(dev, torch, n, m, seed=2000, missing_rate=missing)
 K = torch.zeros((n, n), dtype=torch.float32, device="cuda")
-KNOBS = ("PSTB_RUN_KB_OFF", "PSTB_SYRK_TMA_OUT", "PSTB_SYRK_RED", "PSTB_SYRK_DBG", "PSTB_RUN_KB_FAST", "PSTB_SYRK_GROUP", "PSTB_SYRK_CLUSTERS", "PSTB_SYRK_3TERM")
+KNOBS = ("PSTB_SYRK_DYN", "PSTB_RUN_KB_OFF", "PSTB_SYRK_TMA_OUT", "PSTB_SYRK_RED", "PSTB_SYRK_DBG", "PSTB_RUN_KB_FAST", "PSTB_SYRK_GROUP", "PSTB_SYRK_CLUSTERS", "PSTB_SYRK_3TERM")
 
 
 sampler = bench.ClockSampler(0)
@@ -53,7 +53,10 @@ probe = _lib.lib.pstb_debug_max_active_clusters
 probe.restype = ctypes.c_int
 for cs in (1, 2, 4, 8):
     print("max active clusters of %d CTAs (320 threads, 225 KB smem): %d" % (cs, probe(cs, 320, 225 * 1024)), flush=True)
-run("default (TMA store / reduce-add epilogue, fp8 low term)")
+run("default (dynamic tile feed, TMA store / reduce-add epilogue, fp8 low term)")
+run("static round-robin tile lists", PSTB_SYRK_DYN=0)
+run("default again")
+run("static again", PSTB_SYRK_DYN=0)
 for rk in (6, 12, 24, 63):
     run("off-diagonal tiles: %d k-blocks per TMEM run" % rk, PSTB_RUN_KB_OFF=rk)
     run("off-diagonal tiles: %d k-blocks per TMEM run, fp16 low term" % rk, low_term="fp16", PSTB_RUN_KB_OFF=rk)

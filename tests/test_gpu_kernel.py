@@ -432,6 +432,13 @@ def test_banded_last_chunk_matches_plain_kernel(n, m, chunk, bands, oracle, dev)
         if m:
             assert rel_fro(Kc, Kpc) < 3e-7, rel_fro(Kc, Kpc)
             assert np.array_equal(st.cpu().numpy(), stp.cpu().numpy())
+            # the default multi-GPU path on one GPU: compact tiles with the rank-one vector DEFERRED (all-reduced as n doubles on N GPUs)
+            # and added by the expansion, in slices
+            tiles, _c, st2, u = dev.snp_kernel_tiles(store, standardizer=std, chunk=chunk, low_term=dev.low_term_for(m, n, std), defer_rank1=True)
+            Kd = torch.full((n, n), float("nan"), dtype=torch.float32, device="cuda")
+            parallel.allreduce_tiles_and_expand(tiles, n, Kd, slices=3, u=u)
+            assert np.array_equal(Kd.cpu().numpy(), Kp.cpu().numpy())          # same sums, same single rounding of tile + v_k
+            assert u.dtype == torch.float64 and tuple(u.shape) == (n,)
             ref, _ = oracle.read_kernel(packed, n, **({} if std[0] == "unit" else dict(is_beta=True, a=1, b=25)))
             assert rel_fro(Kc, ref) < K_TOL
         else:

@@ -657,7 +657,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
     def step():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        if compact and args.overlap_allreduce:
+        if compact and not args.serial_allreduce:
             # the NCCL all-reduce of finished tile bands runs on a side stream under the last SNP chunk's multiplication
             _k, stats_box[0] = parallel.snp_kernel_sharded_overlapped(store, n, m, None, spec, chunk=chunk, tiles=tiles, K=K,
                                                                       bands=args.allreduce_bands, reserve_sms=args.allreduce_sms, tail_chunks=args.allreduce_tail_chunks)
@@ -708,7 +708,7 @@ def run_kernel_workload(args, torch, dist, dev, _lib, rank, world, barrier, max_
                  "mirror_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
                  "allreduce": (("compact lower-triangular tiles ({0:.2f} GB) in {1} bands, all-reduced + expanded on a side stream while the last SNP chunks are multiplied "
                                 "({2} SMs left to NCCL; the last {3} chunks are multiplied band-major); compute_ms is the whole overlapped step").format(tiles.numel() * 4 / 1e9, args.allreduce_bands, args.allreduce_sms, args.allreduce_tail_chunks)
-                               if (compact and args.overlap_allreduce) else
+                               if (compact and not args.serial_allreduce) else
                                "compact lower-triangular tiles ({0:.2f} GB) in {1} slices, each expanded to the square matrix while the next is reduced (expansion of the last one in the 'mirror' slot)".format(tiles.numel() * 4 / 1e9, args.allreduce_slices)
                                if compact else ("square matrix" if world > 1 else "none"))}
     tflops = 2.0 * n * n * m / (ms * 1e-3) / 1e12
@@ -816,7 +816,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
         def step():
             d_tight.copy_(t_pk, non_blocking=True)                                  # H2D of this rank's SNP shard
             store.tensor[:, :rec].copy_(d_tight)                                    # re-pitch to the 16-byte record stride
-            if tiles is not None and args.overlap_allreduce:
+            if tiles is not None and not args.serial_allreduce:
                 parallel.snp_kernel_sharded_overlapped(store, n, m, None, ("unit",), chunk=chunk, tiles=tiles, K=K, bands=args.allreduce_bands,
                                                        reserve_sms=args.allreduce_sms, tail_chunks=args.allreduce_tail_chunks)
             elif tiles is not None:
@@ -831,7 +831,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
             elif rank == 0:
                 t_K.copy_(K, non_blocking=True)                                     # D2H of the finished kernel
             torch.cuda.synchronize()
-        api = ("per rank: pinned packed shard -> HBM, SNP-sharded SnpKernel, NCCL all-reduce of the compact triangle, every rank copies its row band of the float32 K "
+        api = ("per rank: pinned packed shard -> HBM, SNP-sharded SnpKernel with the NCCL all-reduce of the compact triangle overlapped, every rank copies its row band of the float32 K "
                "into ONE shared page-locked host matrix" if shared is not None else
                "per rank: pinned packed shard -> HBM, pstb_snp_kernel, NCCL all-reduce, rank 0 copies float32 K to pinned host memory")
     step()
@@ -1054,10 +1054,10 @@ def main():
     ap.add_argument("--kernel-steps", type=int, default=2)
     ap.add_argument("--kernel-chunk", type=int, default=None)
     ap.add_argument("--square-allreduce", action="store_true", help="A/B: all-reduce the square K instead of the compact lower triangle")
-    ap.add_argument("--overlap-allreduce", action="store_true", help="A/B: multiply the last SNP chunks band-major and all-reduce finished bands on a side stream (measured slower: DESIGN.md section 6)")
+    ap.add_argument("--serial-allreduce", action="store_true", help="A/B: all-reduce the compact triangle (in slices, expansion pipelined) after the whole multiplication instead of overlapping it with the last SNP chunks")
     ap.add_argument("--allreduce-slices", type=int, default=4, help="slices of the compact triangle's all-reduce; a reduced slice is expanded while the next is in flight")
     ap.add_argument("--allreduce-bands", type=int, default=8)
-    ap.add_argument("--allreduce-sms", type=int, default=8, help="SMs the tail chunks' SYRK leaves to the overlapped NCCL all-reduce")
+    ap.add_argument("--allreduce-sms", type=int, default=0, help="SMs the tail chunks' SYRK leaves idle for the overlapped NCCL all-reduce (0: the dynamic tile feed absorbs whatever the collective takes)")
     ap.add_argument("--allreduce-tail-chunks", type=int, default=4, help="SNP chunks multiplied band-major at the end, under which the all-reduce runs")
     ap.add_argument("--no-kernel-cpu", dest="kernel_cpu", action="store_false", help="skip the CPU SnpKernel sample (NumPy BLAS) of the kernel leg")
     ap.add_argument("--ncu-traffic", type=float, default=None, help="dram bytes per launch from profiles/ (ncu --set full), for the roofline object")

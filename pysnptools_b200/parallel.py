@@ -93,7 +93,7 @@ def snp_kernel_sharded(store_shard, partial_kernel_fn, n_iid, group=None, mirror
 
 
 def snp_kernel_sharded_overlapped(store, n_iid, total_sid, group=None, standardizer_spec=("unit",), count_A1=False, chunk=None,
-                                  bands=8, reserve_sms=8, tail_chunks=4, tiles=None, K=None):
+                                  bands=8, reserve_sms=0, tail_chunks=4, tiles=None, K=None):
     """SNP-sharded SnpKernel with the NCCL reduction OVERLAPPED: this rank's partial K accumulates in compact
     lower-triangular tiles.  K is final only after the last SNP chunk, so the last ``tail_chunks`` chunks are multiplied BAND-major
     instead of chunk-major (``pstb_snp_kernel_tiles_band``: their operand planes are built once, into one workspace each, then every
@@ -241,15 +241,9 @@ def read_kernel_multi_gpu(bed, standardizer_spec=("unit",), group=None, chunk=No
     if world == 1:
         K, stats = device.snp_kernel(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk, mirror=True)
     else:
-        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix (the low-term
-        # mode follows the SNP count of the whole kernel); reduced slices are expanded while the next ones are in flight
-        import torch
-        tiles, _coords, stats, u = device.snp_kernel_tiles(store, count_A1=bed.count_A1, standardizer=standardizer_spec, chunk=chunk,
-                                                           low_term=device.low_term_for(bed.sid_count, bed.iid_count, standardizer_spec),
-                                                           defer_rank1=True)
-        K = torch.empty((bed.iid_count, bed.iid_count), dtype=torch.float32, device=tiles.device)
-        allreduce_tiles_and_expand(tiles, bed.iid_count, K, group, u=u)
-        del tiles
+        # partial kernel in compact lower-triangular tile storage: the all-reduce moves half the bytes of the square matrix, band by band
+        # under the multiplication of the last SNP chunks (the low-term mode follows the SNP count of the whole kernel)
+        K, stats = snp_kernel_sharded_overlapped(store, bed.iid_count, bed.sid_count, group, standardizer_spec, bed.count_A1, chunk)
         counts = [shard_range(bed.sid_count, r, world)[1] - shard_range(bed.sid_count, r, world)[0] for r in range(world)]
         stats = allgather_rows(stats, counts, group)
     return K, stats

@@ -91,3 +91,31 @@ def test_cfg3_width_kernel_properties(env, oracle):
     ref = xs @ xs.T
     got = K[torch.as_tensor(ii, device="cuda")][:, torch.as_tensor(ii, device="cuda")].double().cpu().numpy()
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.parametrize("spec,m,missing,want_low", [(("unit",), 50_048, 0.0, "fp8"), (("unit",), 50_048, 0.05, "fp8"), (("beta", 1, 25), 50_048, 0.05, "fp16"),
+                                                       (("beta", 1, 25), 200_192, 0.0, "fp8")])
+def test_cfg3_height_kernel_against_oracle_on_sampled_tiles(env, spec, m, missing, want_low):
+    """The K path the benchmark times, at cfg3's FULL height (N = 50 000) and with at least as many SNPs as individuals, so that AUTO takes
+    the fp8 low term exactly as it does for cfg3 (round 1 only tested it up to N = 2 100): 15 sampled 256 x 256 tiles (all pairs of 5 row
+    blocks, the ragged last one among them) against the float64 oracle over ALL SNPs -- per-tile and stratified whole-matrix relative
+    Frobenius error under the 1e-5 gate, diagonal bias under 3e-6 -- for Unit with and without missing genotypes and for Beta(1,25)
+    (fp16 low term below 4 N SNPs, fp8 above)."""
+    torch, bench, dev = env
+    n = 50_000
+    assert dev.low_term_for(m, n, spec) == want_low
+    store = bench.gen_store_device(dev, torch, n, m, seed=31 + m, missing_rate=missing)
+    K, stats = dev.snp_kernel(store, standardizer=spec)
+    blocks = bench.pick_blocks(n, 5, seed=7)
+
+    def fetch(I, J):
+        sub = K[I * 256:I * 256 + 256, J * 256:J * 256 + 256].double().cpu().numpy()
+        out = np.zeros((256, 256))
+        out[: sub.shape[0], : sub.shape[1]] = sub
+        return out
+    res = bench.sampled_tile_parity(torch, None, 1, 0, bench._oracle_lib(), store, stats, n, spec, fetch, blocks)
+    assert res["stats_match_oracle_rtol_1e-12"] and res["sampled_tiles"] == 15
+    assert res["worst_rel_frobenius_vs_oracle"] < 1e-5, res
+    assert res["rel_frobenius_whole_K_estimate"] < 6e-6, res
+    assert abs(res["diag_rel_bias"]) < 3e-6, res
+    assert torch.equal(K[:300, -300:], K[-300:, :300].t())

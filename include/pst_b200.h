@@ -105,7 +105,9 @@ int pstb_pack(const void* d_val, int dtype, int order, int64_t n_iid, int64_t n_
  *   sum over the selected SNPs of x_j x_j^T, where x_j is the standardized column of SNP j.
  *   accumulate != 0 adds to the existing lower triangle of d_K before mirroring (multi-call
  *   streaming).  d_stats [n_sid][2] float64 is written (or read when use_stats).  Missing genotypes
- *   contribute 0 (mean imputation, standardizer.py:145-163).  Exact-dosage 2-term tensor-core path
+ *   contribute 0 (mean imputation, standardizer.py:145-163) -- also under the Identity standardizer (statistics (0, 1) passed with
+ *   use_stats), where the reference's val.dot(val.T) would propagate NaN (snpdata.py:203-206): the one deliberate deviation, see
+ *   INTEGRATION.md section 2.  Exact-dosage 2-term tensor-core path
  *   (see `low_term` below), fp32 accumulation in tensor memory: relative Frobenius error vs float64
  *   ~1e-6 (fp16 low term) / (2..5)e-6 (fp8 low term). */
 int64_t pstb_kernel_workspace_bytes(int64_t n_iid, int64_t chunk);

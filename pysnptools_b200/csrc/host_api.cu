@@ -4,6 +4,7 @@
 // H2D of packed records (2 bits / genotype), the fused decode(+standardize) kernel, and D2H of the float
 // output overlap, so the call runs at the speed of the device->host link.  Pinned caller buffers
 // (pstb_host_alloc) are copied directly; pageable ones go through internal pinned staging.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -49,30 +50,33 @@ struct Buf {
 };
 
 constexpr int kSlots = 4;     // pipeline depth of the host-buffer read: H2D, repack, kernel and D2H of different chunks overlap
+constexpr int kMaxSlots = 16; // ... and with a pageable destination: chunks in flight between the GPU and the host copy workers
 
 struct HostCtx {
     int device = -1;
     cudaStream_t s[kSlots] = {};
-    cudaEvent_t done[kSlots] = {};
-    Buf d_packed[kSlots], d_tight[kSlots], d_out[kSlots], d_stats, d_idx, d_work, d_K, h_in[kSlots], h_out[kSlots];
+    cudaEvent_t done[kMaxSlots] = {};
+    Buf d_packed[kMaxSlots], d_tight[kMaxSlots], d_out[kMaxSlots], d_stats, d_idx, d_work, d_K, h_in[kMaxSlots], h_out[kMaxSlots];
     cudaEvent_t copied[2] = {}, used[2] = {};
     HostCtx() {
-        for (int k = 0; k < kSlots; ++k) { h_in[k].host = true; h_out[k].host = true; }
+        for (int k = 0; k < kMaxSlots; ++k) { h_in[k].host = true; h_out[k].host = true; }
     }
     void release_buffers() {
-        for (int k = 0; k < kSlots; ++k) { d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release(); }
+        for (int k = 0; k < kMaxSlots; ++k) { d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release(); }
         d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
     }
     int init() {
         int dev = 0;
         PSTB_CUDA(cudaGetDevice(&dev));
         if (dev == device) return 0;
-        for (int k = 0; k < kSlots; ++k) {
+        for (int k = 0; k < kMaxSlots; ++k) {
             d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release();
-            if (s[k]) cudaStreamDestroy(s[k]);
             if (done[k]) cudaEventDestroy(done[k]);
-            PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
             PSTB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        }
+        for (int k = 0; k < kSlots; ++k) {
+            if (s[k]) cudaStreamDestroy(s[k]);
+            PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
         }
         d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
         for (int k = 0; k < 2; ++k) {
@@ -193,6 +197,59 @@ class CopyPool {
     bool stop_ = false;
 };
 
+// Workers that each take a WHOLE staged chunk of a pageable destination: wait for its D2H copy (CUDA event), copy it out of the pinned
+// ring, free the slot.  No barrier per chunk -- with the fork-join pool above every chunk waited for its slowest thread (a huge-page
+// fault here, a late wake-up there) and the pipeline delivered 25-28 GB/s into a fresh array where the same threads, left alone, fill
+// one at 38-39 GB/s next to the DMA stream (scripts/probe_pagefault.py).
+class TaskPool {
+  public:
+    ~TaskPool() { stop(); }
+    void ensure(int n) {
+        while ((int)th_.size() < n) th_.emplace_back([this] { loop(); });
+    }
+    void submit(std::function<void()> f) {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.erase(q_.begin());
+            }
+            f();
+        }
+    }
+    void stop() {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    std::vector<std::thread> th_;
+    std::vector<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+TaskPool& task_pool() {
+    static thread_local TaskPool pool;
+    return pool;
+}
+
 CopyPool& copy_pool() {
     static thread_local CopyPool pool;
     return pool;
@@ -280,32 +337,66 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
     const int64_t rec = (iid_count + 3) / 4;
     const int64_t ld = pstb_packed_ld(iid_count);
     const size_t col_bytes = (size_t)n_iid * es;
-    static const size_t target_mb = [] { const char* e = getenv("PSTB_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)((v >= 1 && v <= 4096) ? v : 64); }();
-    const size_t target = target_mb << 20;             // output bytes per pipeline chunk (tuning knob: PSTB_HOST_CHUNK_MB)
+    const bool packed_pinned = is_pinned(h_packed), out_pinned = is_pinned(h_out);
+    static const size_t target_mb = [] { const char* e = getenv("PSTB_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)((v >= 1 && v <= 4096) ? v : 0); }();
+    // output bytes per pipeline chunk (tuning knob: PSTB_HOST_CHUNK_MB): 64 MiB straight into a pinned destination; 32 MiB pieces, each
+    // drained by one host worker, into a pageable one
+    const size_t target = (target_mb ? target_mb : (out_pinned ? 64 : 32)) << 20;
     int64_t chunk = (int64_t)(target / (col_bytes > (size_t)ld ? col_bytes : (size_t)ld));
     if (chunk < 1) chunk = 1;
     if (order == PSTB_ORDER_C && chunk < 64) chunk = 64;   // keep the strided D2H rows at >= 256 bytes
     if (chunk > n_sid) chunk = n_sid;
-    const bool packed_pinned = is_pinned(h_packed), out_pinned = is_pinned(h_out);
+    // slots in flight: 4 for a pinned destination (the DMA is the only consumer); up to 16 for a pageable one, so that ~14 host workers
+    // can each be copying a chunk while the GPU fills the next ones
+    int nslots = kSlots;
+    if (!out_pinned) {
+        nslots = kMaxSlots;
+        if (const char* e = getenv("PSTB_HOST_SLOTS")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSlots) nslots = v; }
+    }
 
     const bool any_stats = mode != PSTB_STD_NONE;
     if (any_stats) {
         if (c.d_stats.ensure((size_t)n_sid * 2 * sizeof(double))) return 1;
         if (use_stats && upload_sync(c.d_stats.p, h_stats, (size_t)n_sid * 2 * sizeof(double), c.s[0])) return 1;
     }
-    for (int k = 0; k < kSlots; ++k) {
+    for (int k = 0; k < nslots; ++k) {
         if (c.d_packed[k].ensure((size_t)chunk * ld) || c.d_out[k].ensure((size_t)chunk * col_bytes)) return 1;
         if (!out_pinned && c.h_out[k].ensure((size_t)chunk * col_bytes)) return 1;
     }
+    // pageable destination: every staged chunk is handed to a worker of the calling thread's task pool
+    std::mutex slot_m;
+    std::condition_variable slot_cv;
+    bool slot_busy[kMaxSlots] = {};
+    std::atomic<int> worker_rc{0};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (!out_pinned) task_pool().ensure(host_copy_threads());
 
-    struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kSlots];
+    struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kMaxSlots];
     const bool trace = getenv("PSTB_HOST_TRACE") != nullptr;
     double t_wait = 0.0, t_copy = 0.0, t_enq = 0.0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    // the copy of one staged chunk into the pageable destination (run by a pool worker)
+    auto drain_chunk = [&](int slot, int64_t b0, int64_t ns) {
+        const char* src = (const char*)c.h_out[slot].p;
+        if (order == PSTB_ORDER_F) {
+            memcpy((char*)h_out + (size_t)b0 * col_bytes, src, (size_t)ns * col_bytes);
+        } else {
+            for (size_t i = 0; i < (size_t)n_iid; ++i)
+                memcpy((char*)h_out + (i * (size_t)n_sid + (size_t)b0) * es, src + i * (size_t)ns * es, (size_t)ns * es);
+        }
+    };
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return 0;
         const auto tw = now();
+        if (!out_pinned) {                                          // wait for the worker that drains this slot
+            std::unique_lock<std::mutex> lk(slot_m);
+            slot_cv.wait(lk, [&] { return !slot_busy[slot]; });
+            t_wait += ms_since(tw);
+            pend[slot].active = false;
+            return worker_rc.load() ? fail("a host copy worker failed (CUDA error %d)", worker_rc.load()) : 0;
+        }
         PSTB_CUDA(cudaEventSynchronize(c.done[slot]));
         t_wait += ms_since(tw);
         pend[slot].active = false;
@@ -336,12 +427,12 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         if (e__ != cudaSuccess) { rc = pstb::fail("%s -> %s", #x, cudaGetErrorString(e__)); break; } \
     }
     for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
-        const int slot = (int)(ch % kSlots);
+        const int slot = (int)(ch % nslots);
         const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
         if ((rc = finish(slot))) break;
         const auto te = now();
         struct EnqTimer { double& acc; std::chrono::steady_clock::time_point t0; ~EnqTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } enq_timer{t_enq, te};
-        cudaStream_t st = c.s[slot];
+        cudaStream_t st = c.s[slot % kSlots];
         // ---- input records ----
         bool contiguous = true;
         const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
@@ -387,15 +478,33 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         pend[slot].b0 = b0;
         pend[slot].ns = ns;
         pend[slot].active = true;
+        if (!out_pinned) {
+            {
+                std::unique_lock<std::mutex> lk(slot_m);
+                slot_busy[slot] = true;
+            }
+            cudaEvent_t ev = c.done[slot];
+            task_pool().submit([&, slot, b0, ns, ev, cur_dev] {
+                static thread_local int dev_set = -1;
+                if (dev_set != cur_dev) { cudaSetDevice(cur_dev); dev_set = cur_dev; }
+                const cudaError_t e = cudaEventSynchronize(ev);
+                if (e != cudaSuccess) worker_rc.store((int)e); else drain_chunk(slot, b0, ns);
+                {
+                    std::unique_lock<std::mutex> lk(slot_m);
+                    slot_busy[slot] = false;
+                }
+                slot_cv.notify_all();
+            });
+        }
     }
 #undef PSTB_CUDA_BREAK
-    for (int k = 0; k < kSlots; ++k) {
+    for (int k = 0; k < kMaxSlots; ++k) {
         int r2 = finish(k);
         if (!rc) rc = r2;
     }
     if (trace)
-        fprintf(stderr, "[pstb_read_host] %lld chunks of %lld SNPs, %d copy threads: event wait %.1f ms, host copy %.1f ms, enqueue %.1f ms\n",
-                (long long)nchunks, (long long)chunk, host_copy_threads(), t_wait, t_copy, t_enq);
+        fprintf(stderr, "[pstb_read_host] %lld chunks of %lld SNPs, %d slots, %d copy workers: waiting for slots %.1f ms, enqueue %.1f ms\n",
+                (long long)nchunks, (long long)chunk, nslots, host_copy_threads(), t_wait, t_enq);
     if (rc) {
         cudaDeviceSynchronize();
         return rc;

@@ -108,3 +108,45 @@ try:
     rt.cudaHostUnregister(d.ctypes.data)
 except Exception as e:
     print("cudaHostRegister probe failed:", e)
+
+# ---- the same fills next to a saturated D2H DMA stream (what pstb_read_host's staging copy competes with) ----
+try:
+    import torch
+    g = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    stop = False
+    moved = [0]
+
+    def dma():
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            while not stop:
+                hp.copy_(g, non_blocking=True)
+                s.synchronize()
+                moved[0] += 1
+    th = threading.Thread(target=dma)
+    th.start()
+    time.sleep(0.2)
+    for threads in (8, 14, 16):
+        d = np.empty(SIZE, dtype=np.uint8)
+        m0, t0 = moved[0], time.perf_counter()
+        dt = fill(d, threads)
+        dma_rate = (moved[0] - m0) * (1 << 30) / (time.perf_counter() - t0) / 1e9
+        dt2 = fill(d, threads)
+        print("next to a D2H DMA stream (%.0f GB/s): fresh fill %2d threads %5.1f GB/s, second pass %5.1f GB/s" % (dma_rate, threads, SIZE / dt / 1e9, SIZE / dt2 / 1e9), flush=True)
+        del d
+    # copying OUT OF the pinned buffer the DMA writes (cold lines, as in the pipeline) instead of a resident source
+    src_pinned = hp.numpy()
+    for threads in (8, 14):
+        d = np.empty(SIZE, dtype=np.uint8)
+        src_backup = src
+        globals()["src"] = src_pinned[: 256 << 20]
+        dt = fill(d, threads)
+        dt2 = fill(d, threads)
+        globals()["src"] = src_backup
+        print("source = the pinned DMA target: fresh fill %2d threads %5.1f GB/s, second pass %5.1f GB/s" % (threads, SIZE / dt / 1e9, SIZE / dt2 / 1e9), flush=True)
+        del d
+    stop = True
+    th.join()
+except Exception as e:
+    print("DMA contention probe failed:", e)

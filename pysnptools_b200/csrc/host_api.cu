@@ -752,29 +752,40 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     mark("slices enqueued");
     if (exact ? pstb_mirror_lower_f64((double*)d_K.p, n_iid, n_iid, comp) : pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
     // ---- K back to the host: row bands, converted on the device, D2H overlapped with the next band's conversion ----
+    // pinned destination: 2 slots of 128 MiB straight into it; pageable one: up to 16 slots of 32 MiB, each drained by one worker of
+    // the calling thread's task pool (as in pstb_read_host)
     const bool out_pinned = is_pinned(h_K);
     const size_t row_bytes = (size_t)n_iid * es;
-    int64_t band = (int64_t)(((size_t)128 << 20) / row_bytes);
+    const int nsl = out_pinned ? 2 : kMaxSlots;
+    int64_t band = (int64_t)(((size_t)(out_pinned ? 128 : 32) << 20) / row_bytes);
     if (band < 1) band = 1;
     if (band > n_iid) band = n_iid;
     if (cudaStreamSynchronize(comp) != cudaSuccess) return cleanup(fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
     mark("kernel finished");
-    struct Pend { int64_t r0 = 0, nr = 0; bool active = false; } pend[2];
+    struct Pend { int64_t r0 = 0, nr = 0; bool active = false; } pend[kMaxSlots];
+    std::mutex slot_m;
+    std::condition_variable slot_cv;
+    bool slot_busy[kMaxSlots] = {};
+    std::atomic<int> worker_rc{0};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (!out_pinned) task_pool().ensure(host_copy_threads());
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return 0;
-        if (cudaEventSynchronize(c.done[slot]) != cudaSuccess) return fail("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         pend[slot].active = false;
-        if (out_pinned) return 0;
-        const char* src = (const char*)c.h_out[slot].p;
-        char* dst = (char*)h_K + (size_t)pend[slot].r0 * row_bytes;
-        parallel_ranges((size_t)pend[slot].nr * row_bytes, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+        if (!out_pinned) {
+            std::unique_lock<std::mutex> lk(slot_m);
+            slot_cv.wait(lk, [&] { return !slot_busy[slot]; });
+            return worker_rc.load() ? fail("a host copy worker failed (CUDA error %d)", worker_rc.load()) : 0;
+        }
+        if (cudaEventSynchronize(c.done[slot]) != cudaSuccess) return fail("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 0;
     };
     for (int64_t r0 = 0, bi = 0; r0 < n_iid && !rc; r0 += band, ++bi) {
-        const int slot = (int)(bi & 1);
+        const int slot = (int)(bi % nsl);
         const int64_t nr = (r0 + band <= n_iid) ? band : n_iid - r0;
         if ((rc = finish(slot))) break;
-        cudaStream_t st = c.s[slot];
+        cudaStream_t st = c.s[slot % 2];
         const float* src = (const float*)d_K.p + (size_t)r0 * n_iid;
         const void* from = src;
         if (exact) {
@@ -797,8 +808,29 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
         pend[slot].r0 = r0;
         pend[slot].nr = nr;
         pend[slot].active = true;
+        if (!out_pinned) {
+            {
+                std::unique_lock<std::mutex> lk(slot_m);
+                slot_busy[slot] = true;
+            }
+            cudaEvent_t ev = c.done[slot];
+            const char* stage = (const char*)c.h_out[slot].p;
+            char* dest = (char*)h_K + (size_t)r0 * row_bytes;
+            const size_t bytes = (size_t)nr * row_bytes;
+            task_pool().submit([&, slot, ev, stage, dest, bytes, cur_dev] {
+                static thread_local int dev_set = -1;
+                if (dev_set != cur_dev) { cudaSetDevice(cur_dev); dev_set = cur_dev; }
+                const cudaError_t e = cudaEventSynchronize(ev);
+                if (e != cudaSuccess) worker_rc.store((int)e); else memcpy(dest, stage, bytes);
+                {
+                    std::unique_lock<std::mutex> lk(slot_m);
+                    slot_busy[slot] = false;
+                }
+                slot_cv.notify_all();
+            });
+        }
     }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kMaxSlots; ++k) {
         int r2 = finish(k);
         if (!rc) rc = r2;
     }

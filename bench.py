@@ -457,11 +457,11 @@ def run_gpu(args):
     traffic = args.ncu_traffic
     if traffic is None:
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_read_f_cfg2_dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_read_f_cfg2_dram_bytes_per_launch"]
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/r1_read_f_full.txt), bytes per launch", "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
+                "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/r2_read_f_full.txt), bytes per launch", "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
 
     # ---- spot parity of the timed configuration against the oracle (not timed) ----

@@ -44,7 +44,8 @@ struct ReadParams {
     long long seg_len;      // outputs per segment (multiple of 16) when direct
     int vec_ok;             // output columns: 2 = 32-byte aligned, 1 = 16-byte aligned, 0 = neither
     unsigned int* miss_flag;    // optional: set to 1 when any selected genotype of any processed SNP is missing (K3 picks its GEMM by it)
-    int l2_prefetch;            // staged gather: prefetch the records two batches ahead into L2
+    int* counter;               // zeroed per launch: records / batches are handed out through it (atomicAdd), not by a static stride --
+                                // SMs do not get equal shares of the memory system, and equal shares of the work left 13 % of the SM time idle
     const uint32_t* sel_mask;   // gather: 2 bits per individual (0b01 = selected), built once per call; word [mask_words] = "index vector has repeats"
     long long mask_words;
 };
@@ -227,11 +228,11 @@ template <typename T, bool kCta>
 __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k_read_f(const ReadParams p) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     __shared__ unsigned int red[3][16];
+    __shared__ int s_claim;
 
     const int gsize = kCta ? (int)blockDim.x : 32;
     const int gid = kCta ? (int)threadIdx.x : (int)(threadIdx.x & 31);
     const int g_in_cta = kCta ? 0 : (int)(threadIdx.x >> 5);
-    const int groups_per_cta = kCta ? 1 : (int)(blockDim.x >> 5);
     auto gsync = [&]() {
         if (kCta) __syncthreads(); else __syncwarp();
     };
@@ -241,9 +242,19 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
     unsigned char* raw0 = gs + 16;
     unsigned char* dense = raw0 + (size_t)p.nbuf * p.raw_stride;
 
-    const long long ngroups = (long long)gridDim.x * groups_per_cta;
     const long long n_out = p.iid.n;
-    long long b = (long long)blockIdx.x * groups_per_cta + g_in_cta;
+    // the next record of this group (warp or CTA), claimed from the launch's counter
+    auto claim = [&]() -> long long {
+        if (kCta) {
+            __syncthreads();                                        // the previous claim has been read by everyone
+            if (threadIdx.x == 0) s_claim = atomicAdd(p.counter, 1);
+            __syncthreads();
+            return (long long)s_claim;
+        }
+        int v = 0;
+        if (gid == 0) v = atomicAdd(p.counter, 1);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
 
     if (p.bulk_ok) {
         if (gid == 0) {
@@ -258,13 +269,14 @@ __global__ void __launch_bounds__(kCta ? 512 : 256, kCta ? 2 : PSTB_READ_MINB) k
         mbar_expect_tx(&bars[buf], p.copy_bytes);
         bulk_g2s(raw0 + (size_t)buf * p.raw_stride, p.packed + j * p.ld, p.copy_bytes, &bars[buf]);
     };
+    long long b = claim(), nb = 0;
     if (p.bulk_ok && !p.direct && gid == 0 && b < p.sid.n) issue(b, 0);
 
-    for (uint32_t it = 0; b < p.sid.n; b += ngroups, ++it) {
+    for (uint32_t it = 0; b < p.sid.n; b = nb, ++it) {
         const int cur = (p.nbuf == 2) ? (int)(it & 1u) : 0;
         const uint32_t parity = (p.nbuf == 2) ? ((it >> 1) & 1u) : (it & 1u);
         unsigned char* raw = raw0 + (size_t)cur * p.raw_stride;
-        const long long nb = b + ngroups;
+        nb = claim();
         const long long j = clampll(p.sid.at(b), p.sid_count);
         const uint8_t* src = p.packed + j * p.ld;
         if (p.direct) {
@@ -393,14 +405,18 @@ __device__ __forceinline__ int8_t shfl_t<int8_t>(int8_t v, int src) { return (in
 template <typename T>
 __global__ void __launch_bounds__(256) k_read_f_small(const ReadParams p, int R) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned buf_bytes = (unsigned)R * (unsigned)p.ld;
     unsigned char* ws = smem_dyn + (size_t)w * (16u + 2u * buf_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(ws);
     unsigned char* raw0 = ws + 16;
     const long long n_out = p.iid.n;
-    const long long nbatch = (p.sid.n + R - 1) / R, nwarps = (long long)gridDim.x * nw;
-    long long bt = (long long)blockIdx.x * nw + w;
+    const long long nbatch = (p.sid.n + R - 1) / R;
+    auto claim = [&]() -> long long {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(p.counter, 1);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
     if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -413,11 +429,13 @@ __global__ void __launch_bounds__(256) k_read_f_small(const ReadParams p, int R)
         mbar_expect_tx(&bars[buf], bytes);
         bulk_g2s(raw0 + (size_t)buf * buf_bytes, p.packed + (p.sid.start + s0) * p.ld, bytes, &bars[buf]);
     };
+    long long bt = claim(), nbt = 0;
     if (lane == 0 && bt < nbatch) issue(bt, 0);
     const long long nwords = (n_out + 15) >> 4;
-    for (uint32_t it = 0; bt < nbatch; bt += nwarps, ++it) {
+    for (uint32_t it = 0; bt < nbatch; bt = nbt, ++it) {
         const int cur = (int)(it & 1u);
-        if (lane == 0 && bt + nwarps < nbatch) issue(bt + nwarps, cur ^ 1);
+        nbt = claim();
+        if (lane == 0 && nbt < nbatch) issue(nbt, cur ^ 1);
         mbar_wait(&bars[cur], (it >> 1) & 1u);
         const unsigned char* raw = raw0 + (size_t)cur * buf_bytes + p.byte_off;
         const long long s0 = bt * R;
@@ -474,12 +492,16 @@ __global__ void __launch_bounds__(256) k_stats_dense(const ReadParams p, int R) 
     // a warp takes R consecutive records at a time (R a power of two <= 32); lane r keeps the counts of record r, so the fp64
     // mean / sd arithmetic runs once per R records with R lanes busy and the statistics leave as one coalesced store
     const int lane = threadIdx.x & 31;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long n_out = p.iid.n;
     const long long full16 = n_out >> 6;                       // 128-bit words holding 64 selected genotypes each
     const long long tail0 = full16 << 6;                       // first genotype of the tail
     const long long tail_words = (n_out - tail0 + 15) >> 4;    // 32-bit words of the tail (last one masked)
-    for (long long b0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; b0 < p.sid.n; b0 += nwarps * R) {
+    auto claim = [&]() -> long long {                          // the warp's next block of R records
+        int v = 0;
+        if (lane == 0) v = atomicAdd(p.counter, 1);
+        return (long long)__shfl_sync(0xffffffffu, v, 0) * R;
+    };
+    for (long long b0 = claim(); b0 < p.sid.n; b0 = claim()) {
         unsigned int k1 = 0, k2 = 0, k3 = 0;
         const int nrec = (int)min((long long)R, p.sid.n - b0);
         for (int r = 0; r < nrec; ++r) {
@@ -541,6 +563,7 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
     __shared__ unsigned int cnt[kGatherMaxS][3];
     __shared__ double st_s[kGatherMaxS][2];
     __shared__ double lut_d[kGatherMaxS][4];
+    __shared__ int s_claim[2];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_dyn);
     unsigned char* raw0 = smem_dyn + 16;
     unsigned char* dense0 = raw0 + (size_t)S * p.raw_stride;
@@ -550,11 +573,6 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
     const long long nbytes = (n_out + 3) >> 2;
     const bool idx_vec = p.iid.idx && ((reinterpret_cast<uintptr_t>(p.iid.idx) & 15u) == 0);
 
-    if (p.bulk_ok && tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
     auto issue = [&](long long batch) {
         const long long b0 = batch * S;
         const int ns = (int)min((long long)S, p.sid.n - b0);
@@ -564,10 +582,20 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
             bulk_g2s(raw0 + (size_t)s * p.raw_stride, p.packed + j * p.ld, p.copy_bytes, bar);
         }
     };
-    long long batch = blockIdx.x;
-    if (p.bulk_ok && tid == 0 && batch < nbatch) issue(batch);
+    // batches are claimed from the launch's counter by thread 0, one ahead (slot it & 1 holds the batch of iteration it)
+    if (tid == 0) {
+        if (p.bulk_ok) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        s_claim[0] = atomicAdd(p.counter, 1);
+        if (p.bulk_ok && s_claim[0] < nbatch) issue(s_claim[0]);
+    }
+    __syncthreads();
 
-    for (uint32_t it = 0; batch < nbatch; batch += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
+        const long long batch = s_claim[it & 1u];
+        if (batch >= nbatch) break;
         const long long b0 = batch * S;
         const int ns = (int)min((long long)S, p.sid.n - b0);
         if (p.bulk_ok) {
@@ -614,8 +642,11 @@ __global__ void __launch_bounds__(1024, 1) k_read_f_gather(const ReadParams p, i
             }
         }
         __syncthreads();
-        const long long nbt = batch + gridDim.x;
-        if (p.bulk_ok && tid == 0 && nbt < nbatch) issue(nbt);      // raw buffers are free again
+        if (tid == 0) {
+            const int nbt = atomicAdd(p.counter, 1);
+            s_claim[(it + 1u) & 1u] = nbt;                           // read after the barrier that ends this iteration
+            if (p.bulk_ok && nbt < nbatch) issue(nbt);               // raw buffers are free again
+        }
 
         if (p.mode != PSTB_STD_NONE) {
             if (!p.use_stats) {
@@ -747,6 +778,7 @@ template <typename T, bool kStaged>
 __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_f_gather4(const ReadParams p) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t stage_bar;
+    __shared__ int s_claim[2];                                     // batch of iteration it in slot it & 1 (claimed one ahead by thread 0)
     __shared__ unsigned int cnt[4][3];
     __shared__ double st_s[4][2];
     __shared__ double lut_d[4][4];
@@ -766,25 +798,15 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
         for (int s = 0; s < 4; ++s)
             bulk_g2s(raw0 + (size_t)s * p.raw_stride, p.packed + clampll(p.sid.at(bb + min(s, nn - 1)), p.sid_count) * p.ld, p.copy_bytes, &stage_bar);
     };
-    // ... and the batch after the staged one into L2 (no shared memory needed), by four lanes of another warp: the staging copy then is an
-    // L2 hit instead of a DRAM read that has to find its way through the write flood within ONE batch time.  Without it the kernel's time
-    // depended on where the buffers happened to lie in HBM: 4.3 ms in one process, 5.6 - 11.8 ms in the next (cfg4, same data).
-    auto prefetch_l2 = [&](long long batch) {
-        if (!p.l2_prefetch || batch >= nbatch || tid < 32 || tid >= 36) return;
-        const long long j = (batch << 2) + (tid - 32);
-        if (j >= p.sid.n) return;
-        const uint8_t* src = p.packed + clampll(p.sid.at(j), p.sid_count) * p.ld;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(p.copy_bytes) : "memory");
-    };
-    if (kStaged) {
-        if (tid == 0) {
+    if (tid == 0) {
+        if (kStaged) {
             mbar_init(&stage_bar, 1);
             fence_mbar_init();
-            if ((long long)blockIdx.x < nbatch) issue(blockIdx.x);
         }
-        prefetch_l2((long long)blockIdx.x + gridDim.x);
-        __syncthreads();
+        s_claim[0] = atomicAdd(p.counter, 1);
+        if (kStaged && s_claim[0] < nbatch) issue(s_claim[0]);
     }
+    __syncthreads();
     uint32_t iter = 0;
     // statistics of gathered reads without a second gather: masked popcounts over the raw records (see k_build_sel_mask)
     const bool mask_count = kStaged && p.mode != PSTB_STD_NONE && !p.use_stats && p.sel_mask != nullptr && __ldg(p.sel_mask + p.mask_words) == 0u;
@@ -812,7 +834,9 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
         return (int)min(4LL, n_out - (q << 2));
     };
 
-    for (long long batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    for (;;) {
+        const long long batch = s_claim[iter & 1u];
+        if (batch >= nbatch) break;
         const long long b0 = batch << 2;
         const int ns = (int)min(4LL, p.sid.n - b0);
         const uint8_t* src[4];
@@ -863,8 +887,11 @@ __global__ void __launch_bounds__(kStaged ? 1024 : 512, kStaged ? 1 : 2) k_read_
             }
         }
         __syncthreads();
-        if (kStaged && tid == 0 && batch + gridDim.x < nbatch) issue(batch + gridDim.x);   // staging area is free again
-        if (kStaged) prefetch_l2(batch + 2 * (long long)gridDim.x);
+        if (tid == 0) {
+            const int nbt = atomicAdd(p.counter, 1);
+            s_claim[iter & 1u] = nbt;                                   // iter was advanced above: the next iteration's slot, read after later barriers
+            if (kStaged && nbt < nbatch) issue(nbt);                     // staging area is free again
+        }
         // ---- pass 1: dosage counts of the 4 SNPs over the selected individuals ----
         if (p.mode != PSTB_STD_NONE) {
             if (!p.use_stats && !mask_count) {
@@ -1283,6 +1310,7 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     }
     p.out_ld = n_out;
     p.vec_ok = 0;
+    if (next_counter(st, &p.counter)) return 1;                   // every F-order kernel below hands its records out through it
     if (p.out) {
         const uintptr_t base = reinterpret_cast<uintptr_t>(p.out);
         const long long col = n_out * (long long)sizeof(T);
@@ -1317,8 +1345,6 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
             const unsigned staged_bytes = inter_bytes + 4u * rec16;
             const bool staged = p.bulk_ok && staged_bytes <= max_smem && !getenv("PSTB_GATHER_NOSTAGE");
             if (staged) {
-                // optional (PSTB_GATHER_L2PF=1): measured 74-79 % of the HBM peak with it, 79-80 % without on cfg4
-                p.l2_prefetch = (getenv("PSTB_GATHER_L2PF") && atoi(getenv("PSTB_GATHER_L2PF")) != 0) ? 1 : 0;
                 keep_pool_memory(st);
                 uint32_t* d_mask = nullptr;
                 if (p.mode != PSTB_STD_NONE && !p.use_stats) {
@@ -1412,18 +1438,18 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     if (warp_group <= 12u * 1024u) {
         p.nbuf = 2;
         p.group_smem = warp_group;
-        const int warps = 8;
+        int warps = 8;
+        if (const char* e = getenv("PSTB_READ_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 8) warps = v; }      // tuning experiments
         const unsigned smem = warps * p.group_smem;
         PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // persistent grid: exactly the CTAs that are resident at once, so every warp streams the same number of records
+        // persistent grid of resident CTAs; the warps claim their records from p.counter.  Eight resident warps per SM write DRAM
+        // best (cfg2, scripts/bench_read.py feed: 8 warps x 1 CTA 101.8 % of the measured copy peak, 6 x 1 102.8 %, 4 x 2 101.5 %, 8 x 2
+        // 98.1 %, 4 x 4 98.0 %; 4 x 1 is too few: 76.8 %).  Short records keep full occupancy.  A statistics-only pass (no output) is a
+        // pure latency-bound read and wants every resident warp it can get.
         int ctas_per_sm = 1;
         PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f<T, false>, warps * 32, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
-        // fewer concurrent column streams write DRAM more efficiently (measured on cfg2: 1 CTA/SM 84.4 %, 2: 83.9 %, 4: 82.6 % of
-        // the HBM peak); two CTAs keep enough warps to hide the per-record statistics chain.  Short records keep full occupancy.
-        // A statistics-only pass (no output: the first pass of a C-order read, every K3 chunk) is a pure latency-bound read and
-        // wants every resident warp it can get (2 CTAs/SM read 2.5 TB/s on cfg2-sized records).
-        if (p.out && p.rec_bytes >= 1024 && ctas_per_sm > 2) ctas_per_sm = 2;
+        if (p.out && p.rec_bytes >= 1024) ctas_per_sm = 1;
         if (const char* e = getenv("PSTB_READ_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctas_per_sm = v; }   // tuning experiments
         long long want = (p.sid.n + warps - 1) / warps;
         long long grid = (long long)sms * ctas_per_sm;

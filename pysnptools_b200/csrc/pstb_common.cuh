@@ -10,6 +10,7 @@ namespace pstb {
 int fail(const char* fmt, ...);           // records the thread-local message, returns 1
 void count_launch(int n = 1);             // feeds pstb_launch_count()
 int sm_count_cached();
+int next_counter(cudaStream_t st, int** out);   // zeroed device int for an atomic work feed (ring, cleared in stream order)
 
 // selection along one axis as the kernels see it
 struct Axis {

@@ -32,6 +32,28 @@ int sm_count_cached() {
     return sms;
 }
 
+// zeroed launch counter for the kernels that feed work through an atomic (k_syrk2's tile feed, the records of the F-order read kernels):
+// a small per-thread, per-device ring, cleared in stream order before every launch
+int next_counter(cudaStream_t st, int** out) {
+    constexpr int kRing = 256;
+    static thread_local int* d_ring = nullptr;
+    static thread_local int ring_dev = -1;
+    static thread_local unsigned seq = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail("cudaGetDevice failed");
+    if (!d_ring || ring_dev != dev) {
+        d_ring = nullptr;                                   // (a ring of another device is left to that device's teardown)
+        cudaError_t e = cudaMalloc(&d_ring, kRing * sizeof(int));
+        if (e != cudaSuccess) return fail("cudaMalloc(counter ring) -> %s", cudaGetErrorString(e));
+        ring_dev = dev;
+    }
+    int* c = d_ring + (seq++ % kRing);
+    cudaError_t e = cudaMemsetAsync(c, 0, sizeof(int), st);
+    if (e != cudaSuccess) return fail("cudaMemsetAsync(counter) -> %s", cudaGetErrorString(e));
+    *out = c;
+    return 0;
+}
+
 }  // namespace pstb
 
 extern "C" int pstb_version(void) { return 100; }

@@ -98,9 +98,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <typename T>
 __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, long long n_sid, int mode, double a, double b,
                                                       double lnB, int apply, int use_stats, double* stats, unsigned col_bytes,
-                                                      int nbuf) {
+                                                      int nbuf, int* counter) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ double scratch[64];
+    __shared__ int s_claim;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn);
     unsigned char* buf0 = smem_dyn + 128;
     const int tid = threadIdx.x;
@@ -114,13 +115,20 @@ __global__ void __launch_bounds__(1024) k_std_f_staged(T* val, long long n_iid, 
         mbar_expect_tx(&bars[buf], col_bytes);
         bulk_g2s(buf0 + (size_t)buf * col_bytes, val + jj * n_iid, col_bytes, &bars[buf]);
     };
-    long long j = blockIdx.x;
+    // columns are claimed from the launch's counter (one ahead), not dealt out by a static stride: see ReadParams::counter
+    auto claim = [&]() -> long long {
+        __syncthreads();                                  // the previous claim has been read by everyone
+        if (tid == 0) s_claim = atomicAdd(counter, 1);
+        __syncthreads();
+        return (long long)s_claim;
+    };
+    long long j = claim(), nj = 0;
     if (tid == 0 && j < n_sid) issue(j, 0);
-    for (uint32_t it = 0; j < n_sid; j += gridDim.x, ++it) {
+    for (uint32_t it = 0; j < n_sid; j = nj, ++it) {
         const int cur = (nbuf == 2) ? (int)(it & 1u) : 0;
         const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1u) : (it & 1u);
         T* col = reinterpret_cast<T*>(buf0 + (size_t)cur * col_bytes);
-        const long long nj = j + gridDim.x;
+        nj = claim();
         if (nbuf == 2 && tid == 0 && nj < n_sid) {
             bulk_store_wait_read();                       // the store of the column that lived in the other buffer has read it
             issue(nj, cur ^ 1);
@@ -340,8 +348,10 @@ static int standardize_impl(T* d_val, int order, int64_t n_iid, int64_t n_sid, i
             if (ctas_per_sm < 1) ctas_per_sm = 1;
             long long grid = (long long)sms * ctas_per_sm;
             if (grid > n_sid) grid = n_sid;
+            int* counter = nullptr;
+            if (next_counter(st, &counter)) return 1;
             k_std_f_staged<T><<<(unsigned)grid, threads, smem, st>>>(d_val, n_iid, n_sid, mode, a, b, lnB, apply, use_stats, d_stats,
-                                                                     (unsigned)col_bytes, nbuf);
+                                                                     (unsigned)col_bytes, nbuf, counter);
             PSTB_AFTER_LAUNCH("k_std_f_staged");
             return 0;
         }

@@ -1145,25 +1145,6 @@ void build_tiles(long long n, std::vector<int2>& out) {
                     if ((long long)J * BN <= (long long)I * BM + BM - 1) out.push_back(make_int2(I, J));
 }
 
-// zeroed launch counter for the dynamic tile feed: a small per-thread, per-device ring, cleared in stream order before every launch
-int next_counter(cudaStream_t st, int** out) {
-    constexpr int kRing = 256;
-    static thread_local int* d_ring = nullptr;
-    static thread_local int ring_dev = -1;
-    static thread_local unsigned seq = 0;
-    int dev = 0;
-    PSTB_CUDA(cudaGetDevice(&dev));
-    if (!d_ring || ring_dev != dev) {
-        d_ring = nullptr;                                   // (a ring of another device is left to that device's teardown)
-        PSTB_CUDA(cudaMalloc(&d_ring, kRing * sizeof(int)));
-        ring_dev = dev;
-    }
-    int* c = d_ring + (seq++ % kRing);
-    PSTB_CUDA(cudaMemsetAsync(c, 0, sizeof(int), st));
-    *out = c;
-    return 0;
-}
-
 struct TileCache {
     long long n = -1;
     int device = -1;

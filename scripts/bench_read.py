@@ -139,3 +139,21 @@ if "nsweep" in which:
     for n in (300, 1000, 2000, 4000, 8000, 16000, 24000, 32000):
         m = int(4e9 // (4 * n)) // 8 * 8
         run("decode+Unit f32 F N=%d" % n, n, m, np.float32, "F", ("unit",))
+if "feed" in which:
+    # k_read_f<warp> knobs (read per launch) under the dynamic record feed: warps per CTA x CTAs per SM, on cfg2 and neighbouring shapes
+    st2 = rand_store(10000, 1000000)
+    for warps, ctas in ((8, 1), (8, 2), (6, 1), (6, 2), (4, 1), (4, 2), (4, 3), (4, 4), (2, 2), (2, 4)):
+        os.environ["PSTB_READ_WARPS"] = str(warps); os.environ["PSTB_READ_CTAS"] = str(ctas)
+        run("cfg2 warps=%d ctas=%d" % (warps, ctas), 10000, 1000000, np.float32, "F", ("unit",), store=st2)
+    for warps, ctas in ((8, 1), (8, 2), (4, 2)):
+        os.environ["PSTB_READ_WARPS"] = str(warps); os.environ["PSTB_READ_CTAS"] = str(ctas)
+        run("cfg2 f64 warps=%d ctas=%d" % (warps, ctas), 10000, 500000, np.float64, "F", ("unit",), store=dev.PackedStore(st2.tensor[:500000], 10000, 500000))
+        run("cfg2 decode only warps=%d ctas=%d" % (warps, ctas), 10000, 1000000, np.float32, "F", None, store=st2)
+    del st2
+    for n in (4104, 6000, 20000):
+        stn = rand_store(n, int(1e10 // n // 8 * 8))
+        for warps, ctas in ((8, 1), (8, 2), (4, 2)):
+            os.environ["PSTB_READ_WARPS"] = str(warps); os.environ["PSTB_READ_CTAS"] = str(ctas)
+            run("warps=%d ctas=%d" % (warps, ctas), n, stn.sid_count, np.float32, "F", ("unit",), store=stn)
+        del stn
+    del os.environ["PSTB_READ_WARPS"], os.environ["PSTB_READ_CTAS"]

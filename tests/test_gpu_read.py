@@ -442,3 +442,37 @@ def test_host_abi_standardize_pipelined_chunks(pinned, oracle, monkeypatch):
             again = np.array(y, dtype=dtype, order="F")
             assert lib.pstb_standardize_host(p(again.ctypes.data), code, 0, n, m, mode, ab[0], ab[1], 1, 1, p(st.ctypes.data)) == 0, _lib.last_error()
             np.testing.assert_allclose(again, val, rtol=1e-12 if dtype == np.float64 else 1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,m", [(256, 37), (1000, 131), (4104, 67), (10000, 94), (12296, 23), (24568, 11)])
+def test_dynamic_record_feed(n, m, oracle, dev):
+    """The F-order kernels hand their records out through an atomic counter (one claim ahead of the record being written): every
+    output column must still be written exactly once whatever the claim order.  Dense rows over the warp-per-record sizes, SNP
+    counts that are not multiples of anything, scattered / strided / reversed SNP selections, a row range starting at a multiple
+    of 16, trained statistics, count_A1 -- decode bit-exact, standardized values at the reference tolerance."""
+    from pysnptools_b200 import _lib
+    rng = np.random.default_rng(n + m)
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.04, seed=n)
+    store = dev.PackedStore.from_host(packed, n)
+    sels = [None, np.arange(m)[::-1].copy(), rng.permutation(m)[: m // 2 + 1].astype(np.int64), np.arange(1, m, 3, dtype=np.int64), np.array([5], dtype=np.int64)]
+    rows = [None]
+    if n >= 1024:
+        rows.append(np.arange(16, 16 + (n - 16) // 8 * 8 - 8, dtype=np.int64))            # dense range, length a multiple of 8
+    before = _lib.lib.pstb_launch_count()
+    for ii in rows:
+        for si in sels:
+            for count_A1 in (False, True):
+                want = oracle.decode(packed, n, ii, si, count_A1, np.float64, "F")
+                for dtype in (np.float32, np.float64):
+                    val, _ = dev.read(store, ii, si, count_A1=count_A1, dtype=dtype, order="F")
+                    assert np.array_equal(_np(val), want.astype(dtype), equal_nan=True), (n, m, dtype, count_A1)
+            raw = oracle.decode(packed, n, ii, si)
+            for std, args in ((("unit",), (False, np.nan, np.nan)), (("beta", 1, 25), (True, 1, 25))):
+                ref, rst = oracle.standardize(raw, *args)
+                for dtype in (np.float64, np.float32):
+                    val, st = dev.read(store, ii, si, dtype=dtype, order="F", standardizer=std)
+                    np.testing.assert_allclose(_np(st), rst, rtol=1e-12)
+                    np.testing.assert_allclose(_np(val), ref, rtol=STD_RTOL, atol=1e-6 if dtype == np.float32 else 1e-12)
+                    val2, _ = dev.read(store, ii, si, dtype=dtype, order="F", standardizer=std, stats=st)
+                    assert np.array_equal(_np(val2), _np(val))                              # trained statistics: the same table, the same bits
+    assert _lib.lib.pstb_launch_count() > before

@@ -1438,7 +1438,11 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
     if (warp_group <= 12u * 1024u) {
         p.nbuf = 2;
         p.group_smem = warp_group;
-        int warps = 8;
+        // eight resident warps per SM write DRAM best; columns up to 20 KB (int8 output, N < ~5 000 float32) want them as two CTAs of four
+        // (cfg2 int8: 4 x 2 89.7 % of the copy peak, 8 x 1 80.9 %, 8 x 2 and more 60 %; float32 N = 4 104: 93.2 vs 90.9 %)
+        const bool long_out = p.out && p.rec_bytes >= 1024;
+        const bool two_ctas = long_out && n_out * (long long)sizeof(T) <= 20 * 1024;
+        int warps = two_ctas ? 4 : 8;
         if (const char* e = getenv("PSTB_READ_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 8) warps = v; }      // tuning experiments
         const unsigned smem = warps * p.group_smem;
         PSTB_CUDA(cudaFuncSetAttribute(k_read_f<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1449,7 +1453,7 @@ static int launch_read(const ReadParams& base, int order, cudaStream_t st) {
         int ctas_per_sm = 1;
         PSTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_read_f<T, false>, warps * 32, smem));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
-        if (p.out && p.rec_bytes >= 1024) ctas_per_sm = 1;
+        if (long_out) ctas_per_sm = two_ctas && ctas_per_sm >= 2 ? 2 : 1;
         if (const char* e = getenv("PSTB_READ_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctas_per_sm = v; }   // tuning experiments
         long long want = (p.sid.n + warps - 1) / warps;
         long long grid = (long long)sms * ctas_per_sm;

@@ -55,7 +55,7 @@ constexpr int kMaxSlots = 16; // ... and with a pageable destination: chunks in 
 struct HostCtx {
     int device = -1;
     cudaStream_t s[kSlots] = {};
-    cudaEvent_t done[kMaxSlots] = {};
+    cudaEvent_t done[kMaxSlots] = {}, in_done[kMaxSlots] = {};
     Buf d_packed[kMaxSlots], d_tight[kMaxSlots], d_out[kMaxSlots], d_stats, d_idx, d_work, d_K, h_in[kMaxSlots], h_out[kMaxSlots];
     cudaEvent_t copied[2] = {}, used[2] = {};
     HostCtx() {
@@ -72,7 +72,9 @@ struct HostCtx {
         for (int k = 0; k < kMaxSlots; ++k) {
             d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release();
             if (done[k]) cudaEventDestroy(done[k]);
+            if (in_done[k]) cudaEventDestroy(in_done[k]);
             PSTB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+            PSTB_CUDA(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
         }
         for (int k = 0; k < kSlots; ++k) {
             if (s[k]) cudaStreamDestroy(s[k]);
@@ -127,8 +129,9 @@ class CopyPool {
   public:
     ~CopyPool() { stop(); }
     template <typename F>
-    void run(size_t count, size_t min_per_thread, F&& body) {
+    void run(size_t count, size_t min_per_thread, F&& body, int max_threads = 0) {
         int nt = host_copy_threads();
+        if (max_threads > 0 && nt > max_threads) nt = max_threads;
         if (count < 2 * min_per_thread) nt = 1;
         if ((size_t)nt > count / (min_per_thread ? min_per_thread : 1)) nt = (int)(count / (min_per_thread ? min_per_thread : 1));
         if (nt <= 1) { body((size_t)0, count); return; }
@@ -214,6 +217,13 @@ class TaskPool {
         }
         cv_.notify_one();
     }
+    void submit_front(std::function<void()> f) {                    // ahead of the queued tasks (input staging: the GPU is waiting for it)
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            q_.insert(q_.begin(), std::move(f));
+        }
+        cv_.notify_one();
+    }
 
   private:
     void loop() {
@@ -256,8 +266,20 @@ CopyPool& copy_pool() {
 }
 
 template <typename F>
-void parallel_ranges(size_t count, size_t min_per_thread, F&& body) {
-    copy_pool().run(count, min_per_thread, body);
+void parallel_ranges(size_t count, size_t min_per_thread, F&& body, int max_threads = 0) {
+    copy_pool().run(count, min_per_thread, body, max_threads);
+}
+
+// Threads for staging a chunk's packed input (pageable source -> pinned ring).  The packed records are 1/16 (float32) or 1/32 (float64)
+// of the output bytes, so ONE thread stages a chunk well inside the time its output needs on PCIe -- and more threads are worse than
+// useless: waking a fork-join team for every chunk slowed the whole pipeline down (cfg2, pageable in, pinned out, scripts/prof_api_read2.py:
+// 0.83 s with 1 thread = the pinned-input time, 0.93 s with 2, 1.02 s with 4, 1.07 s with 8-14).  int8 output (input = 1/4 of it) gets 4.
+int stage_threads(size_t in_bytes, size_t out_bytes) {
+    if (getenv("PSTB_HOST_COPY_THREADS")) return host_copy_threads();     // experiments
+    if (out_bytes == 0) return host_copy_threads();
+    const size_t r = (16 * in_bytes + out_bytes / 2) / out_bytes;
+    const int cap = host_copy_threads();
+    return r < 1 ? 1 : (r > (size_t)cap ? cap : (int)r);
 }
 
 size_t esize_of(int dtype) { return dtype == PSTB_F64 ? 8 : (dtype == PSTB_F32 ? 4 : 1); }
@@ -374,7 +396,7 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
 
     struct Pending { int64_t b0 = 0, ns = 0; bool active = false; } pend[kMaxSlots];
     const bool trace = getenv("PSTB_HOST_TRACE") != nullptr;
-    double t_wait = 0.0, t_copy = 0.0, t_enq = 0.0;
+    double t_wait = 0.0, t_copy = 0.0, t_enq = 0.0, t_stage = 0.0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
     // the copy of one staged chunk into the pageable destination (run by a pool worker)
@@ -426,18 +448,88 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         cudaError_t e__ = (x);                                                                   \
         if (e__ != cudaSuccess) { rc = pstb::fail("%s -> %s", #x, cudaGetErrorString(e__)); break; } \
     }
+    // Input staging (records in pageable memory, or a scattered SNP selection: rows -> the slot's pinned ring buffer at pitch ld).  The
+    // ring buffer of a slot is free as soon as the H2D copy of the chunk that used it last is done (event in_done), long before that
+    // chunk's output has left -- so staging never has to wait for finish(slot):
+    //  * pinned destination: the caller stages chunk ch itself, one thread, BEFORE it waits for the slot (it would only be waiting);
+    //  * pageable destination: all cores are busy draining output, the caller alone gets 2.6 GB/s out of the contended memory system
+    //    and became the critical path (0.95 s for cfg2's 2.5 GB) -- the pool workers stage up to kLook chunks ahead instead, their
+    //    tasks queued in front of the drain tasks.
+    auto chunk_of = [&](int64_t ch2, int64_t& b0, int64_t& ns) {
+        b0 = ch2 * chunk;
+        ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
+    };
+    auto is_staged = [&](int64_t b0, int64_t ns) {
+        if (!packed_pinned) return true;
+        for (int64_t k = 1; h_sid_idx && k < ns; ++k)
+            if (h_sid_idx[b0 + k] != h_sid_idx[b0] + k) return true;
+        return false;
+    };
+    auto stage_rows = [&](char* stage, int64_t b0, size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; ++k) {
+            const int64_t j = h_sid_idx ? h_sid_idx[b0 + (int64_t)k] : b0 + (int64_t)k;
+            memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
+        }
+    };
+    bool in_recorded[kMaxSlots] = {}, stage_ready[kMaxSlots] = {};
+    int stage_inflight = 0;                                       // staging tasks not finished yet (guarded by slot_m)
+    const int64_t kLook = nslots - 1 < 4 ? nslots - 1 : 4;
+    int64_t next_stage = 0;
     for (int64_t ch = 0; ch < nchunks && !rc; ++ch) {
         const int slot = (int)(ch % nslots);
-        const int64_t b0 = ch * chunk, ns = (b0 + chunk <= n_sid) ? chunk : n_sid - b0;
+        int64_t b0, ns;
+        chunk_of(ch, b0, ns);
+        cudaStream_t st = c.s[slot % kSlots];
+        // ---- input records ----
+        const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
+        const bool staged_in = is_staged(b0, ns);
+        if (!out_pinned) {
+            const auto ts = now();
+            for (; next_stage <= ch + kLook && next_stage < nchunks && !rc; ++next_stage) {
+                int64_t b2, n2;
+                chunk_of(next_stage, b2, n2);
+                if (!is_staged(b2, n2)) continue;
+                const int s2 = (int)(next_stage % nslots);
+                if (c.h_in[s2].ensure((size_t)chunk * ld)) { rc = 1; break; }
+                {
+                    std::unique_lock<std::mutex> lk(slot_m);
+                    stage_ready[s2] = false;
+                    ++stage_inflight;
+                }
+                char* stage = (char*)c.h_in[s2].p;
+                cudaEvent_t ev = in_recorded[s2] ? c.in_done[s2] : nullptr;
+                task_pool().submit_front([&, s2, b2, n2, stage, ev, cur_dev] {
+                    static thread_local int dev_set = -1;
+                    if (dev_set != cur_dev) { cudaSetDevice(cur_dev); dev_set = cur_dev; }
+                    const cudaError_t e = ev ? cudaEventSynchronize(ev) : cudaSuccess;     // the H2D copy that read this buffer last
+                    if (e != cudaSuccess) worker_rc.store((int)e); else stage_rows(stage, b2, 0, (size_t)n2);
+                    {
+                        std::unique_lock<std::mutex> lk(slot_m);
+                        stage_ready[s2] = true;
+                        --stage_inflight;
+                    }
+                    slot_cv.notify_all();
+                });
+            }
+            if (rc) break;
+            if (staged_in) {
+                std::unique_lock<std::mutex> lk(slot_m);
+                slot_cv.wait(lk, [&] { return stage_ready[slot]; });
+            }
+            t_stage += ms_since(ts);
+        } else if (staged_in) {
+            const auto ts = now();
+            if (c.h_in[slot].ensure((size_t)chunk * ld)) { rc = 1; break; }
+            if (in_recorded[slot]) PSTB_CUDA_BREAK(cudaEventSynchronize(c.in_done[slot]));
+            char* stage = (char*)c.h_in[slot].p;
+            parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) { stage_rows(stage, b0, lo, hi); },
+                            stage_threads((size_t)ns * rec, (size_t)ns * col_bytes));
+            t_stage += ms_since(ts);
+        }
         if ((rc = finish(slot))) break;
         const auto te = now();
         struct EnqTimer { double& acc; std::chrono::steady_clock::time_point t0; ~EnqTimer() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } enq_timer{t_enq, te};
-        cudaStream_t st = c.s[slot % kSlots];
-        // ---- input records ----
-        bool contiguous = true;
-        const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
-        for (int64_t k = 1; h_sid_idx && k < ns && contiguous; ++k) contiguous = h_sid_idx[b0 + k] == j0 + k;
-        if (contiguous && packed_pinned) {
+        if (!staged_in) {
             // one contiguous DMA over PCIe (rows of ceil(N/4) bytes make a slow 2-D copy), then re-pitch to ld on the device
             if (ld == rec) {
                 PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, st));
@@ -448,15 +540,9 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
                                             cudaMemcpyDeviceToDevice, st));
             }
         } else {
-            if (c.h_in[slot].ensure((size_t)chunk * ld)) { rc = 1; break; }
-            char* stage = (char*)c.h_in[slot].p;
-            parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) {
-                for (size_t k = lo; k < hi; ++k) {
-                    const int64_t j = h_sid_idx ? h_sid_idx[b0 + (int64_t)k] : b0 + (int64_t)k;
-                    memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
-                }
-            });
-            PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
+            PSTB_CUDA_BREAK(cudaMemcpyAsync(c.d_packed[slot].p, c.h_in[slot].p, (size_t)ns * ld, cudaMemcpyHostToDevice, st));
+            PSTB_CUDA_BREAK(cudaEventRecord(c.in_done[slot], st));
+            in_recorded[slot] = true;
         }
         // ---- kernel ----
         pstb_axis sid_ax{nullptr, 0, 1, ns};
@@ -498,13 +584,17 @@ extern "C" int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_
         }
     }
 #undef PSTB_CUDA_BREAK
+    {
+        std::unique_lock<std::mutex> lk(slot_m);                    // (an error exit can leave staging tasks behind: they use this frame)
+        slot_cv.wait(lk, [&] { return stage_inflight == 0; });
+    }
     for (int k = 0; k < kMaxSlots; ++k) {
         int r2 = finish(k);
         if (!rc) rc = r2;
     }
     if (trace)
-        fprintf(stderr, "[pstb_read_host] %lld chunks of %lld SNPs, %d slots, %d copy workers: waiting for slots %.1f ms, enqueue %.1f ms\n",
-                (long long)nchunks, (long long)chunk, nslots, host_copy_threads(), t_wait, t_enq);
+        fprintf(stderr, "[pstb_read_host] %lld chunks of %lld SNPs, %d slots, %d copy workers: staging input %.1f ms, waiting for slots %.1f ms, enqueue %.1f ms\n",
+                (long long)nchunks, (long long)chunk, nslots, host_copy_threads(), t_stage, t_wait, t_enq);
     if (rc) {
         cudaDeviceSynchronize();
         return rc;
@@ -728,7 +818,7 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
                     const int64_t j = h_sid_idx ? h_sid_idx[b0 + (int64_t)k] : b0 + (int64_t)k;
                     memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
                 }
-            });
+            }, 4);                                                 // a slice is staged under the previous slice's SYRK (>= 10 ms): four threads are plenty
             e = cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, cp);
         }
         if (e != cudaSuccess) { rc = fail("H2D copy of packed records failed: %s", cudaGetErrorString(e)); break; }

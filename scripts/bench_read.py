@@ -157,3 +157,10 @@ if "feed" in which:
             run("warps=%d ctas=%d" % (warps, ctas), n, stn.sid_count, np.float32, "F", ("unit",), store=stn)
         del stn
     del os.environ["PSTB_READ_WARPS"], os.environ["PSTB_READ_CTAS"]
+if "feed_i8" in which:
+    st2 = rand_store(10000, 1000000)
+    for warps, ctas in ((8, 1), (8, 2), (8, 3), (8, 4), (4, 2), (4, 4), (4, 6)):
+        os.environ["PSTB_READ_WARPS"] = str(warps); os.environ["PSTB_READ_CTAS"] = str(ctas)
+        run("cfg2 int8 decode warps=%d ctas=%d" % (warps, ctas), 10000, 1000000, np.int8, "F", None, store=st2)
+    del os.environ["PSTB_READ_WARPS"], os.environ["PSTB_READ_CTAS"]
+    del st2

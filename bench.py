@@ -353,6 +353,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa_node = None
+    if world > 1 and args.numa_bind:
+        _lib.require_gpu()
+        numa_node = parallel.bind_to_gpu_numa_node(local)         # before NCCL and the pinned buffers: both then live next to the GPU
+    globals()["NUMA_NODE"] = numa_node
     if world > 1:
         # NCCL announces its version on stdout when the communicator is created; the contract is ONE JSON line on stdout,
         # so stdout points at stderr until the first collective has completed
@@ -462,7 +467,9 @@ def run_gpu(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/r2_read_f_full.txt), bytes per launch", "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
-                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+                "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "peak_note": "the measured peak is a torch copy (reads = writes); this kernel writes 94 % of its bytes, and a fraction slightly above 1 is "
+                             "physical: ncu reads 6.67 TB/s = 81.5 % of its own DRAM peak with sm__cycles_active at 99.8 % of elapsed (profiles/r2_read_f_full.txt)"}
 
     # ---- spot parity of the timed configuration against the oracle (not timed) ----
     lib_o = _oracle_lib()
@@ -521,7 +528,9 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg2: synthetic .bed 10000 iids x 1000000 SNPs per GPU, decode + Unit standardize float32, F order",
                        "packed_bytes": n_sid * rec, "out_bytes": 4 * n_iid * n_sid, "l2": "inputs (2.5 GB) and outputs (40 GB) larger than L2; no flush needed",
-                       "sharding": "SNP ranges, one cfg2-sized shard per GPU, no collective"},
+                       "sharding": "SNP ranges, one cfg2-sized shard per GPU, no collective",
+                       "numa": (None if world == 1 else ("rank 0 bound to the CPUs / memory of its GPU's NUMA node {0} (every rank to its own)".format(NUMA_NODE)
+                                                         if NUMA_NODE is not None and NUMA_NODE >= 0 else "no NUMA binding (none exposed by the host, or --no-numa-bind)"))},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "kernel_ms_per_launch": kern_ms, "kernel_ms_best": float(np.min(per_launch)), "kernel_ms_median": float(np.median(per_launch)),
             "parity_spot_check": parity,
@@ -1095,6 +1104,7 @@ def main():
     ap.add_argument("--no-extra-legs", dest="extra_legs", action="store_false", help="skip the cfg4 / C-order / missing-data / cfg5 legs")
     ap.add_argument("--no-api-e2e", dest="api_e2e", action="store_false", help="skip Bed(file).read(dtype=float32, standardizer=Unit()) -> NumPy through the Python layer")
     ap.add_argument("--only-kernel", action="store_true", help="experiments: run only the cfg3 SnpKernel leg and print its object")
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false", help="N > 1: do not bind each rank to the CPUs / memory of its GPU's NUMA node")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--kernel-n", type=int, default=CFG3["n_iid"])
     ap.add_argument("--kernel-m", type=int, default=CFG3["n_sid"])

@@ -58,6 +58,12 @@ int pstb_host_free(void* p);
 /* the `_host` entry points keep their device / staging buffers (chunk ring, workspace, the device copy of K) cached per
  * calling thread so that repeated calls do not pay cudaMalloc / cudaFree; this returns them to the driver. */
 int pstb_host_release(void);
+/* multi-GPU hosts: bind the CALLING thread (and the threads it creates later: this library's copy workers) to the CPUs of the NUMA
+ * node `device` hangs off and prefer that node's memory, so that pinned buffers allocated afterwards and the staging copies stay
+ * local to the GPU's PCIe root.  One process per GPU calls it once before its first `_host` call (the reference has no such notion:
+ * its readers run on whatever cores the OS picks).  Returns the node (>= 0), -1 when the host exposes no NUMA information for the
+ * device (nothing changed), -2 on error (message in pstb_last_error). */
+int pstb_numa_bind(int device);
 
 /* ---- K1: decode  (replaces open_bed(...).read -> Rust read_f32/f64/i8; bed.py:337-343) ------ */
 int pstb_decode(const uint8_t* d_packed, int64_t ld, int64_t iid_count, int64_t sid_count,

@@ -40,6 +40,7 @@ def _load():
         "pstb_host_alloc": (c_void_p, [c_int64]),
         "pstb_host_free": (c_int, [c_void_p]),
         "pstb_host_release": (c_int, []),
+        "pstb_numa_bind": (c_int, [c_int]),
         "pstb_decode": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_void_p, c_int, c_int, c_void_p]),
         "pstb_decode_standardize": (c_int, [c_void_p, c_int64, c_int64, c_int64, Axis, Axis, c_int, c_int, c_double, c_double,
                                             c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),

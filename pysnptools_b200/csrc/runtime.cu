@@ -2,6 +2,12 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include "pstb_common.cuh"
 
 namespace pstb {
@@ -102,6 +108,57 @@ __global__ void k_cluster_probe(int* out) {
     if (out && threadIdx.x == 0 && blockIdx.x == 0x7fffffff) *out = (int)probe_smem[0];
 }
 }  // namespace pstb
+
+// NUMA placement for one-process-per-GPU hosts (include/pst_b200.h).  No libnuma in the image: /sys for the topology,
+// sched_setaffinity + the raw set_mempolicy syscall for the binding.
+extern "C" int pstb_numa_bind(int device) {
+    char bdf[32] = {};
+    if (cudaDeviceGetPCIBusId(bdf, (int)sizeof(bdf), device) != cudaSuccess) {
+        cudaGetLastError();
+        pstb::fail("pstb_numa_bind: no PCI bus id for device %d", device);
+        return -2;
+    }
+    for (char* c = bdf; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    char list[4096] = {};
+    const bool got = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!got) return -1;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) CPU_ZERO(&allowed);
+    int picked = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {       // "0-15,64-79"
+        int a = 0, b = 0;
+        const int n = sscanf(tok, "%d-%d", &a, &b);
+        if (n < 1) continue;
+        if (n == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); ++picked; }
+    }
+    if (picked == 0) return -1;                                  // the node's CPUs are not ours to use (cgroup / container mask)
+    if (sched_setaffinity(0, sizeof(want), &want) != 0) {
+        pstb::fail("pstb_numa_bind: sched_setaffinity to node %d failed", node);
+        return -2;
+    }
+#ifdef SYS_set_mempolicy
+    if (node < 64) {
+        unsigned long mask = 1ul << node;
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul);     // best effort: first touch from the bound CPUs is local anyway
+    }
+#endif
+    return node;
+}
 
 extern "C" int pstb_debug_max_active_clusters(int cluster_size, int threads, int smem_bytes) {
     if (cluster_size < 1 || threads < 1 || smem_bytes < 0) return -1;

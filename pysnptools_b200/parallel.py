@@ -7,6 +7,20 @@ block loop (snpreader.py:651-655) run in parallel -- so the only exchange is the
 import numpy as np
 
 
+def bind_to_gpu_numa_node(device=None):
+    """One process per GPU on a multi-socket host: bind this process' calling thread (and the threads created after it -- the
+    library's copy workers, NCCL's proxies) to the CPUs of the NUMA node the GPU hangs off and prefer that node's memory
+    (``pstb_numa_bind``), so the page-locked buffers of the host-buffer entry points are allocated next to the GPU's PCIe root.
+    Call it before the first read / ``init_process_group``.  Returns the node, or -1 when the host exposes none (nothing changed)."""
+    import torch
+    from . import _lib
+    dev = torch.cuda.current_device() if device is None else int(device)
+    node = int(_lib.lib.pstb_numa_bind(dev))
+    if node == -2:
+        raise RuntimeError(_lib.last_error())
+    return node
+
+
 def shard_range(count, rank, world):
     """Contiguous, balanced [lo, hi) of ``count`` items for ``rank`` of ``world`` (sizes differ by at most 1)."""
     base, extra = divmod(int(count), int(world))

@@ -135,7 +135,7 @@ struct PlaneParams {
 
 __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
     __shared__ unsigned char codes[PT_S][PT_PITCH];
-    __shared__ __half lut_hi[PT_S][4], lut_lo[PT_S][4];
+    __shared__ __align__(8) __half lut_hi[PT_S][4], lut_lo[PT_S][4];
     const long long tiles_i = p.n_pad / PT_I;
     const long long ts = blockIdx.x / tiles_i, ti = blockIdx.x % tiles_i;
     const long long b0 = ts * PT_S, i0 = ti * PT_I;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         codes[s][q] = (unsigned char)byte;
     }
     const bool fast = p.sc->need_3term == 0u;
-    __shared__ __half lut_p2[PT_S][4];
+    __shared__ __align__(8) __half lut_p2[PT_S][4];
     __shared__ __align__(4) unsigned char lut_l8[PT_S][4], lut_h8[PT_S][4];   // fp8 (e4m3) low term and left factor
     __shared__ float lut_u[PT_S][4];
     if (threadIdx.x < PT_S) {
@@ -235,49 +235,57 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         }
     }
     __syncthreads();
-    // each lane owns SNPs 2*lane, 2*lane+1 of the tile; a warp writes 128 contiguous bytes per row and plane
-    __half2 h01[4], l01[4], q01[4];
-    float ua[4], ub[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        h01[c] = __halves2half2(lut_hi[2 * lane][c], lut_hi[2 * lane + 1][c]);
-        l01[c] = __halves2half2(lut_lo[2 * lane][c], lut_lo[2 * lane + 1][c]);
-        q01[c] = __halves2half2(lut_p2[2 * lane][c], lut_p2[2 * lane + 1][c]);
-        ua[c] = lut_u[2 * lane][c];
-        ub[c] = lut_u[2 * lane + 1][c];
-    }
+    // Each lane owns SNPs 2*lane, 2*lane+1 of the tile, each warp 32 consecutive rows; a warp writes 128 contiguous bytes per row and
+    // fp16 plane (64 per fp8 plane).  The loop is instruction-bound (four small stores per row), so the table look-ups are byte
+    // permutes -- the four fp16 values of a SNP live in two registers and PRMT picks the pair of bytes of code c (selector
+    // 0x10 + 0x22 c); the four fp8 values live in one, and ONE PRMT picks both SNPs' bytes -- and four rows share one code byte.
+    const int sa = 2 * lane, sb = 2 * lane + 1;
+    auto word_of = [](const __half* h) { return *reinterpret_cast<const uint32_t*>(h); };
+    const uint32_t hiA01 = word_of(&lut_hi[sa][0]), hiA23 = word_of(&lut_hi[sa][2]), hiB01 = word_of(&lut_hi[sb][0]), hiB23 = word_of(&lut_hi[sb][2]);
+    const uint32_t loA01 = word_of(&lut_lo[sa][0]), loA23 = word_of(&lut_lo[sa][2]), loB01 = word_of(&lut_lo[sb][0]), loB23 = word_of(&lut_lo[sb][2]);
+    const uint32_t p2A01 = word_of(&lut_p2[sa][0]), p2A23 = word_of(&lut_p2[sa][2]), p2B01 = word_of(&lut_p2[sb][0]), p2B23 = word_of(&lut_p2[sb][2]);
     // the four fp8 table values of a SNP packed in one word: byte `code`
-    const uint32_t l8a = *reinterpret_cast<const uint32_t*>(lut_l8[2 * lane]), l8b = *reinterpret_cast<const uint32_t*>(lut_l8[2 * lane + 1]);
-    const uint32_t h8a = *reinterpret_cast<const uint32_t*>(lut_h8[2 * lane]), h8b = *reinterpret_cast<const uint32_t*>(lut_h8[2 * lane + 1]);
-    const unsigned char* c0 = codes[2 * lane];
-    const unsigned char* c1 = codes[2 * lane + 1];
-    auto sel = [](const __half2 (&t)[4], uint32_t ca, uint32_t cb) {
-        const __half2 x = (ca & 2u) ? ((ca & 1u) ? t[3] : t[2]) : ((ca & 1u) ? t[1] : t[0]);
-        const __half2 y = (cb & 2u) ? ((cb & 1u) ? t[3] : t[2]) : ((cb & 1u) ? t[1] : t[0]);
-        return __halves2half2(__low2half(x), __high2half(y));
+    const uint32_t l8a = *reinterpret_cast<const uint32_t*>(lut_l8[sa]), l8b = *reinterpret_cast<const uint32_t*>(lut_l8[sb]);
+    const uint32_t h8a = *reinterpret_cast<const uint32_t*>(lut_h8[sa]), h8b = *reinterpret_cast<const uint32_t*>(lut_h8[sb]);
+    const unsigned char* c0 = codes[sa];
+    const unsigned char* c1 = codes[sb];
+    auto pick2 = [](uint32_t a01, uint32_t a23, uint32_t b01, uint32_t b23, uint32_t sel_a, uint32_t sel_b) {
+        return __byte_perm(__byte_perm(a01, a23, sel_a), __byte_perm(b01, b23, sel_b), 0x5410);     // {SNP a, SNP b} as fp16 x 2
     };
-    for (int r = warp; r < PT_I; r += 8) {
-        const uint32_t ca = ((uint32_t)c0[r >> 2] >> (2 * (r & 3))) & 3u, cb = ((uint32_t)c1[r >> 2] >> (2 * (r & 3))) & 3u;
-        const long long off = (i0 + r) * p.k_pad + b0 + 2 * lane;
-        *reinterpret_cast<__half2*>(p.hi + off) = sel(h01, ca, cb);
-        *reinterpret_cast<__half2*>(p.lo + off) = sel(l01, ca, cb);
-        if (fast) {
-            // plane 2 may be shared with a second operand stacked above / below this one (train x test): its own row offset
-            const long long offp = (p.p2_row0 + i0 + r) * p.k_pad + b0 + 2 * lane;
-            if (p.fp8lo) {
-                unsigned char* l8 = reinterpret_cast<unsigned char*>(p.p2);
-                unsigned char* h8 = l8 + (p.p2_rows ? p.p2_rows : p.n_pad) * p.k_pad;
-                *reinterpret_cast<uint16_t*>(l8 + offp) = (uint16_t)(((l8a >> (8 * ca)) & 0xffu) | (((l8b >> (8 * cb)) & 0xffu) << 8));
-                *reinterpret_cast<uint16_t*>(h8 + offp) = (uint16_t)(((h8a >> (8 * ca)) & 0xffu) | (((h8b >> (8 * cb)) & 0xffu) << 8));
-            } else {
-                *reinterpret_cast<__half2*>(p.p2 + offp) = sel(q01, ca, cb);
-            }
-            float uv = ((ca & 2u) ? ((ca & 1u) ? ua[3] : ua[2]) : ((ca & 1u) ? ua[1] : ua[0])) +
-                       ((cb & 2u) ? ((cb & 1u) ? ub[3] : ub[2]) : ((cb & 1u) ? ub[1] : ub[0]));
+    unsigned char* const l8 = reinterpret_cast<unsigned char*>(p.p2);
+    unsigned char* const h8 = l8 + (p.p2_rows ? p.p2_rows : p.n_pad) * p.k_pad;
+    for (int g = 0; g < 8; ++g) {
+        const int rbase = warp * 32 + g * 4;
+        const uint32_t byte_a = c0[rbase >> 2], byte_b = c1[rbase >> 2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) uv += __shfl_xor_sync(0xffffffffu, uv, o);
-            if (lane == 0 && uv != 0.0f && i0 + r < n_out && p.u) atomicAdd(p.u + i0 + r, (double)uv);
+        for (int t = 0; t < 4; ++t) {
+            const int r = rbase + t;
+            const uint32_t ca = (byte_a >> (2 * t)) & 3u, cb = (byte_b >> (2 * t)) & 3u;
+            const uint32_t sel_a = 0x10u + 0x22u * ca, sel_b = 0x10u + 0x22u * cb;
+            const long long off = (i0 + r) * p.k_pad + b0 + 2 * lane;
+            *reinterpret_cast<uint32_t*>(p.hi + off) = pick2(hiA01, hiA23, hiB01, hiB23, sel_a, sel_b);
+            *reinterpret_cast<uint32_t*>(p.lo + off) = pick2(loA01, loA23, loB01, loB23, sel_a, sel_b);
+            if (fast) {
+                // plane 2 may be shared with a second operand stacked above / below this one (train x test): its own row offset
+                const long long offp = (p.p2_row0 + i0 + r) * p.k_pad + b0 + 2 * lane;
+                if (p.fp8lo) {
+                    const uint32_t sel8 = ca | ((cb + 4u) << 4);                                    // byte ca of the first word, byte cb of the second
+                    *reinterpret_cast<uint16_t*>(l8 + offp) = (uint16_t)__byte_perm(l8a, l8b, sel8);
+                    *reinterpret_cast<uint16_t*>(h8 + offp) = (uint16_t)__byte_perm(h8a, h8b, sel8);
+                } else {
+                    *reinterpret_cast<uint32_t*>(p.p2 + offp) = pick2(p2A01, p2A23, p2B01, p2B23, sel_a, sel_b);
+                }
+            }
         }
+    }
+    // rank-one vector: one thread per row of the tile sums its 64 SNPs' table values (no cross-lane reduction; the table reads are
+    // broadcasts -- a warp reads one SNP's four entries -- and the code bytes of 32 rows are 8 adjacent bytes)
+    if (fast && p.u) {
+        const int r = threadIdx.x;                                      // blockDim.x == PT_I
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int sn = 0; sn < PT_S; ++sn) acc += lut_u[sn][((uint32_t)codes[sn][r >> 2] >> (2 * (r & 3))) & 3u];
+        if (acc != 0.0f && i0 + r < n_out) atomicAdd(p.u + i0 + r, (double)acc);
     }
 }
 

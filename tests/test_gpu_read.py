@@ -476,3 +476,31 @@ def test_dynamic_record_feed(n, m, oracle, dev):
                     val2, _ = dev.read(store, ii, si, dtype=dtype, order="F", standardizer=std, stats=st)
                     assert np.array_equal(_np(val2), _np(val))                              # trained statistics: the same table, the same bits
     assert _lib.lib.pstb_launch_count() > before
+
+
+@pytest.mark.parametrize("n,m,gather", [(4104, 6000, False), (10000, 2600, False), (300, 40000, False), (30001, 700, False), (10000, 1500, True),
+                                        (2049, 3000, True)])
+def test_dynamic_record_feed_more_records_than_groups(n, m, gather, oracle, dev):
+    """Several claims per warp / CTA: more SNP records than the launch has resident groups (1 184 warps, 296 or 148 CTAs), on the
+    warp-per-record (8 x 1 and 4 x 2 CTAs per SM), short-record, CTA-per-record and gathered (batches of four) kernels, plus the
+    statistics-only pass behind a C-order read -- every column written once, from the right record, with the right statistics."""
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + m)
+    store = dev.PackedStore.from_host(packed, n)
+    ii = np.random.default_rng(m).permutation(n)[: n // 2].astype(np.int64) if gather else None
+    raw = oracle.decode(packed, n, ii, None)
+    for dtype in (np.float32, np.int8) if not gather else (np.float32,):
+        val, _ = dev.read(store, ii, None, dtype=dtype, order="F")
+        want = oracle.decode(packed, n, ii, None, False, dtype, "F")
+        assert np.array_equal(_np(val), want, equal_nan=dtype != np.int8), (n, m, dtype)
+    ref, rst = oracle.standardize(raw, False, np.nan, np.nan)
+    for order in ("F", "C"):
+        val, st = dev.read(store, ii, None, dtype=np.float32, order=order, standardizer=("unit",))
+        np.testing.assert_allclose(_np(st), rst, rtol=1e-12)
+        np.testing.assert_allclose(_np(val), ref, rtol=STD_RTOL, atol=1e-6)
+    # K2f on the decoded matrix (k_std_f_staged hands its columns out the same way)
+    import torch
+    x = torch.from_numpy(np.ascontiguousarray(raw.astype(np.float32).T)).cuda().t()          # [n, m], F-contiguous on the device
+    st2 = dev.standardize(x, ("unit",))
+    fin = np.isfinite(rst).all(axis=1)
+    np.testing.assert_allclose(_np(st2)[fin], rst[fin], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_np(x)[:, fin], ref[:, fin], rtol=1e-5, atol=1e-5)

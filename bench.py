@@ -469,7 +469,7 @@ def run_gpu(args):
                 "traffic": traffic, "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/r2_read_f_full.txt), bytes per launch", "kernel": "k_read_f<float,warp> (fused decode+stats+standardize)",
                 "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "peak_note": "the measured peak is a torch copy (reads = writes); this kernel writes 94 % of its bytes, and a fraction slightly above 1 is "
-                             "physical: ncu reads 6.67 TB/s = 81.5 % of its own DRAM peak with sm__cycles_active at 99.8 % of elapsed (profiles/r2_read_f_full.txt)"}
+                             "physical: ncu reads 6.58-6.67 TB/s = 80-82 % of its own DRAM peak with sm__cycles_active at 99.8 % of elapsed (profiles/r2_read_f_full.txt)"}
 
     # ---- spot parity of the timed configuration against the oracle (not timed) ----
     lib_o = _oracle_lib()

@@ -171,6 +171,9 @@ int pstb_kernel_from_tiles_range(const float* d_tiles, int64_t n_iid, int rank, 
  * it to the tiles; pstb_kernel_workspace_rank1 returns its address.  The caller sums the vectors of its calls, all-reduces the total
  * with the tiles (n_iid doubles) and passes it as d_u to pstb_kernel_from_tiles_range, which adds it while expanding (NULL: nothing). */
 double* pstb_kernel_workspace_rank1(void* d_work, int64_t n_iid, int64_t chunk);
+/* PSTB_LOW_TERM_DEFAULT / _AUTO resolved for a kernel of `total_sid` SNPs (returns PSTB_LOW_TERM_FP16 or _FP8): a caller that splits one
+ * kernel over several calls resolves the mode once and passes the explicit value to each. */
+int pstb_resolve_low_term(int low_term, int64_t total_sid, int64_t n_iid, int mode);
 /* Train x test kernel (what FaST-LMM builds from SnpKernel + the *Trained standardizers: unittrained.py:47-70,
  * betatrained.py:47-63 applied to a second iid set, then train.val.dot(test.val.T)):
  *   d_out [n_r, n_c] float32, C order (ld = n_c):  out[i, k] (+)= sum_j x_ij y_kj

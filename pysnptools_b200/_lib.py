@@ -61,6 +61,7 @@ def _load():
                                                c_void_p]),
         "pstb_kernel_from_tiles_range": (c_int, [c_void_p, c_int64, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
         "pstb_kernel_workspace_rank1": (c_void_p, [c_void_p, c_int64, c_int64]),
+        "pstb_resolve_low_term": (c_int, [c_int, c_int64, c_int64, c_int]),
         "pstb_set_syrk_low_term": (c_int, [c_int]),
         "pstb_kernel_from_tiles": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
         "pstb_cross_kernel_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),

@@ -57,6 +57,8 @@ struct HostCtx {
     cudaStream_t s[kSlots] = {};
     cudaEvent_t done[kMaxSlots] = {}, in_done[kMaxSlots] = {};
     Buf d_packed[kMaxSlots], d_tight[kMaxSlots], d_out[kMaxSlots], d_stats, d_idx, d_work, d_K, h_in[kMaxSlots], h_out[kMaxSlots];
+    Buf d_tiles, d_tail_work, d_tail_packed, d_u;           // pstb_snp_kernel_host with the copy-out of K overlapped (compact tiles, band-major tail)
+    cudaStream_t hp = nullptr;                             // high priority: the expansion of finished bands runs between the SYRK launches
     cudaEvent_t copied[2] = {}, used[2] = {};
     HostCtx() {
         for (int k = 0; k < kMaxSlots; ++k) { h_in[k].host = true; h_out[k].host = true; }
@@ -64,6 +66,7 @@ struct HostCtx {
     void release_buffers() {
         for (int k = 0; k < kMaxSlots; ++k) { d_packed[k].release(); d_tight[k].release(); d_out[k].release(); h_in[k].release(); h_out[k].release(); }
         d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
+        d_tiles.release(); d_tail_work.release(); d_tail_packed.release(); d_u.release();
     }
     int init() {
         int dev = 0;
@@ -81,6 +84,13 @@ struct HostCtx {
             PSTB_CUDA(cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking));
         }
         d_stats.release(); d_idx.release(); d_work.release(); d_K.release();
+        d_tiles.release(); d_tail_work.release(); d_tail_packed.release(); d_u.release();
+        if (hp) cudaStreamDestroy(hp);
+        {
+            int lo_prio = 0, hi_prio = 0;
+            PSTB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            PSTB_CUDA(cudaStreamCreateWithPriority(&hp, cudaStreamNonBlocking, hi_prio));
+        }
         for (int k = 0; k < 2; ++k) {
             if (copied[k]) cudaEventDestroy(copied[k]);
             if (used[k]) cudaEventDestroy(used[k]);
@@ -322,6 +332,12 @@ int make_axis(const int64_t* h_idx, int64_t n, int64_t count, const char* name, 
 }  // namespace pstb
 
 using namespace pstb;
+
+// d_acc[i] += d_x[i]: the deferred rank-one vectors of the calls of one overlapped kernel
+__global__ void k_add_f64(double* acc, const double* x, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += x[i];
+}
 
 
 // Host -> device upload that is COMPLETE when it returns: cudaMemcpyAsync on one of the context's (non-blocking) streams followed by a
@@ -776,6 +792,7 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     int rc = 0;
     auto cleanup = [&](int r) {
         for (int k = 0; k < 3; ++k) cudaStreamSynchronize(c.s[k]);
+        if (c.hp) cudaStreamSynchronize(c.hp);
         return r;
     };
     if (d_K.ensure(kbytes32) || c.d_work.ensure((size_t)work_bytes) || c.d_stats.ensure((size_t)(n_sid > 0 ? n_sid : 1) * 2 * sizeof(double)))
@@ -787,30 +804,26 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     if (n_sid == 0 && cudaMemsetAsync(d_K.p, 0, kbytes32, comp) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
     const bool packed_pinned = n_sid > 0 && is_pinned(h_packed);
     bool used_pending[2] = {false, false};
-    for (int64_t b0 = 0, sl = 0; b0 < n_sid && !rc; b0 += slice, ++sl) {
-        const int slot = (int)(sl & 1);
-        const int64_t ns = (b0 + slice <= n_sid) ? slice : n_sid - b0;
+    // records [b0, b0 + ns) of the selection -> d_dst (pitch ld) on copy stream c.s[1 + slot]; the copy is recorded in copied[slot]
+    auto upload_records = [&](int64_t b0, int64_t ns, void* d_dst, int slot) -> int {
         cudaStream_t cp = c.s[1 + slot];
-        if (c.d_packed[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
-        if (used_pending[slot] && cudaStreamWaitEvent(cp, used[slot], 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
         bool contiguous = true;
         const int64_t j0 = h_sid_idx ? h_sid_idx[b0] : b0;
         for (int64_t k = 1; h_sid_idx && k < ns && contiguous; ++k) contiguous = h_sid_idx[b0 + k] == j0 + k;
         cudaError_t e = cudaSuccess;
         if (contiguous && packed_pinned) {
             if (ld == rec) {
-                e = cudaMemcpyAsync(c.d_packed[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, cp);
+                e = cudaMemcpyAsync(d_dst, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, cp);
             } else {
-                if (c.d_tight[slot].ensure((size_t)slice * rec)) { rc = 1; break; }
+                if (c.d_tight[slot].ensure((size_t)(ns > slice ? ns : slice) * rec)) return 1;
                 e = cudaMemcpyAsync(c.d_tight[slot].p, h_packed + (size_t)j0 * rec, (size_t)ns * rec, cudaMemcpyHostToDevice, cp);
                 if (e == cudaSuccess)
-                    e = cudaMemcpy2DAsync(c.d_packed[slot].p, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns,
-                                          cudaMemcpyDeviceToDevice, cp);
+                    e = cudaMemcpy2DAsync(d_dst, (size_t)ld, c.d_tight[slot].p, (size_t)rec, (size_t)rec, (size_t)ns, cudaMemcpyDeviceToDevice, cp);
             }
         } else {
             // pageable or scattered records: gather them into a pinned staging buffer with host threads (the buffer is free once
             // the previous copy from it has finished)
-            if (c.h_in[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
+            if (c.h_in[slot].ensure((size_t)(ns > slice ? ns : slice) * ld)) return 1;
             if (used_pending[slot]) cudaEventSynchronize(copied[slot]);
             char* stage = (char*)c.h_in[slot].p;
             parallel_ranges((size_t)ns, 64, [&](size_t lo, size_t hi) {
@@ -819,28 +832,14 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
                     memcpy(stage + k * (size_t)ld, h_packed + (size_t)j * rec, (size_t)rec);
                 }
             }, 4);                                                 // a slice is staged under the previous slice's SYRK (>= 10 ms): four threads are plenty
-            e = cudaMemcpyAsync(c.d_packed[slot].p, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, cp);
+            e = cudaMemcpyAsync(d_dst, stage, (size_t)ns * ld, cudaMemcpyHostToDevice, cp);
         }
-        if (e != cudaSuccess) { rc = fail("H2D copy of packed records failed: %s", cudaGetErrorString(e)); break; }
-        if (cudaEventRecord(copied[slot], cp) != cudaSuccess || cudaStreamWaitEvent(comp, copied[slot], 0) != cudaSuccess) {
-            rc = fail("event record / wait failed");
-            break;
-        }
-        pstb_axis sid_ax{nullptr, 0, 1, ns};
-        if (exact)
-            rc = snp_kernel_f64_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
-                                      (double*)c.d_stats.p + 2 * b0, (double*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp);
-        else
-            rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
-                                  (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, low_term, comp,
-                                  (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
-        if (rc) break;
-        if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
-        used_pending[slot] = true;
-    }
-    if (rc) return cleanup(rc);
-    mark("slices enqueued");
-    if (exact ? pstb_mirror_lower_f64((double*)d_K.p, n_iid, n_iid, comp) : pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
+        if (e != cudaSuccess) return fail("H2D copy of packed records failed: %s", cudaGetErrorString(e));
+        if (cudaEventRecord(copied[slot], cp) != cudaSuccess) return fail("cudaEventRecord failed");
+        used_pending[slot] = true;                                  // (the staging buffer / d_tight of this slot are in use until copied[slot])
+        return 0;
+    };
+
     // ---- K back to the host: row bands, converted on the device, D2H overlapped with the next band's conversion ----
     // pinned destination: 2 slots of 128 MiB straight into it; pageable one: up to 16 slots of 32 MiB, each drained by one worker of
     // the calling thread's task pool (as in pstb_read_host)
@@ -850,9 +849,7 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     int64_t band = (int64_t)(((size_t)(out_pinned ? 128 : 32) << 20) / row_bytes);
     if (band < 1) band = 1;
     if (band > n_iid) band = n_iid;
-    if (cudaStreamSynchronize(comp) != cudaSuccess) return cleanup(fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
-    mark("kernel finished");
-    struct Pend { int64_t r0 = 0, nr = 0; bool active = false; } pend[kMaxSlots];
+    struct Pend { bool active = false; } pend[kMaxSlots];
     std::mutex slot_m;
     std::condition_variable slot_cv;
     bool slot_busy[kMaxSlots] = {};
@@ -860,6 +857,7 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (!out_pinned) task_pool().ensure(host_copy_threads());
+    int64_t drain_seq = 0;
     auto finish = [&](int slot) -> int {
         if (!pend[slot].active) return 0;
         pend[slot].active = false;
@@ -871,59 +869,214 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
         if (cudaEventSynchronize(c.done[slot]) != cudaSuccess) return fail("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 0;
     };
-    for (int64_t r0 = 0, bi = 0; r0 < n_iid && !rc; r0 += band, ++bi) {
-        const int slot = (int)(bi % nsl);
-        const int64_t nr = (r0 + band <= n_iid) ? band : n_iid - r0;
-        if ((rc = finish(slot))) break;
-        cudaStream_t st = c.s[slot % 2];
-        const float* src = (const float*)d_K.p + (size_t)r0 * n_iid;
-        const void* from = src;
-        if (exact) {
-            from = (const double*)d_K.p + (size_t)r0 * n_iid;           // already float64: straight D2H
-        } else if (dtype == PSTB_F64) {
-            if (c.d_out[slot].ensure((size_t)band * row_bytes)) { rc = 1; break; }
-            if ((rc = convert_range(src, (long long)nr * n_iid, c.d_out[slot].p, dtype, 1.0, st))) break;
-            from = c.d_out[slot].p;
-        }
-        void* dst = (char*)h_K + (size_t)r0 * row_bytes;
-        if (!out_pinned) {
-            if (c.h_out[slot].ensure((size_t)band * row_bytes)) { rc = 1; break; }
-            dst = c.h_out[slot].p;
-        }
-        if (cudaMemcpyAsync(dst, from, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaEventRecord(c.done[slot], st) != cudaSuccess) {
-            rc = fail("D2H copy of K failed");
-            break;
-        }
-        pend[slot].r0 = r0;
-        pend[slot].nr = nr;
-        pend[slot].active = true;
-        if (!out_pinned) {
-            {
-                std::unique_lock<std::mutex> lk(slot_m);
-                slot_busy[slot] = true;
+    // rows [ra, rb) of the finished device K -> the host.  `after` (may be NULL): the event that makes these rows final; `side`:
+    // copy on streams 1 / 2 only (the compute stream is still busy with other rows)
+    auto drain_rows = [&](int64_t ra, int64_t rb, cudaEvent_t after, bool side) -> int {
+        for (int64_t r0 = ra; r0 < rb; r0 += band, ++drain_seq) {
+            const int slot = (int)(drain_seq % nsl);
+            const int64_t nr = (r0 + band <= rb) ? band : rb - r0;
+            if (int r = finish(slot)) return r;
+            cudaStream_t st = side ? c.s[1 + slot % 2] : c.s[slot % 2];
+            if (after && cudaStreamWaitEvent(st, after, 0) != cudaSuccess) return fail("cudaStreamWaitEvent failed");
+            const float* src = (const float*)d_K.p + (size_t)r0 * n_iid;
+            const void* from = src;
+            if (exact) {
+                from = (const double*)d_K.p + (size_t)r0 * n_iid;           // already float64: straight D2H
+            } else if (dtype == PSTB_F64) {
+                if (c.d_out[slot].ensure((size_t)band * row_bytes)) return 1;
+                if (int r = convert_range(src, (long long)nr * n_iid, c.d_out[slot].p, dtype, 1.0, st)) return r;
+                from = c.d_out[slot].p;
             }
-            cudaEvent_t ev = c.done[slot];
-            const char* stage = (const char*)c.h_out[slot].p;
-            char* dest = (char*)h_K + (size_t)r0 * row_bytes;
-            const size_t bytes = (size_t)nr * row_bytes;
-            task_pool().submit([&, slot, ev, stage, dest, bytes, cur_dev] {
-                static thread_local int dev_set = -1;
-                if (dev_set != cur_dev) { cudaSetDevice(cur_dev); dev_set = cur_dev; }
-                const cudaError_t e = cudaEventSynchronize(ev);
-                if (e != cudaSuccess) worker_rc.store((int)e); else memcpy(dest, stage, bytes);
+            void* dst = (char*)h_K + (size_t)r0 * row_bytes;
+            if (!out_pinned) {
+                if (c.h_out[slot].ensure((size_t)band * row_bytes)) return 1;
+                dst = c.h_out[slot].p;
+            }
+            if (cudaMemcpyAsync(dst, from, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaEventRecord(c.done[slot], st) != cudaSuccess)
+                return fail("D2H copy of K failed");
+            pend[slot].active = true;
+            if (!out_pinned) {
                 {
                     std::unique_lock<std::mutex> lk(slot_m);
-                    slot_busy[slot] = false;
+                    slot_busy[slot] = true;
                 }
-                slot_cv.notify_all();
-            });
+                cudaEvent_t ev = c.done[slot];
+                const char* stage = (const char*)c.h_out[slot].p;
+                char* dest = (char*)h_K + (size_t)r0 * row_bytes;
+                const size_t bytes = (size_t)nr * row_bytes;
+                task_pool().submit([&, slot, ev, stage, dest, bytes, cur_dev] {
+                    static thread_local int dev_set = -1;
+                    if (dev_set != cur_dev) { cudaSetDevice(cur_dev); dev_set = cur_dev; }
+                    const cudaError_t e = cudaEventSynchronize(ev);
+                    if (e != cudaSuccess) worker_rc.store((int)e); else memcpy(dest, stage, bytes);
+                    {
+                        std::unique_lock<std::mutex> lk(slot_m);
+                        slot_busy[slot] = false;
+                    }
+                    slot_cv.notify_all();
+                });
+            }
         }
+        return 0;
+    };
+    auto finish_all = [&](int r) -> int {                           // no worker may outlive this frame, whatever happened
+        for (int k = 0; k < kMaxSlots; ++k) {
+            const int r2 = finish(k);
+            if (!r) r = r2;
+        }
+        return r;
+    };
+
+    // ---- K final only after the last SNP chunk: its 10 GB (cfg3) left over PCIe AFTER the multiplication, 0.18 s of a 1.9 s call.
+    // Overlapped copy-out: K accumulates in compact lower-triangular tiles; the last T chunks (as many as the copy-out takes) are
+    // multiplied BAND-major, from the bottom band of tiles up: once a band's tiles are final and expanded (both orientations + the
+    // rank-one part), the rows of the square K below its first tile row are complete and leave while the bands above still multiply.
+    const int64_t nchunks = (n_sid + chunk - 1) / chunk;
+    const int64_t ntiles = pstb_kernel_tile_count(n_iid, 0, 1);
+    int overlap_mode = 1;
+    if (const char* e = getenv("PSTB_HOST_KERNEL_OVERLAP")) overlap_mode = atoi(e);     // 0: off, 1: large kernels, 2: whenever possible (tests)
+    bool overlap = !exact && overlap_mode > 0 && nchunks >= 2 && ntiles >= 3 && n_iid >= 512 &&
+                   (overlap_mode >= 2 || (n_iid >= 8192 && nchunks >= 8));
+    if (overlap) {
+        // tail length: the copy-out moves n^2 * es bytes at ~50 GB/s (a fresh pageable destination takes them at ~35: first-touch page
+        // faults), a chunk multiplies 2 n^2 chunk flop at ~1.45e15/s
+        int64_t T = (int64_t)((double)es * (out_pinned ? 14500.0 : 21000.0) / (double)chunk) + 1;
+        if (T > 24) T = 24;
+        while (T > 1 && (size_t)T * (size_t)work_bytes > ((size_t)32 << 30)) --T;
+        if (T > nchunks) T = nchunks;
+        const int64_t head = (nchunks - T) * chunk;                // SNPs multiplied chunk-major, slice by slice
+        const int low = pstb_resolve_low_term(low_term, n_sid, n_iid, mode);
+        const size_t n_pad2 = ((size_t)n_iid + 255) / 256 * 256 + 2;
+        if (c.d_tiles.ensure((size_t)ntiles * 65536 * sizeof(float)) || c.d_tail_work.ensure((size_t)T * (size_t)work_bytes) ||
+            c.d_tail_packed.ensure((size_t)T * (size_t)chunk * (size_t)ld) || c.d_u.ensure(n_pad2 * sizeof(double)))
+            return cleanup(1);
+        // bands: cuts of the tile list where every later tile lies in a lower tile row than every earlier one
+        std::vector<int32_t> ij((size_t)ntiles * 2);
+        if (pstb_kernel_tile_coords(n_iid, 0, 1, ij.data())) return cleanup(1);
+        std::vector<int32_t> sufmin((size_t)ntiles + 1, INT32_MAX);
+        for (int64_t t = ntiles - 1; t >= 0; --t) sufmin[(size_t)t] = ij[(size_t)2 * t] < sufmin[(size_t)t + 1] ? ij[(size_t)2 * t] : sufmin[(size_t)t + 1];
+        std::vector<int64_t> cuts;                                   // band starts, ascending; cuts[0] = 0
+        cuts.push_back(0);
+        {
+            const int64_t want = ntiles / 12 > 1 ? ntiles / 12 : 1;
+            int32_t premax = -1;
+            for (int64_t t = 1; t < ntiles; ++t) {
+                premax = ij[(size_t)2 * (t - 1)] > premax ? ij[(size_t)2 * (t - 1)] : premax;
+                if (premax < sufmin[(size_t)t] && t - cuts.back() >= want) cuts.push_back(t);
+            }
+        }
+        cuts.push_back(ntiles);
+        const int nbands = (int)cuts.size() - 1;
+        std::vector<cudaEvent_t> ev_band((size_t)nbands, nullptr), ev_exp((size_t)nbands, nullptr);
+        auto destroy_events = [&]() {
+            for (auto& e : ev_band) if (e) cudaEventDestroy(e);
+            for (auto& e : ev_exp) if (e) cudaEventDestroy(e);
+        };
+        double* d_u = (double*)c.d_u.p;
+        if (cudaMemsetAsync(d_u, 0, n_pad2 * sizeof(double), comp) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+        auto add_rank1 = [&](void* work) -> int {
+            const double* u = pstb_kernel_workspace_rank1(work, n_iid, chunk);
+            if (!u) return fail("no rank-one vector in the workspace");
+            k_add_f64<<<(unsigned)((n_iid + 255) / 256), 256, 0, comp>>>(d_u, u, (long long)n_iid);
+            return cudaGetLastError() == cudaSuccess ? 0 : fail("k_add_f64 launch failed");
+        };
+        // the tail's records first (one short copy), then the head slice by slice as in the plain loop
+        const int64_t tail_sid = n_sid - head;
+        for (int64_t b0 = head, piece = 0; b0 < n_sid && !rc; b0 += slice, ++piece) {
+            const int64_t ns = (b0 + slice <= n_sid) ? slice : n_sid - b0;
+            rc = upload_records(b0, ns, (char*)c.d_tail_packed.p + (size_t)(b0 - head) * ld, (int)(piece & 1));
+        }
+        if (rc) return cleanup(rc);
+        cudaEvent_t tail_copied[2] = {copied[0], copied[1]};
+        for (int k = 0; k < 2; ++k)
+            if (used_pending[k] && cudaStreamWaitEvent(comp, tail_copied[k], 0) != cudaSuccess) return cleanup(fail("cudaStreamWaitEvent failed"));
+        for (int64_t b0 = 0, sl = 0; b0 < head && !rc; b0 += slice, ++sl) {
+            const int slot = (int)(sl & 1);
+            const int64_t ns = (b0 + slice <= head) ? slice : head - b0;
+            if (c.d_packed[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
+            if (used_pending[slot] && cudaStreamWaitEvent(c.s[1 + slot], used[slot], 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+            if ((rc = upload_records(b0, ns, c.d_packed[slot].p, slot))) break;
+            if (cudaStreamWaitEvent(comp, copied[slot], 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+            pstb_axis sid_ax{nullptr, 0, 1, ns};
+            rc = pstb_snp_kernel_tiles((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                                       (double*)c.d_stats.p + 2 * b0, (float*)c.d_tiles.p, 0, 1, (b0 > 0 ? 1 : 0) | 2, c.d_work.p, work_bytes, chunk, low, comp);
+            if (rc || (rc = add_rank1(c.d_work.p))) break;
+            if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
+        }
+        if (rc) return cleanup(rc);
+        mark("head enqueued");
+        auto band_call = [&](int64_t tc, int64_t t0, int64_t t1, int flags) -> int {
+            const int64_t lo = tc * chunk, ns = (lo + chunk <= tail_sid) ? chunk : tail_sid - lo;
+            pstb_axis sid_ax{nullptr, 0, 1, ns};
+            return pstb_snp_kernel_tiles_band((const uint8_t*)c.d_tail_packed.p + (size_t)lo * ld, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b,
+                                              use_stats, (double*)c.d_stats.p + 2 * (head + lo), (float*)c.d_tiles.p, 0, 1, (head > 0 || tc > 0) ? 1 : 0,
+                                              (char*)c.d_tail_work.p + (size_t)tc * (size_t)work_bytes, work_bytes, chunk, low, t0, t1, flags, 0, comp);
+        };
+        for (int64_t tc = 0; tc < T && !rc; ++tc) {                 // statistics + operand planes of the tail chunks, no tiles yet
+            if ((rc = band_call(tc, 0, 0, 1 | 2))) break;
+            rc = add_rank1((char*)c.d_tail_work.p + (size_t)tc * (size_t)work_bytes);
+        }
+        // every band's multiplication and expansion is enqueued first (the copy-out below blocks the caller on its staging slots)
+        for (int bnd = nbands - 1; bnd >= 0 && !rc; --bnd) {
+            const int64_t t0 = cuts[(size_t)bnd], t1 = cuts[(size_t)bnd + 1];
+            for (int64_t tc = 0; tc < T && !rc; ++tc) rc = band_call(tc, t0, t1, 2);
+            if (rc) break;
+            if (cudaEventCreateWithFlags(&ev_band[(size_t)bnd], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_exp[(size_t)bnd], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventRecord(ev_band[(size_t)bnd], comp) != cudaSuccess || cudaStreamWaitEvent(c.hp, ev_band[(size_t)bnd], 0) != cudaSuccess) {
+                rc = fail("band event failed");
+                break;
+            }
+            if ((rc = pstb_kernel_from_tiles_range((const float*)c.d_tiles.p, n_iid, 0, 1, t0, t1, (float*)d_K.p, d_u, c.hp))) break;
+            if (cudaEventRecord(ev_exp[(size_t)bnd], c.hp) != cudaSuccess) rc = fail("cudaEventRecord failed");
+        }
+        mark("tail enqueued");
+        int64_t row_hi = n_iid;
+        for (int bnd = nbands - 1; bnd >= 0 && !rc; --bnd) {
+            int64_t row_lo = bnd == 0 ? 0 : (int64_t)sufmin[(size_t)cuts[(size_t)bnd]] * 256;
+            if (row_lo > n_iid) row_lo = n_iid;
+            if (row_lo < row_hi) {
+                rc = drain_rows(row_lo, row_hi, ev_exp[(size_t)bnd], true);
+                row_hi = row_lo;
+            }
+        }
+        rc = finish_all(rc);
+        if (cudaStreamSynchronize(comp) != cudaSuccess || cudaStreamSynchronize(c.hp) != cudaSuccess)
+            rc = rc ? rc : fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        destroy_events();
+        mark("K on the host");
+        if (!rc && !use_stats && n_sid > 0 &&
+            cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail("D2H copy of the statistics failed");
+        return cleanup(rc);
     }
-    for (int k = 0; k < kMaxSlots; ++k) {
-        int r2 = finish(k);
-        if (!rc) rc = r2;
+
+    for (int64_t b0 = 0, sl = 0; b0 < n_sid && !rc; b0 += slice, ++sl) {
+        const int slot = (int)(sl & 1);
+        const int64_t ns = (b0 + slice <= n_sid) ? slice : n_sid - b0;
+        if (c.d_packed[slot].ensure((size_t)slice * ld)) { rc = 1; break; }
+        if (used_pending[slot] && cudaStreamWaitEvent(c.s[1 + slot], used[slot], 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+        if ((rc = upload_records(b0, ns, c.d_packed[slot].p, slot))) break;
+        if (cudaStreamWaitEvent(comp, copied[slot], 0) != cudaSuccess) { rc = fail("event record / wait failed"); break; }
+        pstb_axis sid_ax{nullptr, 0, 1, ns};
+        if (exact)
+            rc = snp_kernel_f64_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                                      (double*)c.d_stats.p + 2 * b0, (double*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, comp);
+        else
+            rc = snp_kernel_slice((const uint8_t*)c.d_packed[slot].p, ld, iid_count, ns, iid_ax, sid_ax, count_a1, mode, a, b, use_stats,
+                                  (double*)c.d_stats.p + 2 * b0, (float*)d_K.p, b0 > 0 ? 1 : 0, c.d_work.p, work_bytes, chunk, low_term, comp,
+                                  (b0 == 0 ? 1 : 0) | (b0 + slice >= n_sid ? 2 : 0), n_sid);
+        if (rc) break;
+        if (cudaEventRecord(used[slot], comp) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
     }
+    if (rc) return cleanup(rc);
+    mark("slices enqueued");
+    if (exact ? pstb_mirror_lower_f64((double*)d_K.p, n_iid, n_iid, comp) : pstb_mirror_lower((float*)d_K.p, n_iid, n_iid, comp)) return cleanup(1);
+    if (cudaStreamSynchronize(comp) != cudaSuccess) return cleanup(fail("kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    mark("kernel finished");
+    rc = drain_rows(0, n_iid, nullptr, false);
+    rc = finish_all(rc);
     mark("K on the host");
     if (!rc && !use_stats && n_sid > 0 &&
         cudaMemcpy(h_stats, c.d_stats.p, (size_t)n_sid * 2 * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)

@@ -1601,6 +1601,12 @@ extern "C" int pstb_snp_kernel_tiles(const uint8_t* d_packed, int64_t ld, int64_
                            0, d_work, work_bytes, chunk, low_term, stream, rank, world, 1);
 }
 
+// what PSTB_LOW_TERM_DEFAULT / _AUTO mean for a kernel of `total_sid` SNPs: callers that split one kernel over several calls (band
+// calls, streamed slices) resolve the mode ONCE and pass the explicit value to every call
+extern "C" int pstb_resolve_low_term(int low_term, int64_t total_sid, int64_t n_iid, int mode) {
+    return resolve_fp8lo(low_term, total_sid, n_iid, mode) ? PSTB_LOW_TERM_FP8 : PSTB_LOW_TERM_FP16;
+}
+
 // One band of a compact-tile kernel: tiles [tile_begin, tile_end) of `rank`'s list for ONE chunk of SNPs (sid.n <= chunk).  The
 // SNP-sharded multi-GPU path runs its last chunk band by band so that the NCCL all-reduce of finished bands overlaps the
 // multiplication of the later ones (`reserve_sms` SMs are left to the collective).  flags bit 0: first band of the chunk (statistics +

@@ -443,3 +443,65 @@ def test_banded_last_chunk_matches_plain_kernel(n, m, chunk, bands, oracle, dev)
             assert rel_fro(Kc, ref) < K_TOL
         else:
             assert not Kc.any()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("n,m,slice_snps", [(1000, 3000, 512), (1300, 900, 256), (2600, 2200, 1024)])
+def test_snp_kernel_host_overlapped_copy_out(pinned, n, m, slice_snps, oracle, dev, monkeypatch):
+    """pstb_snp_kernel_host with the copy-out of K overlapped (compact tiles, band-major tail from the bottom band up, finished row
+    ranges leave while the bands above multiply; PSTB_HOST_KERNEL_OVERLAP=2 forces the path at test sizes) against the plain path
+    (=0) and the oracle: head of several slices + tail, tail only (m = 900: every chunk is a tail chunk), gathered individuals and
+    scattered SNPs, float32 / float64 output, Unit / Beta with missing genotypes, trained statistics."""
+    import ctypes
+    from pysnptools_b200._lib import lib, check, F32, F64, STD_UNIT, STD_BETA
+    rec = (n + 3) // 4
+    packed = oracle.synth_packed(n, 0, m, missing_rate=0.03, seed=n + 1)
+    monkeypatch.setenv("PSTB_KERNEL_SLICE_SNPS", str(slice_snps))
+    held = []
+    if pinned:
+        p_in = lib.pstb_host_alloc(m * rec)
+        held.append(p_in)
+        h_packed = np.ctypeslib.as_array(ctypes.cast(p_in, ctypes.POINTER(ctypes.c_uint8)), shape=(m, rec))
+        h_packed[...] = packed
+    else:
+        h_packed = packed
+    rng = np.random.default_rng(n)
+    ii = np.sort(rng.permutation(n)[: n - 130]).astype(np.int64)[::-1].copy()
+    si = rng.permutation(m)[: m - 77].astype(np.int64)
+
+    def call(mode, ab, iid_idx, sid_idx, code, dtype, use_stats=0, stats=None, chunk=64):
+        ni, ns = (n if iid_idx is None else len(iid_idx)), (m if sid_idx is None else len(sid_idx))
+        if pinned:
+            p_out = lib.pstb_host_alloc(ni * ni * 8)
+            held.append(p_out)
+            K = np.ctypeslib.as_array(ctypes.cast(p_out, ctypes.POINTER(ctypes.c_double if dtype == np.float64 else ctypes.c_float)), shape=(ni, ni))
+        else:
+            K = np.empty((ni, ni), dtype=dtype)
+        K[...] = -7
+        st = np.empty((ns, 2)) if stats is None else stats
+        check(lib.pstb_snp_kernel_host(h_packed.ctypes.data, n, m, None if iid_idx is None else iid_idx.ctypes.data, ni,
+                                       None if sid_idx is None else sid_idx.ctypes.data, ns, 0, mode, ab[0], ab[1], use_stats,
+                                       st.ctypes.data, K.ctypes.data, code, chunk, -1))
+        return K, st
+
+    try:
+        for dtype, code in ((np.float32, F32), (np.float64, F64)):
+            for (mode, args, ab) in ((STD_UNIT, {}, (float("nan"), float("nan"))), (STD_BETA, dict(is_beta=True, a=1, b=25), (1.0, 25.0))):
+                for iid_idx, sid_idx in ((None, None), (ii, si)):
+                    ref, rst = oracle.read_kernel(packed, n, iid_index=iid_idx, sid_index=sid_idx, **args)
+                    monkeypatch.setenv("PSTB_HOST_KERNEL_OVERLAP", "0")
+                    K0, st0 = call(mode, ab, iid_idx, sid_idx, code, dtype)
+                    K0 = K0.copy()
+                    monkeypatch.setenv("PSTB_HOST_KERNEL_OVERLAP", "2")
+                    K1, st1 = call(mode, ab, iid_idx, sid_idx, code, dtype)
+                    assert np.array_equal(K1, K1.T) and np.isfinite(K1).all()
+                    assert rel_fro(K1.astype(np.float64), ref) < K_TOL
+                    np.testing.assert_allclose(st1, rst, rtol=1e-12)
+                    assert np.array_equal(st0, st1)
+                    # the same tiles, the same chunk order; only the rank-one vectors are summed per call instead of in one buffer
+                    assert rel_fro(K1.astype(np.float64), K0.astype(np.float64)) < 2e-7
+                    K2, _ = call(mode, ab, iid_idx, sid_idx, code, dtype, use_stats=1, stats=st1.copy(), chunk=128)
+                    assert rel_fro(K2.astype(np.float64), ref) < K_TOL
+    finally:
+        for ptr in held:
+            lib.pstb_host_free(ptr)

@@ -839,7 +839,7 @@ def run_kernel_e2e(args, torch, dist, dev, _lib, store, K, tiles, n, m, m_local,
         def step():
             _lib.check(lib.pstb_snp_kernel_host(h_pk, n, m_local, None, n, None, m_local, 0, _lib.STD_UNIT, float("nan"), float("nan"), 0,
                                                 h_stats.ctypes.data, h_K, _lib.F32, chunk, dev._LOW_TERM[low_term]))
-        api = "pstb_snp_kernel_host (host-buffer C ABI): pinned packed bytes in, pinned float32 K out"
+        api = "pstb_snp_kernel_host (host-buffer C ABI): pinned packed bytes in, pinned float32 K out (packed slices cross PCIe under the SYRK, finished row ranges of K under its last chunks)"
     else:
         t_pk = torch.from_numpy(h_packed)
         d_tight = torch.empty((m_local, rec), dtype=torch.uint8, device="cuda")

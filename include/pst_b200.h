@@ -230,7 +230,9 @@ int pstb_read_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count
 /* SnpReader._read_kernel on host buffers (snpreader.py:623-668: the loop of read + standardize + val.dot(val.T) + `K +=`):
  * h_packed as for pstb_read_host; h_K: caller-allocated [n_iid, n_iid] float32 / float64 (C order; K is symmetric), both
  * triangles filled; h_stats [n_sid][2] float64 written (read when use_stats).  The packed records are streamed to the GPU in
- * slices overlapped with the tensor-core work; chunk = SNPs per operand-plane chunk (a multiple of 64). */
+ * slices overlapped with the tensor-core work; chunk = SNPs per operand-plane chunk (a multiple of 64).  For large kernels
+ * (n_iid >= 8192, >= 8 chunks) the copy-out of K is overlapped too: the last chunks are multiplied band-major from the bottom
+ * band of tiles up and finished row ranges of K leave while the bands above multiply (PSTB_HOST_KERNEL_OVERLAP=0: plain loop). */
 int pstb_snp_kernel_host(const uint8_t* h_packed, int64_t iid_count, int64_t sid_count,
                          const int64_t* h_iid_idx, int64_t n_iid, const int64_t* h_sid_idx, int64_t n_sid,
                          int count_a1, int mode, double a, double b, int use_stats, double* h_stats,

@@ -938,6 +938,7 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     if (const char* e = getenv("PSTB_HOST_KERNEL_OVERLAP")) overlap_mode = atoi(e);     // 0: off, 1: large kernels, 2: whenever possible (tests)
     bool overlap = !exact && overlap_mode > 0 && nchunks >= 2 && ntiles >= 3 && n_iid >= 512 &&
                    (overlap_mode >= 2 || (n_iid >= 8192 && nchunks >= 8));
+    int64_t tail_chunks = 0;
     if (overlap) {
         // tail length: the copy-out moves n^2 * es bytes at ~50 GB/s (a fresh pageable destination takes them at ~35: first-touch page
         // faults), a chunk multiplies 2 n^2 chunk flop at ~1.45e15/s
@@ -945,6 +946,21 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
         if (T > 24) T = 24;
         while (T > 1 && (size_t)T * (size_t)work_bytes > ((size_t)32 << 30)) --T;
         if (T > nchunks) T = nchunks;
+        // the extra device memory (compact tiles + T workspaces + the tail's records) must fit beside K: shorten the tail, or take the
+        // plain loop, rather than fail
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+            const size_t have = c.d_tiles.cap + c.d_tail_work.cap + c.d_tail_packed.cap;          // cached from an earlier call: reused or released by ensure()
+            const size_t budget = free_b + have > ((size_t)3 << 30) ? free_b + have - ((size_t)3 << 30) : 0;
+            const size_t tiles_b = (size_t)ntiles * 65536 * sizeof(float);
+            while (T >= 1 && tiles_b + (size_t)T * ((size_t)work_bytes + (size_t)chunk * (size_t)ld) > budget) --T;
+            if (T < 1) overlap = false;
+        }
+        tail_chunks = T;
+    }
+    if (overlap) {
+        int64_t T = tail_chunks;
         const int64_t head = (nchunks - T) * chunk;                // SNPs multiplied chunk-major, slice by slice
         const int low = pstb_resolve_low_term(low_term, n_sid, n_iid, mode);
         const size_t n_pad2 = ((size_t)n_iid + 255) / 256 * 256 + 2;

@@ -138,7 +138,8 @@ extern "C" int pstb_numa_bind(int device) {
     CPU_ZERO(&want);
     if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) CPU_ZERO(&allowed);
     int picked = 0;
-    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {       // "0-15,64-79"
+    char* save = nullptr;
+    for (char* tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {       // "0-15,64-79"
         int a = 0, b = 0;
         const int n = sscanf(tok, "%d-%d", &a, &b);
         if (n < 1) continue;

@@ -1,4 +1,4 @@
-# 8-GPU round-end run: the default bench line under torchrun, the host-bandwidth probe, and the cfg2 legs without the NUMA binding (A/B)
+# 8-GPU round-end run (gpurun --gpus 8 -- bash scripts/final_8gpu.sh 8): the default bench line under torchrun, the host-bandwidth probe, and the cfg2 legs without the NUMA binding (A/B)
 N=${1:-8}
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 $RUN bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "rc=$?" >> gpurun_out/bench_${N}gpu.err

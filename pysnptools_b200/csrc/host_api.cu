@@ -942,9 +942,12 @@ static int snp_kernel_host_impl(const uint8_t* h_packed, int64_t iid_count, int6
     if (overlap) {
         // tail length: the copy-out moves n^2 * es bytes at ~50 GB/s (a fresh pageable destination takes them at ~35: first-touch page
         // faults), a chunk multiplies 2 n^2 chunk flop at ~1.45e15/s
-        int64_t T = (int64_t)((double)es * (out_pinned ? 14500.0 : 21000.0) / (double)chunk) + 1;
-        if (T > 24) T = 24;
-        while (T > 1 && (size_t)T * (size_t)work_bytes > ((size_t)32 << 30)) --T;
+        // (a tail 1.7 x as long measured 10 ms SLOWER on cfg3: the band-major launches are shorter and less efficient than whole chunks)
+        double tail_scale = 1.0;
+        if (const char* e = getenv("PSTB_HOST_KERNEL_TAIL")) { const double v = atof(e); if (v >= 0.1 && v <= 8.0) tail_scale = v; }   // tuning experiments
+        int64_t T = (int64_t)(tail_scale * (double)es * (out_pinned ? 14500.0 : 21000.0) / (double)chunk) + 1;
+        if (T > 32) T = 32;
+        while (T > 1 && (size_t)T * (size_t)work_bytes > ((size_t)40 << 30)) --T;
         if (T > nchunks) T = nchunks;
         // the extra device memory (compact tiles + T workspaces + the tail's records) must fit beside K: shorten the tail, or take the
         // plain loop, rather than fail

@@ -133,8 +133,9 @@ struct PlaneParams {
     long long byte_off;
 };
 
-__global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
-    __shared__ unsigned char codes[PT_S][PT_PITCH];
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_planes(const PlaneParams p) {
+    __shared__ __align__(4) unsigned char codes[PT_S][PT_PITCH];
     __shared__ __align__(8) __half lut_hi[PT_S][4], lut_lo[PT_S][4];
     const long long tiles_i = p.n_pad / PT_I;
     const long long ts = blockIdx.x / tiles_i, ti = blockIdx.x % tiles_i;
@@ -142,31 +143,48 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
     const long long n_out = p.iid.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int e = threadIdx.x; e < PT_S * (PT_I / 4); e += blockDim.x) {
-        const int s = e / (PT_I / 4), q = e % (PT_I / 4);
-        uint32_t byte = 0x55u;                                 // padding decodes as "missing" -> 0
-        if (b0 + s < p.sid.n && i0 + 4 * q < n_out) {
+    // the tile's 2-bit codes: 64 SNPs x 64 bytes.  One 32-bit load per 16 individuals where the rows are dense and word-aligned (the
+    // byte loads this replaces left every CTA waiting on 16 dependent-latency loads per thread: stall long_scoreboard 5.3 per issue)
+    const bool word_ok = p.dense && ((reinterpret_cast<uintptr_t>(p.packed) + (uintptr_t)p.byte_off) & 3u) == 0 && (p.ld & 3) == 0;
+    for (int e = threadIdx.x; e < PT_S * (PT_I / 16); e += blockDim.x) {
+        const int s = e / (PT_I / 16), w = e % (PT_I / 16);
+        uint32_t word = 0x55555555u;                           // padding decodes as "missing" -> 0
+        if (b0 + s < p.sid.n && i0 + 16 * w < n_out) {
             long long j = p.sid.at(b0 + s);
             j = j < 0 ? 0 : (j >= p.sid_count ? p.sid_count - 1 : j);
             const uint8_t* src = p.packed + j * p.ld;
-            if (p.dense && i0 + 4 * q + 3 < n_out) {
-                byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+            if (word_ok && i0 + 16 * w + 15 < n_out) {
+                word = __ldg(reinterpret_cast<const uint32_t*>(src + p.byte_off + (i0 >> 2)) + w);
             } else {
-                byte = 0;
+                word = 0;
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int q = 4 * w + qq;
+                    uint32_t byte = 0x55u;
+                    if (i0 + 4 * q < n_out) {
+                        if (p.dense && i0 + 4 * q + 3 < n_out) {
+                            byte = __ldg(src + p.byte_off + (i0 >> 2) + q);
+                        } else {
+                            byte = 0;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    long long a = i0 + 4 * q + t;
-                    uint32_t code = 1u;
-                    if (a < n_out) {
-                        long long i = p.iid.at(a);
-                        i = i < 0 ? 0 : (i >= p.iid_count ? p.iid_count - 1 : i);
-                        code = ((uint32_t)__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u;
+                            for (int t = 0; t < 4; ++t) {
+                                long long a = i0 + 4 * q + t;
+                                uint32_t code = 1u;
+                                if (a < n_out) {
+                                    long long i = p.iid.at(a);
+                                    i = i < 0 ? 0 : (i >= p.iid_count ? p.iid_count - 1 : i);
+                                    code = ((uint32_t)__ldg(src + (i >> 2)) >> (2 * (i & 3))) & 3u;
+                                }
+                                byte |= code << (2 * t);
+                            }
+                        }
                     }
-                    byte |= code << (2 * t);
+                    word |= byte << (8 * qq);
                 }
             }
         }
-        codes[s][q] = (unsigned char)byte;
+        // rows of `codes` are 66 bytes apart: 2-byte aligned
+        *reinterpret_cast<uint16_t*>(&codes[s][4 * w]) = (uint16_t)word;
+        *reinterpret_cast<uint16_t*>(&codes[s][4 * w + 2]) = (uint16_t)(word >> 16);
     }
     const bool fast = p.sc->need_3term == 0u;
     __shared__ __align__(8) __half lut_p2[PT_S][4];
@@ -287,6 +305,14 @@ __global__ void __launch_bounds__(256) k_planes(const PlaneParams p) {
         for (int sn = 0; sn < PT_S; ++sn) acc += lut_u[sn][((uint32_t)codes[sn][r >> 2] >> (2 * (r & 3))) & 3u];
         if (acc != 0.0f && i0 + r < n_out) atomicAdd(p.u + i0 + r, (double)acc);
     }
+}
+
+// 4 resident CTAs per SM at 64 registers (32 bytes of spilled table registers) or 3 at 80: cfg3 chunk 0.31 vs 0.325 ms
+// (PSTB_PLANES_MINB=3: A/B runs)
+static void launch_planes(const PlaneParams& pp, long long ptiles, cudaStream_t st) {
+    static const int minb = [] { const char* e = getenv("PSTB_PLANES_MINB"); const int v = e ? atoi(e) : 0; return v == 3 ? 3 : 4; }();
+    if (minb == 4) k_planes<4><<<(unsigned)ptiles, 256, 0, st>>>(pp);
+    else k_planes<3><<<(unsigned)ptiles, 256, 0, st>>>(pp);
 }
 
 // ---- tcgen05 / TMA primitives ------------------------------------------------------------------------------
@@ -1538,7 +1564,7 @@ static int snp_kernel_impl(const uint8_t* d_packed, int64_t ld, int64_t iid_coun
         pp.dense = dense;
         pp.byte_off = dense ? iid.start / 4 : 0;
         const long long ptiles = (k_pad / PT_S) * (n_pad / PT_I);
-        k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
+        launch_planes(pp, ptiles, st);
         PSTB_AFTER_LAUNCH("k_planes");
         int rc = launch_syrk(hi, lo, n, n_pad, k_pad, d_K, n, (accumulate || c0 > 0) ? 1 : 0, sc, 1.0f, st, rank, world, compact, p2,
                              &d_tiles, &ntiles, pp.fp8lo, tile_begin, tile_end, reserve_sms);
@@ -1783,7 +1809,7 @@ extern "C" int pstb_snp_cross_kernel(const uint8_t* d_packed_r, int64_t ld_r, in
             pp.dense = (iid.idx == nullptr && iid.step == 1 && (iid.start % 4) == 0) ? 1 : 0;
             pp.byte_off = pp.dense ? iid.start / 4 : 0;
             const long long ptiles = (k_pad / PT_S) * (pp.n_pad / PT_I);
-            k_planes<<<(unsigned)ptiles, 256, 0, st>>>(pp);
+            launch_planes(pp, ptiles, st);
             PSTB_AFTER_LAUNCH("k_planes");
         }
         int rc = launch_cross(hi, lo, p2, fp8lo, nr, rows_pad, nc, cols_pad, k_pad, d_out, nc, (accumulate || c0 > 0) ? 1 : 0, sc, st);

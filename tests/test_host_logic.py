@@ -509,3 +509,43 @@ def test_bench_sampled_tile_parity_checker(oracle):
         wrong = stats.copy()
         wrong[0, 0] += 1e-6
         assert not bench.sampled_tile_parity(torch, None, 1, 0, bench._oracle_lib(), store, torch.from_numpy(wrong), n, spec, fetch, blocks)["stats_match_oracle_rtol_1e-12"]
+
+
+@pytest.mark.parametrize("n", [600, 2600, 8192, 50_000, 131_073])
+def test_tile_order_admits_row_complete_bands(n):
+    """The overlapped copy-out of K (pstb_snp_kernel_host) and the overlapped all-reduce cut the rasterised list of lower-triangular
+    tiles into bands and rely on this property of the order: at a cut t where every earlier tile lies in a higher tile row than
+    every later one, the rows of the square K from the first tile row of [t, end) down receive nothing from tiles before t --
+    neither a tile itself nor the transpose of one.  Restated here on the host (pstb_kernel_tile_coords needs no GPU), together
+    with the choice of cuts the library makes, so a change of the rasterisation cannot silently break the early copy-out."""
+    from pysnptools_b200 import _lib
+    lib = _lib.lib
+    cnt = int(lib.pstb_kernel_tile_count(n, 0, 1))
+    blocks = (n + 255) // 256
+    assert cnt == blocks * (blocks + 1) // 2
+    ij = np.zeros((cnt, 2), dtype=np.int32)
+    assert lib.pstb_kernel_tile_coords(n, 0, 1, ij.ctypes.data) == 0
+    I, J = ij[:, 0].astype(np.int64), ij[:, 1].astype(np.int64)
+    assert (J <= I).all() and len({(a, b) for a, b in zip(I.tolist(), J.tolist())}) == cnt       # every lower-triangular tile once
+    sufmin = np.minimum.accumulate(I[::-1])[::-1]
+    premax = np.maximum.accumulate(I)
+    cand = [t for t in range(1, cnt) if premax[t - 1] < sufmin[t]]
+    assert cnt < 4 or len(cand) >= 1, "no cut at all: the copy-out could not overlap anything"
+    want = max(1, cnt // 64)
+    cuts = [0]
+    for t in cand:
+        if t - cuts[-1] >= want:
+            cuts.append(t)
+    cuts.append(cnt)
+    touched_by = np.full(blocks, -1, dtype=np.int64)                 # last band (processed bottom-up) that writes into a row block
+    order = list(range(len(cuts) - 2, -1, -1))
+    for step, b in enumerate(order):
+        t0, t1 = cuts[b], cuts[b + 1]
+        for r in np.unique(np.concatenate([I[t0:t1], J[t0:t1]])):
+            touched_by[r] = step
+    row_hi = blocks
+    for step, b in enumerate(order):
+        row_lo = 0 if b == 0 else int(sufmin[cuts[b]])
+        assert (touched_by[row_lo:row_hi] <= step).all(), (n, b)     # rows declared final after this band are never written later
+        row_hi = min(row_hi, row_lo)
+    assert row_hi == 0
